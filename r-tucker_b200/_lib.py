@@ -1,0 +1,93 @@
+"""ctypes binding of librtucker_b200.so (the C ABI declared in include/rtucker.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librtucker_b200.so")
+
+_lib = None
+
+vp, i32, i64, f32, f64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/rtucker.h one to one
+PROTOTYPES = {
+    "rt_abi_version": (i32, []),
+    "rt_last_error": (C.c_char_p, []),
+    "rt_device_info": (i32, [C.POINTER(i32)] * 3),
+    "rt_rank_filtered": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "rt_target_prob": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "rt_score_rank_ws_bytes": (sz, [i32, i32, i32]),
+    "rt_score_rank_fused": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rt_gather_rows": (i32, [vp, i32, i32, i32, vp, i32, vp, vp]),
+    "rt_scatter_rows_add": (i32, [vp, i32, i32, i32, vp, i32, vp, vp]),
+    "rt_query_ws_bytes": (sz, [i32, i32, i32, i32]),
+    "rt_query_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "rt_query_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "rt_score_bce_ws_bytes": (sz, [i32, i32, i32, i32]),
+    "rt_score_bce_fwd_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp,
+                                   i32, vp, vp]),
+    "rt_gram_ws_bytes": (sz, [i32, i32, i32]),
+    "rt_gram": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp]),
+    "rt_apply": (i32, [vp, i64, i32, i32, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i64),
+                       C.POINTER(i32), C.POINTER(vp), vp]),
+    "rt_small_ws_bytes": (sz, [i32, i32, i32, i32]),
+    "rt_small_prepare": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "rt_rows_times_ainv": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "rt_small_grad": (i32, [vp] * 9 + [f64, vp, i32, i32, i32, i32, i32] + [vp] * 9),
+    "rt_small_norm": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "rt_small_project": (i32, [vp] * 7 + [i32, i32, i32, i32] + [vp] * 9),
+    "rt_core_axpby": (i32, [vp, vp, vp, i32, vp, vp]),
+    "rt_small_retract": (i32, [vp] * 6 + [i32, i32, i32, i32] + [vp] * 9),
+    "rt_eigh_ws_bytes": (sz, [i32]),
+    "rt_eigh": (i32, [vp, i32, vp, vp, vp, vp]),
+}
+
+
+class RTuckerError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library once; raise loudly if it is absent (no CPU fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RTuckerError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). rtucker_b200 has no CPU or PyTorch fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)  # AttributeError if the .so does not export the symbol
+            fn.restype, fn.argtypes = res, args
+        if handle.rt_abi_version() != 1:
+            raise RTuckerError("librtucker_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().rt_last_error().decode(errors="replace")
+        raise RTuckerError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RTuckerError("rtucker_b200 ops need CUDA tensors: there is no CPU path")

@@ -1,0 +1,330 @@
+// Device kernels of the N-independent ("small") stage: generic strided fp64 GEMM with a two-level
+// K index (covers mode products and unfolding Grams of r0 x r1 x r2 tensors without permuting
+// them), SPD factorisation / inverse, small elementwise helpers.  Internal to small.cu.
+#pragma once
+#include "common.h"
+#include <math.h>
+
+namespace rt {
+namespace small {
+
+// C[m,n] = alpha * sum_{k1<K1,k2<K2} A[m,(k1,k2)] B[(k1,k2),n] + beta * C[m,n]      (batched)
+struct Gemm {
+  const double* A; const double* B; double* C;
+  int m, n, K1, K2;
+  int64_t a_m, a_k1, a_k2;
+  int64_t b_k1, b_k2, b_n;
+  int64_t c_m, c_n;
+  int batch; int64_t a_b, b_b, c_b;
+  double alpha, beta;
+  int ksplit, k_per_split;  // split over the flattened K (batch == 1 only)
+  double* partial;          // [ksplit][m][n] when ksplit > 1
+};
+
+constexpr int GT = 64, GK = 16;
+
+__global__ void __launch_bounds__(256)
+gemm64_kernel(Gemm g) {
+  __shared__ double As[GK][GT + 2];
+  __shared__ double Bs[GK][GT + 2];
+  const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
+  int z = blockIdx.z, split = 0, bidx = 0;
+  if (g.ksplit > 1) split = z; else bidx = z;
+  const double* A = g.A + (int64_t)bidx * g.a_b;
+  const double* B = g.B + (int64_t)bidx * g.b_b;
+  const int K = g.K1 * g.K2;
+  const int kbeg = split * g.k_per_split;
+  const int kend = (g.ksplit > 1) ? min(K, kbeg + g.k_per_split) : K;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const bool a_lanes_m = (g.a_m == 1);   // lanes along m when m is the contiguous index
+  const bool b_lanes_n = (g.b_n == 1);
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = kbeg; k0 < kend; k0 += GK) {
+#pragma unroll
+    for (int it = 0; it < (GT * GK) / 256; ++it) {
+      const int e = it * 256 + threadIdx.x;
+      int rr, kk;
+      if (a_lanes_m) { kk = e / GT; rr = e % GT; } else { rr = e / GK; kk = e % GK; }
+      int k = k0 + kk;
+      double v = 0.0;
+      if (m0 + rr < g.m && k < kend) {
+        const int k1 = k / g.K2, k2 = k - k1 * g.K2;
+        v = A[(int64_t)(m0 + rr) * g.a_m + (int64_t)k1 * g.a_k1 + (int64_t)k2 * g.a_k2];
+      }
+      As[kk][rr] = v;
+      int cc, kb;
+      if (b_lanes_n) { kb = e / GT; cc = e % GT; } else { cc = e / GK; kb = e % GK; }
+      k = k0 + kb;
+      v = 0.0;
+      if (n0 + cc < g.n && k < kend) {
+        const int k1 = k / g.K2, k2 = k - k1 * g.K2;
+        v = B[(int64_t)k1 * g.b_k1 + (int64_t)k2 * g.b_k2 + (int64_t)(n0 + cc) * g.b_n];
+      }
+      Bs[kb][cc] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int mm = m0 + ty + 16 * i;
+    if (mm >= g.m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int nn = n0 + tx + 16 * j;
+      if (nn >= g.n) continue;
+      if (g.ksplit > 1) {
+        g.partial[((int64_t)split * g.m + mm) * g.n + nn] = acc[i][j];
+      } else {
+        double* c = g.C + (int64_t)bidx * g.c_b + (int64_t)mm * g.c_m + (int64_t)nn * g.c_n;
+        *c = g.alpha * acc[i][j] + (g.beta != 0.0 ? g.beta * (*c) : 0.0);
+      }
+    }
+  }
+}
+
+__global__ void gemm64_reduce_kernel(Gemm g) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= g.m * g.n) return;
+  const int mm = e / g.n, nn = e - mm * g.n;
+  double s = 0.0;
+  for (int k = 0; k < g.ksplit; ++k) s += g.partial[(int64_t)k * g.m * g.n + e];
+  double* c = g.C + (int64_t)mm * g.c_m + (int64_t)nn * g.c_n;
+  *c = g.alpha * s + (g.beta != 0.0 ? g.beta * (*c) : 0.0);
+}
+
+// ---- elementwise helpers ----------------------------------------------------------------
+__global__ void f32_to_f64_kernel(const float* __restrict__ x, double* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = (double)x[i];
+}
+// y(f32) = a * x(f64), a = a_host * (a_dev ? *a_dev : 1)
+__global__ void f64_to_f32_scaled_kernel(const double* __restrict__ x, float* __restrict__ y, int64_t n,
+                                         double a_host, const double* __restrict__ a_dev) {
+  const double a = a_host * (a_dev ? *a_dev : 1.0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = (float)(a * x[i]);
+}
+// z = a*x + b*y (fp64), scalars = host * optional device factor
+__global__ void axpby64_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                               double* __restrict__ z, int64_t n, double a_host,
+                               const double* __restrict__ a_dev, double b_host,
+                               const double* __restrict__ b_dev) {
+  const double a = a_host * (a_dev ? *a_dev : 1.0);
+  const double b = b_host * (b_dev ? *b_dev : 1.0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    z[i] = a * x[i] + (y ? b * y[i] : 0.0);
+}
+// out(f64) = x32 - lr * y32   (lr from device)
+__global__ void core_minus_lr_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                     const double* __restrict__ lr, double* __restrict__ out, int64_t n) {
+  const double l = *lr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (double)x[i] - l * (double)y[i];
+}
+// dS_g(f32) = d_core + 2*reg*core
+__global__ void grad_core_kernel(const float* __restrict__ d_core, const float* __restrict__ core,
+                                 const double* __restrict__ hyper, float* __restrict__ out, int64_t n) {
+  const float two_reg = (float)(2.0 * hyper[1]);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = fmaf(two_reg, core[i], d_core[i]);
+}
+
+// Deterministic two-stage sum of squares / dot product.  stage 1: grid partials; stage 2: 1 block.
+template <typename TA, typename TB>
+__global__ void dot_partial_kernel(const TA* __restrict__ x, const TB* __restrict__ y, int64_t n,
+                                   double* __restrict__ partial) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s += (double)x[i] * (double)y[i];
+  s = rt::warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+// out[0] = scale * sum(partial) (+ out[0] if accumulate)
+__global__ void dot_final_kernel(const double* __restrict__ partial, int n, double scale,
+                                 double* __restrict__ out, int accumulate) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += partial[i];
+    out[0] = (accumulate ? out[0] : 0.0) + scale * s;
+  }
+}
+
+// C(f32)[m, r] = A(f32)[m, r] . K(f64)[r, r]
+__global__ void __launch_bounds__(256)
+rows_times_mat_kernel(const float* __restrict__ A, int m, int r, const double* __restrict__ K,
+                      float* __restrict__ C) {
+  extern __shared__ float rows[];  // [16][r]
+  const int b0 = blockIdx.x * 16;
+  for (int e = threadIdx.x; e < 16 * r; e += 256) {
+    const int rr = e / r, cc = e - rr * r;
+    rows[e] = (b0 + rr < m) ? A[(int64_t)(b0 + rr) * r + cc] : 0.0f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < r; j += 256) {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+    for (int k = 0; k < r; ++k) {
+      const double kv = K[(int64_t)k * r + j];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fma((double)rows[i * r + k], kv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (b0 + i < m) C[(int64_t)(b0 + i) * r + j] = (float)acc[i];
+  }
+}
+
+// lower -> full symmetric
+__global__ void symmetrize_lower_kernel(double* A, int n) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * n) return;
+  const int i = e / n, j = e - i * n;
+  if (j > i) A[e] = A[(int64_t)j * n + i];
+}
+
+// out = scale_host * (*scale_dev)^pow * in   (pow in {1,2})
+__global__ void scale_mat_kernel(const double* __restrict__ in, double* __restrict__ out, int n,
+                                 double scale_host, const double* __restrict__ scale_dev, int pow2) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  double s = scale_host;
+  if (scale_dev) s *= pow2 ? (*scale_dev) * (*scale_dev) : (*scale_dev);
+  out[e] = s * in[e];
+}
+
+// ---- SPD factorisation: G = L L^T (packed in smem), Linv = L^-1, Ginv = Linv^T Linv ---------
+// One CTA per problem.  Pivots <= tol * max diag are treated as zero (pseudo-inverse on the rest).
+struct SpdProblem {
+  const double* G;   // [n][n]
+  double* L;         // [n][n] lower (may be NULL)
+  double* Linv;      // [n][n] lower (may be NULL)
+  double* Ginv;      // [n][n] (may be NULL)
+  int n;
+};
+struct SpdBatch { SpdProblem p[3]; };
+
+__device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }
+
+__global__ void __launch_bounds__(1024, 1)
+spd_factor_kernel(SpdBatch batch) {
+  extern __shared__ double sm[];
+  const SpdProblem P = batch.p[blockIdx.x];
+  const int n = P.n;
+  if (n <= 0) return;
+  double* Lp = sm;                       // packed lower n(n+1)/2
+  double* col = sm + n * (n + 1) / 2;    // [n] scratch column
+  __shared__ double s_piv, s_maxd;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int e = tid; e < n * (n + 1) / 2; e += nt) {
+    // invert pk: find i with i(i+1)/2 <= e
+    int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+    while (i * (i + 1) / 2 > e) --i;
+    while ((i + 1) * (i + 2) / 2 <= e) ++i;
+    const int j = e - i * (i + 1) / 2;
+    Lp[e] = 0.5 * (P.G[(int64_t)i * n + j] + P.G[(int64_t)j * n + i]);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double m = 0.0;
+    for (int i = 0; i < n; ++i) m = fmax(m, Lp[pk(i, i)]);
+    s_maxd = m;
+  }
+  __syncthreads();
+  const double tol = 1e-13 * s_maxd;
+  for (int k = 0; k < n; ++k) {
+    if (tid == 0) {
+      const double d = Lp[pk(k, k)];
+      s_piv = (d > tol) ? sqrt(d) : 0.0;
+    }
+    __syncthreads();
+    const double piv = s_piv;
+    const double inv = piv > 0.0 ? 1.0 / piv : 0.0;
+    for (int i = k + tid; i < n; i += nt) {
+      const double v = (i == k) ? piv : Lp[pk(i, k)] * inv;
+      Lp[pk(i, k)] = v;
+      col[i] = v;
+    }
+    __syncthreads();
+    // trailing update: rows i > k, cols k < j <= i
+    const int mrem = n - k - 1;
+    const int cnt = mrem * (mrem + 1) / 2;
+    for (int e = tid; e < cnt; e += nt) {
+      int ii = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while (ii * (ii + 1) / 2 > e) --ii;
+      while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+      const int jj = e - ii * (ii + 1) / 2;
+      const int i = k + 1 + ii, j = k + 1 + jj;
+      Lp[pk(i, j)] -= col[i] * col[j];
+    }
+    __syncthreads();
+  }
+  if (P.L) {
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e - i * n;
+      P.L[e] = (j <= i) ? Lp[pk(i, j)] : 0.0;
+    }
+  }
+  if (!P.Linv && !P.Ginv) return;
+  __syncthreads();
+  // in-place inverse of the packed lower triangle (column by column from the right, dtrti2 style)
+  const int sub = tid & 3, row_t = tid >> 2;  // 4 threads per row
+  for (int j = n - 1; j >= 0; --j) {
+    const double d = Lp[pk(j, j)];
+    const double dinv = d > 0.0 ? 1.0 / d : 0.0;
+    for (int i = j + 1 + tid; i < n; i += nt) col[i] = Lp[pk(i, j)];
+    __syncthreads();
+    for (int i0 = j + 1; i0 < n; i0 += nt / 4) {
+      const int i = i0 + row_t;
+      double s = 0.0;
+      if (i < n)
+        for (int k = j + 1 + sub; k <= i; k += 4) s += Lp[pk(i, k)] * col[k];
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (i < n && sub == 0) Lp[pk(i, j)] = -s * dinv;
+    }
+    if (tid == 0) Lp[pk(j, j)] = dinv;
+    __syncthreads();
+  }
+  if (P.Linv) {
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e - i * n;
+      P.Linv[e] = (j <= i) ? Lp[pk(i, j)] : 0.0;
+    }
+  }
+  if (P.Ginv) {
+    for (int e = tid; e < n * n; e += nt) {
+      const int i = e / n, j = e - i * n;
+      double s = 0.0;
+      for (int k = (i > j ? i : j); k < n; ++k) s += Lp[pk(k, i)] * Lp[pk(k, j)];
+      P.Ginv[e] = s;
+    }
+  }
+}
+
+}  // namespace small
+}  // namespace rt

@@ -1,0 +1,318 @@
+// Tall-skinny passes over the N x r factor matrices: Gram products, factor updates, row
+// gather / scatter.  These carry every N-sized piece of the Riemannian projection, momentum
+// transport and retraction (reference: tucker_riemopt grad / project / construct / round as
+// called from src/model/asymmetric/optim.py:86-114 and src/model/symmetric/optim.py:80-107).
+//
+// Bound: HBM for thin ranks; at r ~ 200 the N x r x r products are FP32-FFMA bound
+// (2*N*ra*rb flops per Gram, 2*N*rk*rc per update term).
+#include "common.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// gather / scatter
+// ------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float* __restrict__ table, int rows, int r, int row_begin,
+                                   const int32_t* __restrict__ idx, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int g = idx[b] - row_begin;
+  const bool own = (g >= 0 && g < rows);
+  for (int c = threadIdx.x; c < r; c += blockDim.x)
+    out[(int64_t)b * r + c] = own ? __ldg(table + (int64_t)g * r + c) : 0.0f;
+}
+
+// One CTA per batch row; the first occurrence of an index is the leader and sums its
+// duplicates in ascending batch order, so the result does not depend on scheduling.
+__global__ void scatter_rows_add_kernel(float* __restrict__ table, int rows, int r, int row_begin,
+                                        const int32_t* __restrict__ idx, int B,
+                                        const float* __restrict__ rows_in) {
+  const int b = blockIdx.x;
+  const int me = idx[b];
+  const int g = me - row_begin;
+  if (g < 0 || g >= rows) return;
+  for (int bb = 0; bb < b; ++bb)
+    if (idx[bb] == me) return;  // not the leader (uniform across the CTA)
+  for (int c = threadIdx.x; c < r; c += blockDim.x) {
+    float acc = 0.0f;
+    for (int bb = b; bb < B; ++bb)
+      if (idx[bb] == me) acc += rows_in[(int64_t)bb * r + c];
+    table[(int64_t)g * r + c] += acc;
+  }
+}
+
+__global__ void core_axpby_kernel(const float* __restrict__ x, const double* __restrict__ alpha,
+                                  const float* __restrict__ y, int count, float* __restrict__ out) {
+  const float a = alpha ? (float)(*alpha) : 1.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+    out[i] = a * x[i] + (y ? y[i] : 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------
+// Gram:  out[ra, rb] = A^T B over n rows, fp32 products, fp64 accumulation across row blocks
+// ------------------------------------------------------------------------------------------
+constexpr int GT = 64;       // output tile edge
+constexpr int GKC = 32;      // rows per smem chunk
+constexpr int GFLUSH = 8;    // chunks accumulated in fp32 before flushing to fp64
+
+__global__ void __launch_bounds__(256)
+gram_partial_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+                    int n, int ra, int rb, int tiles_b, int rows_per_split,
+                    double* __restrict__ partial) {
+  __shared__ float As[GKC][GT + 4];
+  __shared__ float Bs[GKC][GT + 4];
+  const int tile = blockIdx.x;
+  const int ta = tile / tiles_b, tb = tile % tiles_b;
+  const int a0 = ta * GT, b0 = tb * GT;
+  const int split = blockIdx.y;
+  const int n0 = split * rows_per_split;
+  const int n1 = min(n, n0 + rows_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+
+  double acc64[4][4];
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc64[i][j] = 0.0; acc[i][j] = 0.0f; }
+
+  int chunk = 0;
+  for (int row = n0; row < n1; row += GKC, ++chunk) {
+    // cooperative load: 32 rows x 64 cols per operand, 8 elements per thread
+#pragma unroll
+    for (int it = 0; it < (GKC * GT) / 256; ++it) {
+      const int e = it * 256 + threadIdx.x;
+      const int rr = e / GT, cc = e % GT;
+      const int gr = row + rr;
+      float va = 0.0f, vb = 0.0f;
+      if (gr < n1) {
+        if (a0 + cc < ra) va = __ldg(A + (int64_t)gr * lda + a0 + cc);
+        if (b0 + cc < rb) vb = __ldg(B + (int64_t)gr * ldb + b0 + cc);
+      }
+      As[rr][cc] = va;
+      Bs[rr][cc] = vb;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < GKC; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w};
+      const float bq[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bq[j], acc[i][j]);
+    }
+    __syncthreads();
+    if ((chunk % GFLUSH) == GFLUSH - 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc64[i][j] += (double)acc[i][j]; acc[i][j] = 0.0f; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gi = a0 + ty * 4 + i, gj = b0 + tx * 4 + j;
+      if (gi < ra && gj < rb)
+        partial[((int64_t)split * ra + gi) * rb + gj] = acc64[i][j] + (double)acc[i][j];
+    }
+}
+
+__global__ void gram_reduce_kernel(const double* __restrict__ partial, int nsplit, int count,
+                                   double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double s = 0.0;
+  for (int k = 0; k < nsplit; ++k) s += partial[(int64_t)k * count + i];  // fixed order
+  out[i] = s;
+}
+
+struct GramPlan {
+  int tiles_a, tiles_b, nsplit, rows_per_split;
+};
+
+GramPlan gram_plan(int n, int ra, int rb) {
+  GramPlan p;
+  p.tiles_a = rt::cdiv(ra, GT);
+  p.tiles_b = rt::cdiv(rb, GT);
+  const int tiles = p.tiles_a * p.tiles_b;
+  const int target = 4 * 148;  // ~4 CTAs per SM in flight
+  int nsplit = rt::cdiv(target, tiles);
+  const int max_split = rt::cdiv(n, 4 * GKC);
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  int rows = rt::cdiv(n, nsplit);
+  rows = rt::cdiv(rows, GKC) * GKC;
+  p.rows_per_split = rows;
+  p.nsplit = rt::cdiv(n, rows);
+  if (p.nsplit < 1) p.nsplit = 1;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// Apply:  Y = a0*X0 + sum_k X_k K_k
+// ------------------------------------------------------------------------------------------
+constexpr int AT_M = 128;  // rows per tile
+constexpr int AT_N = 64;   // cols per tile
+constexpr int AT_K = 16;
+constexpr int kMaxTerms = 4;
+
+struct ApplyArgs {
+  const float* X[kMaxTerms];
+  int64_t ldx[kMaxTerms];
+  int rk[kMaxTerms];
+  const double* K[kMaxTerms];
+  int nk;
+};
+
+__global__ void __launch_bounds__(256)
+apply_kernel(float* __restrict__ Y, int64_t ldy, int n, int rc, const float* __restrict__ X0,
+             int64_t ldx0, const double* __restrict__ a0_dev, ApplyArgs args) {
+  __shared__ float Xs[AT_K][AT_M + 4];  // transposed: [k][row]
+  __shared__ float Ks[AT_K][AT_N + 4];
+  const int row0 = blockIdx.x * AT_M;
+  const int col0 = blockIdx.y * AT_N;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // ty: 8 rows each, tx: 4 cols each
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  for (int t = 0; t < args.nk; ++t) {
+    const float* __restrict__ X = args.X[t];
+    const double* __restrict__ K = args.K[t];
+    const int64_t ldx = args.ldx[t];
+    const int rk = args.rk[t];
+    for (int k0 = 0; k0 < rk; k0 += AT_K) {
+      // X tile: 128 rows x 16 k  -> 8 per thread; lanes run along k (contiguous in memory)
+#pragma unroll
+      for (int it = 0; it < (AT_M * AT_K) / 256; ++it) {
+        const int e = it * 256 + threadIdx.x;
+        const int rr = e / AT_K, kk = e % AT_K;
+        const int gr = row0 + rr, gk = k0 + kk;
+        Xs[kk][rr] = (gr < n && gk < rk) ? __ldg(X + (int64_t)gr * ldx + gk) : 0.0f;
+      }
+#pragma unroll
+      for (int it = 0; it < (AT_K * AT_N) / 256; ++it) {
+        const int e = it * 256 + threadIdx.x;
+        const int kk = e / AT_N, cc = e % AT_N;
+        const int gk = k0 + kk, gc = col0 + cc;
+        Ks[kk][cc] = (gk < rk && gc < rc) ? (float)__ldg(K + (int64_t)gk * rc + gc) : 0.0f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < AT_K; ++kk) {
+        const float4 x0 = *reinterpret_cast<const float4*>(&Xs[kk][ty * 8]);
+        const float4 x1 = *reinterpret_cast<const float4*>(&Xs[kk][ty * 8 + 4]);
+        const float4 kv = *reinterpret_cast<const float4*>(&Ks[kk][tx * 4]);
+        const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const float kb[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], kb[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  const float a0 = a0_dev ? (float)(*a0_dev) : 1.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gr = row0 + ty * 8 + i;
+    if (gr >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = col0 + tx * 4 + j;
+      if (gc >= rc) continue;
+      float v = acc[i][j];
+      if (X0) v = fmaf(a0, X0[(int64_t)gr * ldx0 + gc], v);
+      Y[(int64_t)gr * ldy + gc] = v;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int rt_gather_rows(const float* table, int rows, int r, int row_begin, const int32_t* idx,
+                              int B, float* out, void* stream) {
+  RT_REQUIRE(B >= 0 && r > 0 && rows >= 0, "rt_gather_rows: bad shape");
+  if (B == 0) return 0;
+  gather_rows_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(table, rows, r, row_begin, idx, out);
+  RT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rt_scatter_rows_add(float* table, int rows, int r, int row_begin, const int32_t* idx,
+                                   int B, const float* rows_in, void* stream) {
+  RT_REQUIRE(B >= 0 && r > 0 && rows >= 0, "rt_scatter_rows_add: bad shape");
+  if (B == 0 || rows == 0) return 0;
+  scatter_rows_add_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(table, rows, r, row_begin, idx, B,
+                                                               rows_in);
+  RT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rt_core_axpby(const float* dS_g, const double* alpha_dev, const float* pS_beta,
+                             int count, float* dS_dir, void* stream) {
+  RT_REQUIRE(count > 0, "rt_core_axpby: bad count");
+  int blocks = rt::cdiv(count, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  core_axpby_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dS_g, alpha_dev, pS_beta, count,
+                                                              dS_dir);
+  RT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t rt_gram_ws_bytes(int n, int ra, int rb) {
+  if (n <= 0 || ra <= 0 || rb <= 0) return 0;
+  GramPlan p = gram_plan(n, ra, rb);
+  return (size_t)p.nsplit * ra * rb * sizeof(double);
+}
+
+extern "C" int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb, int n, int ra,
+                       int rb, double* out, void* ws, void* stream) {
+  RT_REQUIRE(n >= 0 && ra > 0 && rb > 0 && lda >= ra && ldb >= rb, "rt_gram: bad shape n=%d ra=%d rb=%d",
+             n, ra, rb);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) {
+    RT_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * ra * rb, s));
+    return 0;
+  }
+  RT_REQUIRE(ws != nullptr, "rt_gram: workspace is NULL");
+  GramPlan p = gram_plan(n, ra, rb);
+  dim3 grid(p.tiles_a * p.tiles_b, p.nsplit);
+  gram_partial_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, n, ra, rb, p.tiles_b, p.rows_per_split,
+                                           (double*)ws);
+  RT_LAUNCH_CHECK();
+  const int count = ra * rb;
+  gram_reduce_kernel<<<rt::cdiv(count, 256), 256, 0, s>>>((const double*)ws, p.nsplit, count, out);
+  RT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rt_apply(float* Y, int64_t ldy, int n, int rc, const float* X0, int64_t ldx0,
+                        const double* a0_dev, int nk, const float* const* X_host,
+                        const int64_t* ldx_host, const int* rk_host, const double* const* K_host,
+                        void* stream) {
+  RT_REQUIRE(n >= 0 && rc > 0 && ldy >= rc, "rt_apply: bad shape n=%d rc=%d", n, rc);
+  RT_REQUIRE(nk >= 0 && nk <= kMaxTerms, "rt_apply: nk=%d out of range (max %d)", nk, kMaxTerms);
+  RT_REQUIRE(X0 != nullptr || nk > 0, "rt_apply: nothing to compute");
+  if (n == 0) return 0;
+  ApplyArgs a;
+  a.nk = nk;
+  for (int k = 0; k < kMaxTerms; ++k) {
+    a.X[k] = k < nk ? X_host[k] : nullptr;
+    a.ldx[k] = k < nk ? ldx_host[k] : 0;
+    a.rk[k] = k < nk ? rk_host[k] : 0;
+    a.K[k] = k < nk ? K_host[k] : nullptr;
+    if (k < nk) RT_REQUIRE(a.X[k] != Y, "rt_apply: Y may alias X0 only");
+  }
+  dim3 grid(rt::cdiv(n, AT_M), rt::cdiv(rc, AT_N));
+  apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, ldy, n, rc, X0, ldx0, a0_dev, a);
+  RT_LAUNCH_CHECK();
+  return 0;
+}

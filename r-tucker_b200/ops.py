@@ -1,0 +1,249 @@
+"""Thin tensor-level wrappers over the C ABI (include/rtucker.h).  PyTorch supplies device memory
+and the current CUDA stream only; all arithmetic happens in librtucker_b200.so.
+"""
+import ctypes as C
+
+import torch
+
+from ._lib import check, lib, ptr, require_cuda, stream_ptr
+
+f32, f64, i32 = torch.float32, torch.float64, torch.int32
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _c(t, dtype):
+    if t.dtype != dtype or not t.is_contiguous():
+        raise TypeError(f"expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t
+
+
+# ---------------------------------------------------------------- (d) ranking
+def rank_filtered(P, target, flt_off, flt_idx):
+    """Counts (greater, equal, equal_before) per row of the dense prediction matrix ``P`` [B,N]
+    -- see rt_rank_filtered in include/rtucker.h (filter_predictions + metrics of the reference)."""
+    require_cuda(P, target, flt_off, flt_idx)
+    assert P.dim() == 2 and P.dtype == f32 and P.stride(1) == 1
+    B, N = P.shape
+    out = torch.empty(3, max(B, 1), dtype=i32, device=P.device)
+    check(lib().rt_rank_filtered(ptr(P), P.stride(0), B, N, ptr(_c(target, i32)), ptr(_c(flt_off, i32)),
+                                 ptr(_c(flt_idx, i32)), ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                                 stream_ptr()), "rt_rank_filtered")
+    return out[0, :B], out[1, :B], out[2, :B]
+
+
+def target_prob(q, O, target, n_begin=0):
+    require_cuda(q, O, target)
+    B, r2 = q.shape
+    out = torch.empty(B, dtype=f32, device=q.device)
+    check(lib().rt_target_prob(ptr(_c(q, f32)), ptr(_c(O, f32)), B, r2, n_begin, O.shape[0],
+                               ptr(_c(target, i32)), ptr(out), stream_ptr()), "rt_target_prob")
+    return out
+
+
+def score_rank_fused(q, O, target, p_target, flt_off, flt_idx, n_begin=0, want_bce=True):
+    require_cuda(q, O, target, p_target, flt_off, flt_idx)
+    B, r2 = q.shape
+    n_local = O.shape[0]
+    out = torch.empty(3, B, dtype=i32, device=q.device)
+    bce = torch.zeros(1, dtype=f64, device=q.device) if want_bce else None
+    ws = _ws(lib().rt_score_rank_ws_bytes(B, n_local, r2), q.device)
+    check(lib().rt_score_rank_fused(ptr(_c(q, f32)), ptr(_c(O, f32)), B, r2, n_begin, n_local,
+                                    ptr(_c(target, i32)), ptr(_c(p_target, f32)), ptr(_c(flt_off, i32)),
+                                    ptr(_c(flt_idx, i32)), ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                                    ptr(bce), ptr(ws), stream_ptr()), "rt_score_rank_fused")
+    return out[0], out[1], out[2], bce
+
+
+# ---------------------------------------------------------------- (a) query contraction
+def gather_rows(table, idx, row_begin=0):
+    require_cuda(table, idx)
+    rows, r = table.shape
+    B = idx.shape[0]
+    out = torch.empty(B, r, dtype=f32, device=table.device)
+    check(lib().rt_gather_rows(ptr(_c(table, f32)), rows, r, row_begin, ptr(_c(idx, i32)), B, ptr(out),
+                               stream_ptr()), "rt_gather_rows")
+    return out
+
+
+def scatter_rows_add(table, idx, rows_in, row_begin=0):
+    require_cuda(table, idx, rows_in)
+    rows, r = table.shape
+    check(lib().rt_scatter_rows_add(ptr(_c(table, f32)), rows, r, row_begin, ptr(_c(idx, i32)),
+                                    idx.shape[0], ptr(_c(rows_in, f32)), stream_ptr()),
+          "rt_scatter_rows_add")
+    return table
+
+
+def query_fwd(core, r_rows, s_rows, ws=None):
+    require_cuda(core, r_rows, s_rows)
+    r0, r1, r2 = core.shape
+    B = r_rows.shape[0]
+    q = torch.empty(B, r2, dtype=f32, device=core.device)
+    ws = ws if ws is not None else _ws(lib().rt_query_ws_bytes(B, r0, r1, r2), core.device)
+    check(lib().rt_query_fwd(ptr(_c(core, f32)), ptr(_c(r_rows, f32)), ptr(_c(s_rows, f32)), B, r0, r1, r2,
+                             ptr(q), ptr(ws), stream_ptr()), "rt_query_fwd")
+    return q
+
+
+def query_bwd(core, r_rows, s_rows, H, ws=None):
+    require_cuda(core, r_rows, s_rows, H)
+    r0, r1, r2 = core.shape
+    B = r_rows.shape[0]
+    d_core = torch.empty_like(core)
+    ds_rows = torch.empty(B, r1, dtype=f32, device=core.device)
+    dr_rows = torch.empty(B, r0, dtype=f32, device=core.device)
+    ws = ws if ws is not None else _ws(lib().rt_query_ws_bytes(B, r0, r1, r2), core.device)
+    check(lib().rt_query_bwd(ptr(_c(core, f32)), ptr(_c(r_rows, f32)), ptr(_c(s_rows, f32)), ptr(_c(H, f32)),
+                             B, r0, r1, r2, ptr(d_core), ptr(ds_rows), ptr(dr_rows), ptr(ws),
+                             stream_ptr()), "rt_query_bwd")
+    return d_core, ds_rows, dr_rows
+
+
+# ---------------------------------------------------------------- (b) fused score + BCE + backward
+def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None, b_total=None,
+                      n_begin=0, variant=0, out=None, ws=None):
+    """Returns (loss_sum[1] f64 -- un-normalised, H [B,r2], dO [n_local,r2])."""
+    require_cuda(q, qp, O, tgt_off, tgt_idx)
+    B, r2 = q.shape
+    n_local = O.shape[0]
+    n_total = n_local if n_total is None else n_total
+    b_total = B if b_total is None else b_total
+    dev = q.device
+    if out is None:
+        loss = torch.empty(1, dtype=f64, device=dev)
+        H = torch.empty(B, r2, dtype=f32, device=dev)
+        dO = torch.empty(n_local, r2, dtype=f32, device=dev)
+    else:
+        loss, H, dO = out
+    ws = ws if ws is not None else _ws(lib().rt_score_bce_ws_bytes(B, n_local, r2, variant), dev)
+    check(lib().rt_score_bce_fwd_bwd(ptr(_c(q, f32)), ptr(_c(qp, f32)), ptr(_c(O, f32)), B, r2, n_begin,
+                                     n_local, n_total, b_total, ptr(_c(tgt_off, i32)), ptr(_c(tgt_idx, i32)),
+                                     float(label_smoothing), ptr(loss), ptr(H), ptr(dO), variant, ptr(ws),
+                                     stream_ptr()), "rt_score_bce_fwd_bwd")
+    return loss, H, dO
+
+
+# ---------------------------------------------------------------- (c) tall-skinny
+def gram(A, B, out=None, ws=None):
+    """out[ra,rb] (f64) = A^T B over the rows."""
+    require_cuda(A, B)
+    n, ra = A.shape
+    rb = B.shape[1]
+    assert B.shape[0] == n and A.stride(1) == 1 and B.stride(1) == 1
+    out = out if out is not None else torch.empty(ra, rb, dtype=f64, device=A.device)
+    ws = ws if ws is not None else _ws(lib().rt_gram_ws_bytes(n, ra, rb), A.device)
+    check(lib().rt_gram(ptr(A), A.stride(0), ptr(B), B.stride(0), n, ra, rb, ptr(_c(out, f64)), ptr(ws),
+                        stream_ptr()), "rt_gram")
+    return out
+
+
+def apply(Y, X0, a0_dev, terms):
+    """Y = a0*X0 + sum_k X_k @ K_k;  terms = [(X_k f32 [n,rk], K_k f64 [rk,rc]), ...]."""
+    require_cuda(Y, X0, a0_dev, *[t for pair in terms for t in pair])
+    n, rc = Y.shape
+    nk = len(terms)
+    Xp = (C.c_void_p * max(nk, 1))(*[x.data_ptr() for x, _ in terms])
+    ld = (C.c_int64 * max(nk, 1))(*[x.stride(0) for x, _ in terms])
+    rk = (C.c_int * max(nk, 1))(*[x.shape[1] for x, _ in terms])
+    Kp = (C.c_void_p * max(nk, 1))(*[_c(k, f64).data_ptr() for _, k in terms])
+    for x, k in terms:
+        assert x.dtype == f32 and x.stride(1) == 1 and k.shape == (x.shape[1], rc) and x.shape[0] == n
+    check(lib().rt_apply(ptr(Y), Y.stride(0), n, rc, ptr(X0), X0.stride(0) if X0 is not None else 0,
+                         ptr(a0_dev), nk, Xp, ld, rk, Kp, stream_ptr()), "rt_apply")
+    return Y
+
+
+def core_axpby(dS_g, alpha_dev, pS_beta, out=None):
+    require_cuda(dS_g, alpha_dev, pS_beta)
+    out = out if out is not None else torch.empty_like(dS_g)
+    check(lib().rt_core_axpby(ptr(_c(dS_g, f32)), ptr(alpha_dev), ptr(pS_beta), dS_g.numel(), ptr(out),
+                              stream_ptr()), "rt_core_axpby")
+    return out
+
+
+# ---------------------------------------------------------------- (c) small stage
+class SmallStage:
+    """Owns the fp64 workspace of the N-independent stage for fixed ranks (r0,r1,r2)."""
+
+    def __init__(self, rank, B, sym, device):
+        self.r0, self.r1, self.r2 = (int(x) for x in rank)
+        self.B, self.sym, self.device = int(B), int(bool(sym)), device
+        self.ws = _ws(lib().rt_small_ws_bytes(self.r0, self.r1, self.r2, self.B), device)
+
+    def _r(self):
+        return self.r0, self.r1, self.r2
+
+    def prepare(self, core):
+        check(lib().rt_small_prepare(ptr(_c(core, f32)), *self._r(), self.sym, ptr(self.ws), stream_ptr()),
+              "rt_small_prepare")
+
+    def rows_times_ainv(self, A, mode):
+        out = torch.empty_like(A)
+        check(lib().rt_rows_times_ainv(ptr(_c(A, f32)), A.shape[0], mode, *self._r(), ptr(out), ptr(self.ws),
+                                       stream_ptr()), "rt_rows_times_ainv")
+        return out
+
+    def grad(self, core, d_core, qp, H, r_rows, s_rows, dr_rows, ds_rows, bce_sum, inv_count, hyper):
+        dev, (r0, r1, r2) = self.device, self._r()
+        B = H.shape[0]
+        dS_g = torch.empty_like(core)
+        loss = torch.empty(1, dtype=f64, device=dev)
+        drA = torch.empty(B, r0, dtype=f32, device=dev)
+        dsA = torch.empty(B, r1, dtype=f32, device=dev)
+        P_R = torch.empty(r0, r0, dtype=f64, device=dev)
+        P_S = torch.empty(r1, r1, dtype=f64, device=dev)
+        P_O = P_S if self.sym else torch.empty(r2, r2, dtype=f64, device=dev)
+        check(lib().rt_small_grad(ptr(core), ptr(d_core), ptr(qp), ptr(H), ptr(r_rows), ptr(s_rows),
+                                  ptr(dr_rows), ptr(ds_rows), ptr(bce_sum), float(inv_count), ptr(hyper), B,
+                                  r0, r1, r2, self.sym, ptr(dS_g), ptr(loss), ptr(drA), ptr(dsA), ptr(P_R),
+                                  ptr(P_S), ptr(P_O), ptr(self.ws), stream_ptr()), "rt_small_grad")
+        return dS_g, loss, drA, dsA, P_R, P_S, P_O
+
+    def norm(self, dS_g, gram_R, gram_S, gram_O, hyper):
+        out = torch.empty(2, dtype=f64, device=self.device)
+        check(lib().rt_small_norm(ptr(dS_g), ptr(gram_R), ptr(gram_S), ptr(gram_O), ptr(hyper), *self._r(),
+                                  self.sym, ptr(out[0:1]), ptr(out[1:2]), ptr(self.ws), stream_ptr()),
+              "rt_small_norm")
+        return out[0:1], out[1:2]
+
+    def project(self, core, core_old, dS_old, M_R, M_S, M_O, hyper):
+        dev, (r0, r1, r2) = self.device, self._r()
+        pS = torch.empty_like(core)
+        K = [torch.empty(2 * r, r, dtype=f64, device=dev) for r in (r0, r1, r2)]
+        L = [torch.empty(r, r, dtype=f64, device=dev) for r in (r0, r1, r2)]
+        if self.sym:
+            K[2], L[2] = K[1], L[1]
+        check(lib().rt_small_project(ptr(core), ptr(core_old), ptr(dS_old), ptr(M_R), ptr(M_S), ptr(M_O),
+                                     ptr(hyper), r0, r1, r2, self.sym, ptr(pS), ptr(K[0]), ptr(K[1]),
+                                     ptr(K[2]), ptr(L[0]), ptr(L[1]), ptr(L[2]), ptr(self.ws), stream_ptr()),
+              "rt_small_project")
+        return pS, K, L
+
+    def retract(self, core, dS_dir, gram_R, gram_S, gram_O, hyper):
+        dev, (r0, r1, r2) = self.device, self._r()
+        core_new = torch.empty_like(core)
+        Z1 = [torch.empty(r, r, dtype=f64, device=dev) for r in (r0, r1, r2)]
+        Z2 = [torch.empty(r, r, dtype=f64, device=dev) for r in (r0, r1, r2)]
+        if self.sym:
+            Z1[2], Z2[2] = Z1[1], Z2[1]
+        check(lib().rt_small_retract(ptr(core), ptr(dS_dir), ptr(gram_R), ptr(gram_S), ptr(gram_O),
+                                     ptr(hyper), r0, r1, r2, self.sym, ptr(core_new), ptr(Z1[0]), ptr(Z2[0]),
+                                     ptr(Z1[1]), ptr(Z2[1]), ptr(Z1[2]), ptr(Z2[2]), ptr(self.ws),
+                                     stream_ptr()), "rt_small_retract")
+        return core_new, Z1, Z2
+
+
+def eigh(A):
+    """Eigen-decomposition of a symmetric fp64 matrix on the device (block Jacobi); returns
+    (w descending, V with eigenvectors in columns).  A is not modified."""
+    require_cuda(A)
+    n = A.shape[0]
+    A = A.clone().contiguous()
+    w = torch.empty(n, dtype=f64, device=A.device)
+    V = torch.empty(n, n, dtype=f64, device=A.device)
+    ws = _ws(lib().rt_eigh_ws_bytes(n), A.device)
+    check(lib().rt_eigh(ptr(A), n, ptr(w), ptr(V), ptr(ws), stream_ptr()), "rt_eigh")
+    return w, V

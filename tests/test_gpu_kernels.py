@@ -1,0 +1,270 @@
+"""GPU parity tests, one per kernel family, through the C ABI, against the CPU oracle.
+
+Tolerances: integer outputs bit-exact; fp32 kernels 1e-5 norm-wise relative vs the fp64 oracle
+(north_star: "loss, gradients and retracted factors within 1e-5 relative in fp32").
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / max(float(b.norm()), 1e-300))
+
+
+def make_csr(B, N, gen, max_per_row=5, dense_row=None):
+    counts = torch.randint(1, max_per_row + 1, (B,), generator=gen)
+    if dense_row is not None:
+        counts[dense_row] = min(N, 70)
+    off = torch.zeros(B + 1, dtype=torch.int64)
+    off[1:] = counts.cumsum(0)
+    idx = torch.cat([torch.randperm(N, generator=gen)[:c] for c in counts.tolist()])
+    return off.int(), idx.int()
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N", [(7, 1000), (33, 40943), (4, 17), (512, 14951)])
+def test_rank_filtered_bitexact(cuda_device, B, N):
+    import ranking as oracle_rank
+    from rtucker_b200 import ops
+    g = torch.Generator().manual_seed(B * 7 + N)
+    P = torch.sigmoid(3 * torch.randn(B, N, generator=g))
+    # adversarial ties: quantise some rows so many exact duplicates exist, saturate others
+    P[0] = torch.round(P[0] * 16) / 16
+    if B > 2:
+        P[1] = 1.0
+        P[2] = 0.0
+    target = torch.randint(0, N, (B,), generator=g).int()
+    off, idx = make_csr(B, N, g, max_per_row=min(9, N), dense_row=0 if N > 100 else None)
+    # most filter lists contain the target (as in the reference's eval set), some do not
+    for b in range(0, B, 2):
+        idx[off[b]] = target[b]
+    eg, ee, eb = oracle_rank.filtered_counts(P.numpy(), target.numpy(), off.numpy(), idx.numpy())
+    dev = cuda_device
+    cg, ce, cb = ops.rank_filtered(P.to(dev), target.to(dev), off.to(dev), idx.to(dev))
+    assert np.array_equal(cg.cpu().numpy(), eg)
+    assert np.array_equal(ce.cpu().numpy(), ee)
+    assert np.array_equal(cb.cpu().numpy(), eb)
+
+
+def test_rank_filtered_strided_rows(cuda_device):
+    import ranking as oracle_rank
+    from rtucker_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, N, ld = 9, 777, 1001
+    buf = torch.rand(B, ld, generator=g)
+    P = buf[:, :N]
+    target = torch.randint(0, N, (B,), generator=g).int()
+    off, idx = make_csr(B, N, g)
+    eg, ee, eb = oracle_rank.filtered_counts(P.numpy(), target.numpy(), off.numpy(), idx.numpy())
+    dev = cuda_device
+    cg, ce, cb = ops.rank_filtered(buf.to(dev)[:, :N], target.to(dev), off.to(dev), idx.to(dev))
+    assert np.array_equal(cg.cpu().numpy(), eg) and np.array_equal(ce.cpu().numpy(), ee)
+    assert np.array_equal(cb.cpu().numpy(), eb)
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,ra,rb", [(1000, 20, 20), (4097, 200, 200), (333, 10, 20), (22, 10, 10), (70000, 200, 64)])
+def test_gram(cuda_device, n, ra, rb):
+    from rtucker_b200 import ops
+    g = torch.Generator().manual_seed(n + ra)
+    A = torch.randn(n, ra, generator=g)
+    Bm = torch.randn(n, rb, generator=g)
+    ref = A.double().T @ Bm.double()
+    out = ops.gram(A.to(cuda_device), Bm.to(cuda_device))
+    assert relerr(out, ref) < 1e-6
+
+
+@pytest.mark.parametrize("n,rc,rks", [(1000, 20, [20]), (4097, 200, [200, 200, 200]), (130, 10, [10, 10]), (22, 10, [])])
+def test_apply(cuda_device, n, rc, rks):
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(n + rc)
+    X0 = torch.randn(n, rc, generator=g)
+    a0 = torch.tensor([0.37], dtype=torch.float64)
+    terms = [(torch.randn(n, rk, generator=g), torch.randn(rk, rc, generator=g, dtype=torch.float64)) for rk in rks]
+    ref = a0 * X0.double() + sum((x.double() @ k for x, k in terms), torch.zeros(n, rc, dtype=torch.float64))
+    Y = torch.empty(n, rc, device=dev)
+    ops.apply(Y, X0.to(dev), a0.to(dev), [(x.to(dev), k.to(dev)) for x, k in terms])
+    assert relerr(Y, ref) < 1e-6
+    # in-place on X0, no scalar
+    if rks:
+        Y2 = X0.to(dev).clone()
+        ops.apply(Y2, Y2, None, [(x.to(dev), k.to(dev)) for x, k in terms])
+        ref2 = X0.double() + sum(x.double() @ k for x, k in terms)
+        assert relerr(Y2, ref2) < 1e-6
+
+
+def test_gather_scatter(cuda_device):
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(1)
+    N, r, B = 300, 20, 64
+    table = torch.randn(N, r, generator=g)
+    idx = torch.randint(0, 40, (B,), generator=g).int()  # many duplicates
+    rows = ops.gather_rows(table.to(dev), idx.to(dev))
+    assert torch.equal(rows.cpu(), table[idx.long()])
+    # shard-aware: rows outside [row_begin, row_begin+rows) come back as zeros
+    part = ops.gather_rows(table[10:30].contiguous().to(dev), idx.to(dev), row_begin=10)
+    own = (idx >= 10) & (idx < 30)
+    assert torch.equal(part.cpu()[own], table[idx.long()][own]) and float(part.cpu()[~own].abs().sum()) == 0
+    upd = torch.randn(B, r, generator=g)
+    out = ops.scatter_rows_add(torch.zeros(N, r, device=dev), idx.to(dev), upd.to(dev))
+    ref = torch.zeros(N, r, dtype=torch.float64).index_add_(0, idx.long(), upd.double())
+    assert relerr(out, ref) < 1e-6
+    out2 = ops.scatter_rows_add(torch.zeros(N, r, device=dev), idx.to(dev), upd.to(dev))
+    assert torch.equal(out, out2)  # deterministic
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,rank", [(512, (10, 200, 200)), (512, (200, 20, 20)), (37, (3, 5, 7)), (64, (16, 64, 64))])
+def test_query_fwd_bwd(cuda_device, B, rank):
+    import analytic as A
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(sum(rank) + B)
+    core = torch.randn(*rank, generator=g)
+    r_rows = torch.randn(B, rank[0], generator=g)
+    s_rows = torch.randn(B, rank[1], generator=g)
+    H = torch.randn(B, rank[2], generator=g)
+    ar = torch.arange(B)
+    q_ref = A.query_fwd(core.double(), r_rows.double(), s_rows.double(), ar, ar)
+    dc_ref, ds_ref, dr_ref = A.query_bwd(core.double(), r_rows.double(), s_rows.double(), ar, ar, H.double())
+    q = ops.query_fwd(core.to(dev), r_rows.to(dev), s_rows.to(dev))
+    dc, ds, dr = ops.query_bwd(core.to(dev), r_rows.to(dev), s_rows.to(dev), H.to(dev))
+    assert relerr(q, q_ref) < 2e-6
+    assert relerr(dc, dc_ref) < 2e-6
+    assert relerr(ds, ds_ref) < 2e-6
+    assert relerr(dr, dr_ref) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,r2,ls,scale", [
+    (64, 1000, 20, 0.1, 1.0), (100, 777, 200, 0.1, 1.0), (512, 4099, 100, 0.0, 1.0),
+    (33, 129, 10, 0.1, 40.0),   # saturating logits: log clamp at -100 and zero gradient
+    (512, 14541, 20, 0.1, 3.0),
+])
+def test_score_bce_fwd_bwd(cuda_device, B, N, r2, ls, scale):
+    import analytic as A
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(B + N + r2)
+    q = scale * torch.randn(B, r2, generator=g) / r2 ** 0.5
+    O = torch.randn(N, r2, generator=g)
+    off, idx = make_csr(B, N, g, max_per_row=6, dense_row=1)
+    # oracle in fp32 arithmetic for p / log (the reference's own arithmetic) accumulated in fp64
+    z = (q.double() @ O.double().T).float()
+    t = A.dense_targets(B, N, off.long(), idx, ls, torch.float32)
+    _, loss_el, gsum = A.bce_sigmoid_terms(z, t)
+    loss_ref = loss_el.double().sum()
+    G = gsum.double() / (B * N)
+    H_ref, dO_ref = G @ O.double(), G.T @ q.double()
+    loss, H, dO = ops.score_bce_fwd_bwd(q.to(dev), q.to(dev), O.to(dev), off.to(dev), idx.to(dev), ls)
+    assert abs(float(loss.cpu()) - float(loss_ref)) / abs(float(loss_ref)) < REL
+    assert relerr(H, H_ref) < REL
+    assert relerr(dO, dO_ref) < REL
+    # determinism
+    loss2, H2, dO2 = ops.score_bce_fwd_bwd(q.to(dev), q.to(dev), O.to(dev), off.to(dev), idx.to(dev), ls)
+    assert torch.equal(H, H2) and torch.equal(dO, dO2) and torch.equal(loss, loss2)
+
+
+def test_score_bce_matches_reference_semantics_cpu_torch(cuda_device):
+    """Same as above but the expected values come from torch's own BCELoss + autograd (the ops the
+    reference executes, train.py:79/136), fp32."""
+    import analytic as A
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(11)
+    B, N, r2, ls = 96, 1501, 20, 0.1
+    q = (8 * torch.randn(B, r2, generator=g) / r2 ** 0.5).requires_grad_(True)
+    O = torch.randn(N, r2, generator=g).requires_grad_(True)
+    off, idx = make_csr(B, N, g)
+    t = A.dense_targets(B, N, off.long(), idx, ls, torch.float32)
+    loss_ref = torch.nn.BCELoss(reduction="mean")(torch.sigmoid(q @ O.T), t)
+    gq, gO = torch.autograd.grad(loss_ref, [q, O])
+    loss, H, dO = ops.score_bce_fwd_bwd(q.detach().to(dev), q.detach().to(dev), O.detach().to(dev),
+                                        off.to(dev), idx.to(dev), ls)
+    assert abs(float(loss.cpu()) / (B * N) - float(loss_ref)) / float(loss_ref) < REL
+    assert relerr(H, gq) < REL and relerr(dO, gO) < REL
+
+
+def test_score_bce_sharded_equals_whole(cuda_device):
+    """Entity sharding: partial loss / H sum to the unsharded result, dO shards concatenate."""
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    B, N, r2, ls = 128, 1000, 20, 0.1
+    q = torch.randn(B, r2, generator=g).to(dev)
+    O = torch.randn(N, r2, generator=g).to(dev)
+    off, idx = make_csr(B, N, g)
+    off, idx = off.to(dev), idx.to(dev)
+    loss, H, dO = ops.score_bce_fwd_bwd(q, q, O, off, idx, ls)
+    parts = [(0, 300), (300, 1000)]
+    acc_loss, acc_H, dOs = 0.0, 0.0, []
+    for lo, hi in parts:
+        l, h, d = ops.score_bce_fwd_bwd(q, q, O[lo:hi].contiguous(), off, idx, ls, n_total=N, b_total=B, n_begin=lo)
+        acc_loss, acc_H = acc_loss + l, acc_H + h
+        dOs.append(d)
+    assert abs(float(acc_loss) - float(loss)) / float(loss) < 1e-9
+    assert relerr(acc_H, H) < 1e-6 and relerr(torch.cat(dOs), dO) < 1e-7
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N,r2", [(64, 1000, 20), (130, 4099, 200), (512, 14951, 100)])
+def test_score_rank_fused(cuda_device, B, N, r2):
+    """Fused scoring + ranking: the probabilities are produced on the device, so the check is
+    against ranks computed from the DEVICE probabilities (target via rt_target_prob) with the
+    dense-input kernel's semantics on a CPU recomputation in fp32."""
+    import ranking as oracle_rank
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(B + N)
+    q = 3 * torch.randn(B, r2, generator=g) / r2 ** 0.5
+    O = torch.randn(N, r2, generator=g)
+    target = torch.randint(0, N, (B,), generator=g).int()
+    off, idx = make_csr(B, N, g, max_per_row=8)
+    for b in range(B):
+        idx[off[b]] = target[b]
+    qd, Od, td, offd, idxd = (x.to(dev) for x in (q, O, target, off, idx))
+    pt = ops.target_prob(qd, Od, td)
+    cg, ce, cb, bce = ops.score_rank_fused(qd, Od, td, pt, offd, idxd)
+    # reference counts from an fp64 logit matrix: ranks may differ only where |p - p_t| is at fp32
+    # rounding level; require exact equality on all queries whose margin is clear
+    z = q.double() @ O.double().T
+    p = torch.sigmoid(z).float()
+    eg, ee, eb = oracle_rank.filtered_counts(p.numpy(), target.numpy(), off.numpy(), idx.numpy())
+    ranks_dev = 1 + cg.cpu().numpy() + cb.cpu().numpy()
+    ranks_ref = 1 + eg + eb
+    mismatch = int(np.count_nonzero(ranks_dev != ranks_ref))
+    assert mismatch <= max(1, B // 50), f"{mismatch} of {B} ranks differ"
+    assert np.max(np.abs(ranks_dev - ranks_ref)) <= 2
+    # BCE (train.py:113): un-smoothed multi-hot over the filter list
+    t = torch.zeros(B, N)
+    for b in range(B):
+        t[b, idx[off[b]:off[b + 1]].long()] = 1
+    bce_ref = torch.nn.functional.binary_cross_entropy(p, t, reduction="sum").double()
+    assert abs(float(bce.cpu()) - float(bce_ref)) / float(bce_ref) < REL
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 20, 40, 129, 400])
+def test_eigh(cuda_device, n):
+    from rtucker_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    X = torch.randn(n, 3 * n + 5, generator=g, dtype=torch.float64)
+    A = X @ X.T
+    if n > 8:  # make it rank deficient with a cluster of equal eigenvalues, like a padded Gram
+        A[:, -3:] = 0
+        A[-3:, :] = 0
+    w, V = ops.eigh(A.to(cuda_device))
+    w, V = w.cpu(), V.cpu()
+    w_ref = torch.linalg.eigvalsh(A).flip(0)
+    assert float((w - w_ref).abs().max()) <= 1e-11 * float(w_ref.abs().max())
+    assert float((V.T @ V - torch.eye(n, dtype=torch.float64)).abs().max()) < 1e-11
+    assert float((A @ V - V * w).abs().max()) <= 1e-10 * float(w_ref.abs().max())
