@@ -76,6 +76,14 @@ int rt_score_rank_fused(const float* q, const float* O, int B, int r2, int n_beg
                         int32_t* greater, int32_t* equal, int32_t* equal_before,
                         double* bce_sum, void* ws, void* stream);
 
+/* Dense compatibility path: P[b, j] = sigmoid(q_b . O_j), what score_fn(T) returns in the reference
+ * (src/model/asymmetric/R_TuckER.py:47-48).  Bit-identical to the values the fused kernels use. */
+int rt_score_dense(const float* q, const float* O, int B, int r2, int n_local, float* P, int64_t ldp,
+                   void* stream);
+/* In-place dense filter, exactly src/utils/utils.py:18-21 (filter_col = features[:,2]). */
+int rt_filter_dense(float* P, int64_t ldp, float* T, int64_t ldt, int B, int N,
+                    const int32_t* filter_col, void* stream);
+
 /* ---- (a) query contraction ----------------------------------------------------------- */
 /* out[b,:] = table[idx[b] - row_begin, :] if row_begin <= idx[b] < row_begin+rows else 0.
  * Replaces the gathers at src/model/asymmetric/R_TuckER.py:43-44 (shard-aware). */
@@ -119,11 +127,13 @@ int rt_score_bce_fwd_bwd(const float* q, const float* qp, const float* O,
 
 /* ---- (c) tall-skinny passes over the N x r factors ----------------------------------- */
 /* out[ra, rb] (fp64) = A[n, :ra]^T  B[n, :rb]   (deterministic two-stage reduction).
+ * precise = 0: fp32 products accumulated in fp32 over 256-row blocks, fp64 across blocks;
+ * precise = 1: exact fp64 accumulation (needed where the Gram feeds a Cholesky: the retraction).
  * Replaces the N-sized Gram products inside tucker_riemopt grad/project/norm/round
  * (call sites asymmetric/optim.py:86-90,108). */
 size_t rt_gram_ws_bytes(int n, int ra, int rb);
 int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb, int n, int ra, int rb,
-            double* out, void* ws, void* stream);
+            double* out, int precise, void* ws, void* stream);
 /*
  * Y[n, rc] = a0 * X0 + sum_{k<nk} X_k[n, rk_k] . K_k[rk_k, rc]      (K_k fp64, row-major dense)
  * a0 is read from device memory (a0_dev, may be NULL => 1.0 when X0 != NULL).  X0 may be NULL.

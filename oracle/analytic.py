@@ -77,9 +77,19 @@ def dense_targets(B, N, tgt_off, tgt_idx, label_smoothing, dtype):
     return t
 
 
+# When True, the elementwise sigmoid / log / gradient terms are evaluated in float32 even if the
+# contractions run in float64: this reproduces the reference's fp32 saturation semantics (p rounds to
+# exactly 1.0 for z > 16.6, log terms clamp at -100, the gradient vanishes where p(1-p) < 1e-12,
+# SURVEY.md App. B.1) while keeping the linear algebra exact.
+ELEMENTWISE_FP32 = False
+
+
 def bce_sigmoid_terms(z, t):
     """Elementwise loss and dL_sum/dz exactly as BCELoss(sigmoid(z)) computes them
     (before the 1/(B*N) mean factor)."""
+    if ELEMENTWISE_FP32 and z.dtype != torch.float32:
+        p, loss, g = bce_sigmoid_terms(z.float(), t.float())
+        return p.to(z.dtype), loss.to(z.dtype), g.to(z.dtype)
     p = torch.sigmoid(z)
     loss = -(t * torch.clamp(torch.log(p), min=BCE_LOG_CLAMP)
              + (1 - t) * torch.clamp(torch.log1p(-p), min=BCE_LOG_CLAMP))
@@ -229,15 +239,15 @@ def project(x: Point, old: Point, xi_old: Tangent):
 
 def retract(x: Point, xi: Tangent, lr, rank=None):
     """round(construct(X - lr*xi)) by the structured route of SURVEY.md App. A.5:
-    Gram of W_i = -lr dV_i, Cholesky, small rank-2r tensor, HOSVD through the
-    symmetric eigenproblem of each unfolding Gram.  Returns the new Point."""
+    thin QR of W_i = -lr dV_i (U_i^T W_i = 0, so [U_i|W_i] = [U_i|Q_i] blkdiag(I,R_i)), small rank-2r
+    tensor, HOSVD through the symmetric eigenproblem of each unfolding Gram.  Returns the new Point."""
     r = x.core.shape if rank is None else rank
-    Rf, W = [], []
+    Rf, W, Q = [], [], []
     for k in range(3):
         w = -lr * xi.d_factors[k]
-        gram = w.T @ w
-        L = torch.linalg.cholesky(gram)
-        Rf.append(L.T)
+        q, rr = torch.linalg.qr(w)       # Householder QR: fine for rank-deficient W (e.g. M - r0 < r0)
+        Q.append(q)
+        Rf.append(rr)
         W.append(w)
     T = group_cores(x.core - lr * xi.d_core, x.core)
     blk = []
@@ -265,7 +275,7 @@ def retract(x: Point, xi: Tangent, lr, rank=None):
             new_f.append(new_f[1])
             continue
         y1, y2 = Y[k][: r[k]], Y[k][r[k]:]
-        new_f.append(x.factors[k] @ y1 + W[k] @ torch.linalg.solve_triangular(Rf[k], y2, upper=True))
+        new_f.append(x.factors[k] @ y1 + Q[k] @ y2)
     return Point(new_core, new_f, x.sym)
 
 

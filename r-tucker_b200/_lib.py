@@ -23,6 +23,8 @@ PROTOTYPES = {
     "rt_target_prob": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
     "rt_score_rank_ws_bytes": (sz, [i32, i32, i32]),
     "rt_score_rank_fused": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "rt_score_dense": (i32, [vp, vp, i32, i32, i32, vp, i64, vp]),
+    "rt_filter_dense": (i32, [vp, i64, vp, i64, i32, i32, vp, vp]),
     "rt_gather_rows": (i32, [vp, i32, i32, i32, vp, i32, vp, vp]),
     "rt_scatter_rows_add": (i32, [vp, i32, i32, i32, vp, i32, vp, vp]),
     "rt_query_ws_bytes": (sz, [i32, i32, i32, i32]),
@@ -32,7 +34,7 @@ PROTOTYPES = {
     "rt_score_bce_fwd_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp, vp,
                                    i32, vp, vp]),
     "rt_gram_ws_bytes": (sz, [i32, i32, i32]),
-    "rt_gram": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp]),
+    "rt_gram": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, i32, vp, vp]),
     "rt_apply": (i32, [vp, i64, i32, i32, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i64),
                        C.POINTER(i32), C.POINTER(vp), vp]),
     "rt_small_ws_bytes": (sz, [i32, i32, i32, i32]),

@@ -92,7 +92,34 @@ rank_dense_kernel(const float* __restrict__ P, int64_t ldp, int N,
   }
 }
 
+// In-place dense filter, exactly reference src/utils/utils.py:18-21: keep the score at the filter
+// column, zero scores and targets wherever targets == 1, restore the kept score, set targets to
+// one-hot at the filter column.
+__global__ void __launch_bounds__(kThreads)
+filter_dense_kernel(float* __restrict__ P, int64_t ldp, float* __restrict__ T, int64_t ldt, int N,
+                    const int32_t* __restrict__ filter_col) {
+  const int b = blockIdx.y;
+  const int f = filter_col[b];
+  float* prow = P + (int64_t)b * ldp;
+  float* trow = T + (int64_t)b * ldt;
+  for (int j = blockIdx.x * kThreads + threadIdx.x; j < N; j += gridDim.x * kThreads) {
+    const float t = trow[j];
+    if (j == f) { trow[j] = 1.0f; continue; }   // prediction kept as is
+    if (t == 1.0f) { prow[j] = 0.0f; trow[j] = 0.0f; }
+  }
+}
+
 }  // namespace
+
+extern "C" int rt_filter_dense(float* P, int64_t ldp, float* T, int64_t ldt, int B, int N,
+                               const int32_t* filter_col, void* stream) {
+  RT_REQUIRE(B >= 0 && N > 0 && ldp >= N && ldt >= N && B <= 65535, "rt_filter_dense: bad shape");
+  if (B == 0) return 0;
+  dim3 grid(rt::cdiv(N, kThreads * 8), B);
+  filter_dense_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(P, ldp, T, ldt, N, filter_col);
+  RT_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int rt_rank_filtered(const float* P, int64_t ldp, int B, int N, const int32_t* target,
                                 const int32_t* flt_off, const int32_t* flt_idx, int32_t* greater,

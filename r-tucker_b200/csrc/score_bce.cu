@@ -304,6 +304,58 @@ __global__ void target_prob_kernel(const float* __restrict__ q, const float* __r
   p_target[b] = p;
 }
 
+// Dense compatibility path: P[b, j] = sigmoid(q_b . O_j) written out (what score_fn(T) returns in
+// the reference, R_TuckER.py:47-48).  Same staging and k order as score_kernel, so the values are
+// bit-identical to the ones the fused kernels see.
+__global__ void __launch_bounds__(256)
+score_dense_kernel(const float* __restrict__ q, const float* __restrict__ O, int B, int r2, int n_local,
+                   float* __restrict__ P, int64_t ldp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int ldw = row_ld(r2, 1);
+  const int k_end = (r2 + 3) / 4 * 4;
+  float* Os = reinterpret_cast<float*>(smem_raw);
+  float* Qs = Os + NT * ldw;
+  const int n0 = blockIdx.x * NT, b0 = blockIdx.y * BT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  for (int e = threadIdx.x; e < NT * ldw; e += 256) {
+    const int rr = e / ldw, cc = e - rr * ldw;
+    Os[e] = (n0 + rr < n_local && cc < r2) ? __ldg(O + (int64_t)(n0 + rr) * r2 + cc) : 0.0f;
+    Qs[e] = (b0 + rr < B && cc < r2) ? __ldg(q + (int64_t)(b0 + rr) * r2 + cc) : 0.0f;
+  }
+  __syncthreads();
+  float z[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) z[i][j] = 0.0f;
+  for (int k = 0; k < k_end; k += 4) {
+    float4 qv[4], ov[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(Qs + (ty + 16 * i) * ldw + k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ov[j] = *reinterpret_cast<const float4*>(Os + (tx + 16 * j) * ldw + k);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        z[i][j] = fmaf(qv[i].x, ov[j].x, z[i][j]);
+        z[i][j] = fmaf(qv[i].y, ov[j].y, z[i][j]);
+        z[i][j] = fmaf(qv[i].z, ov[j].z, z[i][j]);
+        z[i][j] = fmaf(qv[i].w, ov[j].w, z[i][j]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int b = b0 + ty + 16 * i;
+    if (b >= B) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n < n_local) P[(int64_t)b * ldp + n] = 1.0f / (1.0f + expf(-z[i][j]));
+    }
+  }
+}
+
 struct Plan {
   int cpt, grid, n_tiles;
   size_t smem;
@@ -435,5 +487,18 @@ extern "C" int rt_score_rank_fused(const float* q, const float* O, int B, int r2
     reduce_loss_kernel<<<1, 32, 0, s>>>(a.loss_partial, p.grid, bce_sum, 0);
     RT_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+extern "C" int rt_score_dense(const float* q, const float* O, int B, int r2, int n_local, float* P,
+                              int64_t ldp, void* stream) {
+  RT_REQUIRE(B >= 0 && r2 > 0 && r2 <= 1024 && n_local >= 0 && ldp >= n_local, "rt_score_dense: bad shape");
+  if (B == 0 || n_local == 0) return 0;
+  const size_t smem = (size_t)(NT + BT) * row_ld(r2, 1) * sizeof(float);
+  RT_CHECK_CUDA(cudaFuncSetAttribute(score_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  dim3 grid(rt::cdiv(n_local, NT), rt::cdiv(B, BT));
+  score_dense_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(q, O, B, r2, n_local, P, ldp);
+  RT_LAUNCH_CHECK();
   return 0;
 }

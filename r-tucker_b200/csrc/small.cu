@@ -270,7 +270,7 @@ extern "C" int rt_rows_times_ainv(const float* A, int m, int mode, int r0, int r
 }
 
 extern "C" int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb, int n, int ra, int rb,
-                       double* out, void* ws, void* stream);
+                       double* out, int precise, void* ws, void* stream);
 
 extern "C" int rt_small_grad(const float* core, const float* d_core, const float* qp, const float* H,
                              const float* r_rows, const float* s_rows, const float* dr_rows,
@@ -292,11 +292,11 @@ extern "C" int rt_small_grad(const float* core, const float* d_core, const float
   if ((rc = rt_rows_times_ainv(ds_rows, B, 1, r0, r1, r2, dsA, small_ws, stream))) return rc;
   void* gws = c.base + c.L.gram_ws;
   // P_i = -(U_i^T g_i A_i): the Gram of the gathered rows with the A-scaled gradient rows
-  if ((rc = rt_gram(r_rows, r0, drA, r0, B, r0, r0, P_R, gws, stream))) return rc;
+  if ((rc = rt_gram(r_rows, r0, drA, r0, B, r0, r0, P_R, 0, gws, stream))) return rc;
   c.axpby(P_R, nullptr, P_R, (int64_t)r0 * r0, -1.0, nullptr, 0.0, nullptr);
-  if ((rc = rt_gram(s_rows, r1, dsA, r1, B, r1, r1, P_S, gws, stream))) return rc;
+  if ((rc = rt_gram(s_rows, r1, dsA, r1, B, r1, r1, P_S, 0, gws, stream))) return rc;
   double* tmp = c.p(c.L.tmpK[2]);
-  if ((rc = rt_gram(H, r2, qp, r2, B, r2, r2, sym ? tmp : P_O, gws, stream))) return rc;
+  if ((rc = rt_gram(H, r2, qp, r2, B, r2, r2, sym ? tmp : P_O, 0, gws, stream))) return rc;
   if (sym) {
     c.axpby(P_S, tmp, P_S, (int64_t)r1 * r1, -1.0, nullptr, -1.0, nullptr);
     if (P_O && P_O != P_S) c.axpby(P_S, nullptr, P_O, (int64_t)r1 * r1, 1.0, nullptr, 0.0, nullptr);

@@ -255,7 +255,7 @@ spd_factor_kernel(SpdBatch batch) {
     s_maxd = m;
   }
   __syncthreads();
-  const double tol = 1e-13 * s_maxd;
+  const double tol = 1e-12 * s_maxd;
   for (int k = 0; k < n; ++k) {
     if (tid == 0) {
       const double d = Lp[pk(k, k)];

@@ -54,6 +54,7 @@ constexpr int GT = 64;       // output tile edge
 constexpr int GKC = 32;      // rows per smem chunk
 constexpr int GFLUSH = 8;    // chunks accumulated in fp32 before flushing to fp64
 
+template <bool PRECISE>
 __global__ void __launch_bounds__(256)
 gram_partial_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
                     int n, int ra, int rb, int tiles_b, int rows_per_split,
@@ -101,10 +102,13 @@ gram_partial_kernel(const float* __restrict__ A, int64_t lda, const float* __res
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bq[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) {
+          if (PRECISE) acc64[i][j] = fma((double)a[i], (double)bq[j], acc64[i][j]);  // exact products
+          else acc[i][j] = fmaf(a[i], bq[j], acc[i][j]);
+        }
     }
     __syncthreads();
-    if ((chunk % GFLUSH) == GFLUSH - 1) {
+    if (!PRECISE && (chunk % GFLUSH) == GFLUSH - 1) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -274,7 +278,7 @@ extern "C" size_t rt_gram_ws_bytes(int n, int ra, int rb) {
 }
 
 extern "C" int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb, int n, int ra,
-                       int rb, double* out, void* ws, void* stream) {
+                       int rb, double* out, int precise, void* ws, void* stream) {
   RT_REQUIRE(n >= 0 && ra > 0 && rb > 0 && lda >= ra && ldb >= rb, "rt_gram: bad shape n=%d ra=%d rb=%d",
              n, ra, rb);
   cudaStream_t s = (cudaStream_t)stream;
@@ -285,8 +289,12 @@ extern "C" int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb,
   RT_REQUIRE(ws != nullptr, "rt_gram: workspace is NULL");
   GramPlan p = gram_plan(n, ra, rb);
   dim3 grid(p.tiles_a * p.tiles_b, p.nsplit);
-  gram_partial_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, n, ra, rb, p.tiles_b, p.rows_per_split,
-                                           (double*)ws);
+  if (precise)
+    gram_partial_kernel<true><<<grid, 256, 0, s>>>(A, lda, B, ldb, n, ra, rb, p.tiles_b,
+                                                   p.rows_per_split, (double*)ws);
+  else
+    gram_partial_kernel<false><<<grid, 256, 0, s>>>(A, lda, B, ldb, n, ra, rb, p.tiles_b,
+                                                    p.rows_per_split, (double*)ws);
   RT_LAUNCH_CHECK();
   const int count = ra * rb;
   gram_reduce_kernel<<<rt::cdiv(count, 256), 256, 0, s>>>((const double*)ws, p.nsplit, count, out);

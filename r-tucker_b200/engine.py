@@ -1,0 +1,217 @@
+"""Host-side orchestration of one Riemannian step on the (SF-)Tucker manifold.
+
+This is the state machine of the reference optimisers
+  RGD / RSGDwithMomentum.fit + .step   src/model/asymmetric/optim.py:23-57,74-114
+                                       src/model/symmetric/optim.py:23-107
+expressed over the C-ABI kernels (ops.py).  The order of operations is the reference's:
+transport the previous direction to the current point (optim.py:85-88), Riemannian gradient
+(optim.py:89), its norm (optim.py:90), direction = g/||g||*normalize + beta*momentum (optim.py:92);
+then step(): X <- round(construct(-lr*direction + X)) (optim.py:106-108), the direction kept as an
+ambient tensor at the OLD point for the next transport (optim.py:109), parameters written back
+(optim.py:111-114).
+
+Entity sharding: when ``group`` is given, the rows of S/O (or E) and of every
+N x r tangent / momentum buffer are split into contiguous blocks over the ranks; the core, R and all
+r-sized objects are replicated; the only exchanges are all-reduces of [B,r] row blocks, the loss
+scalar and r x r Gram matrices.  ``ops`` is injectable so the sharding logic can be exercised on CPU
+(gloo) by the tests with the oracle's arithmetic; the product always uses the CUDA ops.
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import ops as cuda_ops
+
+f32, f64 = torch.float32, torch.float64
+
+
+@dataclass
+class SparseTargets:
+    """Multi-hot targets of a batch in CSR form: objects of query b are idx[off[b]:off[b+1]]
+    (GLOBAL entity ids, unique per query).  Equivalent of the dense rows built at
+    src/data/Dataset.py:43-52."""
+    off: torch.Tensor  # int32 [B+1]
+    idx: torch.Tensor  # int32 [nnz]
+
+
+class Direction:
+    """The optimiser's ``direction``: a tangent vector at ``point`` = (core, [R, S, O])."""
+
+    def __init__(self, d_core, d_factors, point_core, point_factors):
+        self.d_core, self.d_factors = d_core, d_factors
+        self.point_core, self.point_factors = point_core, point_factors
+
+
+class StepEngine:
+    def __init__(self, core, factors: List[torch.Tensor], sym: bool, batch_size: int,
+                 momentum_beta: Optional[float], group=None, n_total: Optional[int] = None,
+                 n_begin: int = 0, score_variant: int = 0, ops=None):
+        """core: Parameter [r0,r1,r2]; factors: [R, S, O] Parameters (sym: [R, E]); entity factors
+        hold rows [n_begin, n_begin + n_local) of the global n_total entities."""
+        self.ops = ops if ops is not None else cuda_ops
+        self.core = core
+        self.sym = bool(sym)
+        self.params = list(factors)
+        self.nf = len(self.params)            # 3 (asym) or 2 (sym)
+        self.rank = tuple(core.shape)
+        self.B = int(batch_size)
+        self.beta = momentum_beta
+        self.group = group
+        self.n_begin = int(n_begin)
+        self.n_local = self.params[1].shape[0]
+        self.n_total = int(n_total) if n_total is not None else self.n_local
+        self.score_variant = int(score_variant)
+        dev = core.device
+        self.dev = dev
+        self.small = self.ops.SmallStage(self.rank, self.B, self.sym, dev)
+        self.hyper = torch.zeros(4, dtype=f64, device=dev)
+        self._hyper_host = None
+        self._hyper_vals = None
+        # per-factor buffers (allocated lazily in the factor's shape)
+        self.U_old = [None] * self.nf
+        self.spare = [torch.empty_like(p.data) for p in self.params]
+        self.dV_dir = [None] * self.nf        # direction kept from the previous step (old point)
+        self.dV_new = [torch.empty_like(p.data) for p in self.params]
+        self.core_old = None
+        self.dS_dir_old = None
+        self.has_old = False
+        self.pending = None                    # (dS_dir, [dV]) produced by fit(), consumed by step()
+        self.loss = None
+
+    # -------------------------------------------------------------------------------------------
+    def _set_hyper(self, lr, reg, beta, normalize):
+        vals = (float(lr), float(reg), float(beta or 0.0), float(normalize or 0.0))
+        if vals != self._hyper_vals:
+            host = torch.tensor(vals, dtype=f64)
+            if self.dev.type == "cuda":
+                host = host.pin_memory()
+            self._hyper_host = host            # keep alive until replaced
+            self.hyper.copy_(host, non_blocking=True)
+            self._hyper_vals = vals
+
+    def _allreduce(self, *tensors):
+        if self.group is None:
+            return
+        import torch.distributed as dist
+        for t in tensors:
+            dist.all_reduce(t, group=self.group)
+
+    def _entity_factor_ids(self):
+        return (1, 2) if not self.sym else (1,)
+
+    def _U(self, k):
+        return self.params[k].data
+
+    def _obj(self):
+        return self._U(2) if not self.sym else self._U(1)
+
+    # -------------------------------------------------------------------------------------------
+    def fit(self, rel_idx, sub_idx, targets: SparseTargets, label_smoothing, reg, lr_hint=0.0,
+            normalize_grad=1.0):
+        ops, small, sym = self.ops, self.small, self.sym
+        r0, r1, r2 = self.rank
+        core = self.core.data
+        B = rel_idx.shape[0]
+        self._set_hyper(self._hyper_vals[0] if self._hyper_vals else lr_hint, reg, self.beta,
+                        normalize_grad if normalize_grad else 0.0)
+        small.prepare(core)
+        R, S, O = self._U(0), self._U(1), self._obj()
+        r_rows = ops.gather_rows(R, rel_idx)
+        s_rows = ops.gather_rows(S, sub_idx, self.n_begin)
+        self._allreduce(s_rows)
+        q = ops.query_fwd(core, r_rows, s_rows)
+        qp = small.rows_times_ainv(q, 2)
+        # dO' = G^T (q A_O) lands directly in the object factor's scratch buffer
+        k_obj = 2 if not sym else 1
+        dOp = self.spare[k_obj]
+        bce_sum = torch.empty(1, dtype=f64, device=self.dev)
+        H = torch.empty(B, r2, dtype=core.dtype, device=self.dev)
+        ops.score_bce_fwd_bwd(q, qp, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
+                              b_total=B, n_begin=self.n_begin, variant=self.score_variant,
+                              out=(bce_sum, H, dOp))
+        self._allreduce(H, bce_sum)
+        d_core, ds_rows, dr_rows = ops.query_bwd(core, r_rows, s_rows, H)
+        inv_count = 1.0 / (float(B) * float(self.n_total))
+        dS_g, loss, drA, dsA, P_R, P_S, P_O = small.grad(core, d_core, qp, H, r_rows, s_rows, dr_rows,
+                                                         ds_rows, bce_sum, inv_count, self.hyper)
+        # ---- factor parts of the Riemannian gradient: dV_i = g_i A_i - U_i (U_i^T g_i A_i) ----
+        dV_g = [None] * self.nf
+        dV_g[0] = ops.apply(self.spare[0], None, None, [(R, P_R)])
+        ops.scatter_rows_add(dV_g[0], rel_idx, drA)
+        if not sym:
+            dV_g[1] = ops.apply(self.spare[1], None, None, [(S, P_S)])
+            ops.scatter_rows_add(dV_g[1], sub_idx, dsA, self.n_begin)
+            dV_g[2] = ops.apply(dOp, dOp, None, [(O, P_O)])
+        else:
+            dV_g[1] = ops.apply(dOp, dOp, None, [(S, P_S)])
+            ops.scatter_rows_add(dV_g[1], sub_idx, dsA, self.n_begin)
+        # ---- norm of the Riemannian gradient ----
+        grams = [ops.gram(v, v) for v in dV_g]
+        self._allreduce(*[grams[k] for k in self._entity_factor_ids()])
+        norm, alpha = small.norm(dS_g, grams[0], grams[1], grams[2] if not sym else grams[1], self.hyper)
+        # ---- momentum: transport the previous direction, then combine ----
+        use_momentum = self.beta is not None and self.has_old
+        dV_new = self.dV_new
+        if use_momentum:
+            M = []
+            for k in range(self.nf):
+                Mk = torch.cat([ops.gram(self._U(k), self.U_old[k]), ops.gram(self._U(k), self.dV_dir[k])], dim=1)
+                M.append(Mk.contiguous())
+            self._allreduce(*[M[k] for k in self._entity_factor_ids()])
+            pS_beta, K, L = small.project(core, self.core_old, self.dS_dir_old, M[0], M[1],
+                                          M[2] if not sym else M[1], self.hyper)
+            dS_dir = ops.core_axpby(dS_g, alpha, pS_beta)
+            for k in range(self.nf):
+                rk = self.rank[k]
+                ops.apply(dV_new[k], dV_g[k], alpha,
+                          [(self.U_old[k], K[k][:rk]), (self.dV_dir[k], K[k][rk:]), (self._U(k), L[k])])
+        else:
+            dS_dir = ops.core_axpby(dS_g, alpha, None)
+            for k in range(self.nf):
+                ops.apply(dV_new[k], dV_g[k], alpha, [])
+        self.pending = (dS_dir, dV_new)
+        self.loss = loss
+        self.rgrad_norm = norm
+        self.debug = dict(q=q, H=H, dS_g=dS_g, dV_g=dV_g, alpha=alpha, bce_sum=bce_sum)
+        return norm
+
+    # -------------------------------------------------------------------------------------------
+    def step(self, lr):
+        assert self.pending is not None, "step() called before fit()"
+        ops, small, sym = self.ops, self.small, self.sym
+        hv = self._hyper_vals
+        self._set_hyper(lr, hv[1], hv[2], hv[3])
+        dS_dir, dV = self.pending
+        core = self.core.data
+        # exact fp64 Gram: it feeds the Cholesky that stands in for the reference's QR of [U | W]
+        grams = [ops.gram(v, v, precise=True) for v in dV]
+        self._allreduce(*[grams[k] for k in self._entity_factor_ids()])
+        core_new, Z1, Z2 = small.retract(core, dS_dir, grams[0], grams[1], grams[2] if not sym else grams[1],
+                                         self.hyper)
+        new_U = []
+        for k in range(self.nf):
+            # spare[k] held dV_g during fit(); it is free again now
+            new_U.append(ops.apply(self.spare[k], None, None, [(self._U(k), Z1[k]), (dV[k], Z2[k])]))
+        # ---- rotate state: the current point becomes the "old" point of the kept direction ----
+        keep = self.beta is not None
+        for k in range(self.nf):
+            prev_U = self.params[k].data
+            self.params[k].data = new_U[k]
+            recycled = self.U_old[k] if self.U_old[k] is not None else torch.empty_like(prev_U)
+            if keep:
+                self.U_old[k] = prev_U
+                self.spare[k] = recycled
+                prev_dir = self.dV_dir[k] if self.dV_dir[k] is not None else torch.empty_like(prev_U)
+                self.dV_dir[k] = dV[k]
+                self.dV_new[k] = prev_dir
+            else:
+                self.spare[k] = prev_U
+        prev_core = self.core.data
+        self.core.data = core_new
+        if keep:
+            self.core_old = prev_core
+            self.dS_dir_old = dS_dir
+            self.has_old = True
+        self.pending = None
+        return core_new

@@ -127,16 +127,16 @@ def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None,
 
 
 # ---------------------------------------------------------------- (c) tall-skinny
-def gram(A, B, out=None, ws=None):
-    """out[ra,rb] (f64) = A^T B over the rows."""
+def gram(A, B, out=None, ws=None, precise=False):
+    """out[ra,rb] (f64) = A^T B over the rows (precise: exact fp64 accumulation)."""
     require_cuda(A, B)
     n, ra = A.shape
     rb = B.shape[1]
     assert B.shape[0] == n and A.stride(1) == 1 and B.stride(1) == 1
     out = out if out is not None else torch.empty(ra, rb, dtype=f64, device=A.device)
     ws = ws if ws is not None else _ws(lib().rt_gram_ws_bytes(n, ra, rb), A.device)
-    check(lib().rt_gram(ptr(A), A.stride(0), ptr(B), B.stride(0), n, ra, rb, ptr(_c(out, f64)), ptr(ws),
-                        stream_ptr()), "rt_gram")
+    check(lib().rt_gram(ptr(A), A.stride(0), ptr(B), B.stride(0), n, ra, rb, ptr(_c(out, f64)),
+                        int(bool(precise)), ptr(ws), stream_ptr()), "rt_gram")
     return out
 
 
@@ -247,3 +247,24 @@ def eigh(A):
     ws = _ws(lib().rt_eigh_ws_bytes(n), A.device)
     check(lib().rt_eigh(ptr(A), n, ptr(w), ptr(V), ptr(ws), stream_ptr()), "rt_eigh")
     return w, V
+
+
+def score_dense(q, O, out=None):
+    """Dense sigmoid scores P[B, n] (compat path of R_TuckER.py:47-48)."""
+    require_cuda(q, O)
+    B, r2 = q.shape
+    n = O.shape[0]
+    P = out if out is not None else torch.empty(B, n, dtype=f32, device=q.device)
+    check(lib().rt_score_dense(ptr(_c(q, f32)), ptr(_c(O, f32)), B, r2, n, ptr(P), P.stride(0), stream_ptr()),
+          "rt_score_dense")
+    return P
+
+
+def filter_dense_(P, T, filter_col):
+    """In place: exactly src/utils/utils.py:18-21."""
+    require_cuda(P, T, filter_col)
+    B, N = P.shape
+    assert P.dtype == f32 and T.dtype == f32 and P.stride(1) == 1 and T.stride(1) == 1
+    check(lib().rt_filter_dense(ptr(P), P.stride(0), ptr(T), T.stride(0), B, N, ptr(_c(filter_col, i32)),
+                                stream_ptr()), "rt_filter_dense")
+    return P, T
