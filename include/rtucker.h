@@ -40,6 +40,8 @@ int rt_abi_version(void);
 const char* rt_last_error(void);
 /* SM count and compute capability of the current device. */
 int rt_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+/* Number of CUDA kernels this library has launched in the calling process (bench.py: gpu_launches). */
+unsigned long long rt_launch_count(void);
 
 /* ---- (d) filtered ranking ------------------------------------------------------------ */
 /*

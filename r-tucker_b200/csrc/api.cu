@@ -4,6 +4,7 @@
 
 namespace rt {
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -22,3 +23,4 @@ extern "C" int rt_device_info(int* sm, int* major, int* minor) {
   RT_CHECK_CUDA(cudaDeviceGetAttribute(minor, cudaDevAttrComputeCapabilityMinor, dev));
   return 0;
 }
+extern "C" unsigned long long rt_launch_count(void) { return rt::g_launches; }

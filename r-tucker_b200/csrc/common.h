@@ -9,6 +9,7 @@
 namespace rt {
 
 void set_error(const char* fmt, ...);
+extern unsigned long long g_launches;  // kernels launched by this library in this process
 
 #define RT_CHECK_CUDA(expr)                                                            \
   do {                                                                                 \
@@ -28,7 +29,11 @@ void set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
-#define RT_LAUNCH_CHECK() RT_CHECK_CUDA(cudaGetLastError())
+#define RT_LAUNCH_CHECK()                 \
+  do {                                    \
+    ++rt::g_launches;                     \
+    RT_CHECK_CUDA(cudaGetLastError());    \
+  } while (0)
 
 inline int sm_count() {
   static int n = 0;

@@ -5,10 +5,10 @@
 // where the left singular vectors of each unfolding of the rank-2r core are the eigenvectors of
 // its (2r_i x 2r_i) Gram matrix.  The reference calls cuSOLVER gesvd on the unfoldings.
 //
-// Scheme: blocks of 8 indices; a round-robin tournament pairs the blocks; per round
-//   phase A: one warp per block pair diagonalises its 16x16 sub-matrix (scalar cyclic Jacobi in
-//            shared memory) and publishes the 16x16 rotation Q;
-//   phase B: every 16x16 tile (pair k rows, pair l cols) becomes Q_k^T A_kl Q_l, and V <- V Q.
+// Scheme: blocks of 16 indices; a round-robin tournament pairs the blocks; per round
+//   phase A: one warp per block pair rotates every cross index pair of its 32x32 tile once (and, in
+//            the first round of a sweep, every pair inside the two blocks) and publishes the product Q;
+//   phase B: every 32x32 tile (pair k rows, pair l cols) becomes Q_k^T A_kl Q_l, and V <- V Q.
 // grid.sync() separates the phases.  N-independent, latency-bound: reported separately from the
 // HBM / tensor rooflines (SURVEY.md section 8d "N-independent serial part").
 #include "common.h"
@@ -19,13 +19,16 @@ namespace cg = cooperative_groups;
 
 namespace rt {
 
-constexpr int EB = 8;          // block size
-constexpr int EP = 2 * EB;     // pair size (16)
-constexpr int ELD = EP + 1;    // padded smem leading dim
+constexpr int EB = 16;         // block size
+constexpr int EP = 2 * EB;     // pair tile edge (32)
+constexpr int ELD = EP + 2;    // padded smem leading dim (even: 16-byte aligned rows for LDS.128)
 constexpr int kMaxProblems = 4;
-constexpr int kEigThreads = 512;
+constexpr int kEigThreads = 256;
 constexpr int kEigWarps = kEigThreads / 32;
-constexpr int kMaxSweeps = 16;
+constexpr int kMaxSweeps = 20;
+constexpr int kScaleSlot = 1 + kMaxSweeps;   // scal[kScaleSlot] = max |a_ij| (positive doubles order like uint64)
+constexpr int kPermSlot = 2 + kMaxSweeps;    // scal[kPermSlot + i] = rank of eigenvalue i
+static_assert(EP == 32, "phase B register blocking (4 rows x 8 cols per lane) assumes 32x32 tiles");
 
 struct EigProblem {
   const double* A_in;  // [n][n] dense symmetric
@@ -35,13 +38,14 @@ struct EigProblem {
   double* Vp;          // [np][np]
   double* J;           // [npairs][EP*EP]
   int* skip;           // [npairs]
-  double* scal;        // [0]=norm2, [1+sweep]=off2 of that sweep
+  double* scal;        // [0]=norm2, [1+sweep]=off2 of that sweep, scale, permutation
   int n, np, nb, npairs;
 };
 
 struct EigBatch {
   EigProblem p[kMaxProblems];
   int count;
+  long long* prof;   // optional [gridDim][4] cycle counters: phase A, sync, phase B, sync
 };
 
 // round-robin tournament (circle method) on nb (even) players: pair k of round t
@@ -52,74 +56,115 @@ __device__ __forceinline__ void rr_pair(int nb, int t, int k, int& bi, int& bj) 
   if (bi > bj) { const int x = bi; bi = bj; bj = x; }
 }
 
-__device__ __forceinline__ int pair_index(int bi, int bj, int i) {  // i in [0,16)
+__device__ __forceinline__ int pair_index(int bi, int bj, int i) {  // i in [0, EP)
   return (i < EB) ? bi * EB + i : bj * EB + (i - EB);
 }
 
-// One warp diagonalises the symmetric 16x16 matrix S (smem, ld ELD); Q accumulates rotations.
-__device__ void warp_jacobi16(double* S, double* Q, double* cs, int lane) {
-  for (int e = lane; e < EP * EP; e += 32) Q[(e / EP) * ELD + (e % EP)] = (e / EP == e % EP) ? 1.0 : 0.0;
-  __syncwarp();
-  for (int sweep = 0; sweep < 10; ++sweep) {
-    double off = 0.0, dg = 0.0;
-    for (int e = lane; e < EP * EP; e += 32) {
-      const int i = e / EP, j = e % EP;
-      const double v = S[i * ELD + j];
-      if (i == j) dg += v * v; else off += v * v;
+// Rotation parameters for the pivot (app, aqq, apq).  The ANGLE is evaluated in fp32 (MUFU + FFMA,
+// a short dependent chain); (c, s) is then re-normalised in fp64 so the rotation is orthogonal to
+// ~1e-21.  An fp32-accurate angle leaves a residual of ~1e-7 |apq| instead of an exact zero, which only
+// replaces the last quadratic step of the Jacobi iteration by one more sweep.
+__device__ __forceinline__ void rotation(double app, double aqq, double apq, double& c, double& s) {
+  c = 1.0;
+  s = 0.0;
+  if (apq * apq > 1e-34) {   // entries are scaled to <= 1: keeps the fp32 chain inside float range
+    const float d = (float)(aqq - app), a = (float)apq;
+    // tan(2 theta) = 2 apq / d:  cos(2 theta) = |d| / h,  h = sqrt(d^2 + 4 apq^2)
+    const float x = fmaf(d, d, 4.0f * a * a);
+    const float rh = rsqrtf(x);
+    const float y = fmaf(0.5f * fabsf(d), rh, 0.5f);       // cos^2(theta) in [0.5, 1]
+    const float ry = rsqrtf(y);
+    const double c0 = (double)(y * ry);
+    const double s0 = (double)((d >= 0.0f ? a : -a) * rh * ry);   // sin(theta) = sin(2 theta) / (2 cos(theta))
+    const double e = fma(c0, c0, fma(s0, s0, -1.0));       // c0^2 + s0^2 - 1 ~ 1e-7
+    const double f = fma(e, fma(e, 0.375, -0.5), 1.0);     // (1 + e)^(-1/2) to O(e^3)
+    c = c0 * f;
+    s = s0 * f;
+  }
+}
+
+struct VisitSmem {
+  double* S;      // [EP][ELD] tile
+  double* Q;      // [EP][ELD] accumulated rotations
+  double* cs;     // [2][EB][2]  (c, s), double buffered over inner rounds
+  int* pq;        // [2][EB][2]  (p, q)
+};
+
+__device__ __forceinline__ void set_pairs(const VisitSmem& m, int buf, int t, bool intra_pass) {
+  const int tid = threadIdx.x;
+  if (tid < EB) {
+    int p, q;
+    if (intra_pass) {
+      rr_pair(EB, t, tid % (EB / 2), p, q);
+      const int o = (tid < EB / 2) ? 0 : EB;
+      p += o; q += o;
+    } else {
+      p = tid;
+      q = EB + (tid + t) % EB;
     }
-    off = rt::warp_sum(off);
-    dg = rt::warp_sum(dg);
-    if (off <= 1e-30 * dg || off == 0.0) break;
-    for (int t = 0; t < EP - 1; ++t) {
-      if (lane < EP / 2) {
-        int p, q;
-        rr_pair(EP, t, lane, p, q);
-        const double apq = S[p * ELD + q];
-        double c = 1.0, s = 0.0;
-        if (apq != 0.0) {
-          const double tau = (S[q * ELD + q] - S[p * ELD + p]) / (2.0 * apq);
-          const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + tt * tt);
-          s = tt * c;
-        }
-        cs[lane * 4 + 0] = c;
-        cs[lane * 4 + 1] = s;
-        cs[lane * 4 + 2] = (double)p;
-        cs[lane * 4 + 3] = (double)q;
-      }
-      __syncwarp();
-      // two-sided update, 64 independent 2x2 blocks, 2 per lane
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int blk = lane + 32 * h;
-        const int k = blk >> 3, l = blk & 7;
-        const double ck = cs[k * 4], sk = cs[k * 4 + 1];
-        const int p = (int)cs[k * 4 + 2], q = (int)cs[k * 4 + 3];
-        const double cl = cs[l * 4], sl = cs[l * 4 + 1];
-        const int u = (int)cs[l * 4 + 2], v = (int)cs[l * 4 + 3];
-        const double m00 = S[p * ELD + u], m01 = S[p * ELD + v];
-        const double m10 = S[q * ELD + u], m11 = S[q * ELD + v];
-        const double t00 = ck * m00 - sk * m10, t01 = ck * m01 - sk * m11;
-        const double t10 = sk * m00 + ck * m10, t11 = sk * m01 + ck * m11;
-        double n00 = cl * t00 - sl * t01, n01 = sl * t00 + cl * t01;
-        double n10 = cl * t10 - sl * t11, n11 = sl * t10 + cl * t11;
-        if (k == l) { n01 = 0.0; n10 = 0.0; }
-        S[p * ELD + u] = n00; S[p * ELD + v] = n01;
-        S[q * ELD + u] = n10; S[q * ELD + v] = n11;
-      }
-      // Q <- Q R : 16 rows x 8 pairs, 4 per lane
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const int it = lane + 32 * h;
-        const int row = it >> 3, l = it & 7;
-        const double cl = cs[l * 4], sl = cs[l * 4 + 1];
-        const int u = (int)cs[l * 4 + 2], v = (int)cs[l * 4 + 3];
-        const double qu = Q[row * ELD + u], qv = Q[row * ELD + v];
-        Q[row * ELD + u] = cl * qu - sl * qv;
-        Q[row * ELD + v] = sl * qu + cl * qv;
-      }
-      __syncwarp();
+    m.pq[(buf * EB + tid) * 2 + 0] = p;
+    m.pq[(buf * EB + tid) * 2 + 1] = q;
+    double c, s;
+    rotation(m.S[p * ELD + p], m.S[q * ELD + q], m.S[p * ELD + q], c, s);
+    m.cs[(buf * EB + tid) * 2 + 0] = c;
+    m.cs[(buf * EB + tid) * 2 + 1] = s;
+  }
+}
+
+// S <- R^T S R for the EB disjoint rotations of buffer `buf` (one 2x2 block per thread)
+__device__ __forceinline__ void update_S(const VisitSmem& m, int buf) {
+  const double* cs = m.cs + buf * EB * 2;
+  const int* pq = m.pq + buf * EB * 2;
+  for (int blk = threadIdx.x; blk < EB * EB; blk += kEigThreads) {
+    const int k = blk / EB, l = blk % EB;
+    const double ck = cs[k * 2], sk = cs[k * 2 + 1], cl = cs[l * 2], sl = cs[l * 2 + 1];
+    const int p = pq[k * 2], q = pq[k * 2 + 1], u = pq[l * 2], v = pq[l * 2 + 1];
+    const double m00 = m.S[p * ELD + u], m01 = m.S[p * ELD + v];
+    const double m10 = m.S[q * ELD + u], m11 = m.S[q * ELD + v];
+    const double t00 = ck * m00 - sk * m10, t01 = ck * m01 - sk * m11;
+    const double t10 = sk * m00 + ck * m10, t11 = sk * m01 + ck * m11;
+    m.S[p * ELD + u] = cl * t00 - sl * t01; m.S[p * ELD + v] = sl * t00 + cl * t01;
+    m.S[q * ELD + u] = cl * t10 - sl * t11; m.S[q * ELD + v] = sl * t10 + cl * t11;
+  }
+}
+
+__device__ __forceinline__ void update_Q(const VisitSmem& m, int buf, int first_thread) {
+  const double* cs = m.cs + buf * EB * 2;
+  const int* pq = m.pq + buf * EB * 2;
+  const int nthr = kEigThreads - first_thread;
+  for (int it = threadIdx.x - first_thread; it < EP * EB; it += nthr) {
+    if (it < 0) break;
+    const int row = it / EB, l = it % EB;
+    const double cl = cs[l * 2], sl = cs[l * 2 + 1];
+    const int u = pq[l * 2], v = pq[l * 2 + 1];
+    const double qu = m.Q[row * ELD + u], qv = m.Q[row * ELD + v];
+    m.Q[row * ELD + u] = cl * qu - sl * qv;
+    m.Q[row * ELD + v] = sl * qu + cl * qv;
+  }
+}
+
+// One visit of a block pair by the whole CTA: (first round of a sweep only) one cyclic pass over the
+// pairs INSIDE each of the two blocks, then one pass over the EB*EB cross pairs, as rounds of EB
+// disjoint rotations.  Over a sweep every index pair of the matrix is rotated exactly once: this is
+// cyclic Jacobi whose rotations are applied to the rest of the matrix tile-wise in phase B.
+// Pipeline per inner round: [S update] | sync | [warp 0: next rotations  ||  warps 1..: Q update] | sync.
+__device__ void cta_visit(const VisitSmem& m, bool intra) {
+  const int tid = threadIdx.x;
+  for (int e = tid; e < EP * EP; e += kEigThreads) m.Q[(e / EP) * ELD + (e % EP)] = (e / EP == e % EP) ? 1.0 : 0.0;
+  const int n_intra = intra ? EB - 1 : 0;
+  const int total = n_intra + EB;
+  set_pairs(m, 0, 0, n_intra > 0);
+  __syncthreads();
+  for (int r = 0; r < total; ++r) {
+    const int buf = r & 1;
+    update_S(m, buf);
+    __syncthreads();
+    if (r + 1 < total) {
+      const int rn = r + 1;
+      if (tid < 32) set_pairs(m, buf ^ 1, rn < n_intra ? rn : rn - n_intra, rn < n_intra);
     }
+    update_Q(m, buf, 32);
+    __syncthreads();
   }
 }
 
@@ -132,19 +177,32 @@ eig_block_jacobi_kernel(EigBatch batch) {
   const int nwarps = gridDim.x * kEigWarps;
   const int gtid = blockIdx.x * kEigThreads + threadIdx.x;
   const int nthreads = gridDim.x * kEigThreads;
-  double* T = esm + warp * (3 * EP * ELD + 32);  // per-warp: T, Qk, Ql, cs
+  double* T = esm + warp * (3 * EP * ELD + 4 * EB);  // per-warp: T, Qk, Ql, cs
   double* Qk = T + EP * ELD;
   double* Ql = Qk + EP * ELD;
-  double* cs = Ql + EP * ELD;
+  __shared__ double red[kEigWarps];
 
-  // ---- phase 0: padded copies, V = I, norms ----
+  // ---- phase 0: scale factor, padded copies, V = I, norms ----
   for (int pi = 0; pi < batch.count; ++pi) {
     const EigProblem& P = batch.p[pi];
+    double m = 0.0;
+    for (int e = gtid; e < P.n * P.n; e += nthreads) m = fmax(m, fabs(P.A_in[e]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m > 0.0)
+      atomicMax(reinterpret_cast<unsigned long long*>(&P.scal[kScaleSlot]),
+                (unsigned long long)__double_as_longlong(m));
+  }
+  grid.sync();
+  for (int pi = 0; pi < batch.count; ++pi) {
+    const EigProblem& P = batch.p[pi];
+    const double amax = P.scal[kScaleSlot];
+    const double inv_scale = amax > 0.0 ? 1.0 / amax : 1.0;
     double loc = 0.0;
     for (int e = gtid; e < P.np * P.np; e += nthreads) {
       const int i = e / P.np, j = e - i * P.np;
       double v = 0.0;
-      if (i < P.n && j < P.n) v = 0.5 * (P.A_in[(int64_t)i * P.n + j] + P.A_in[(int64_t)j * P.n + i]);
+      if (i < P.n && j < P.n) v = 0.5 * inv_scale * (P.A_in[(int64_t)i * P.n + j] + P.A_in[(int64_t)j * P.n + i]);
       P.Ap[e] = v;
       P.Vp[e] = (i == j) ? 1.0 : 0.0;
       loc += v * v;
@@ -157,52 +215,63 @@ eig_block_jacobi_kernel(EigBatch batch) {
   int max_rounds = 0;
   for (int pi = 0; pi < batch.count; ++pi) max_rounds = max(max_rounds, batch.p[pi].nb - 1);
   bool done[kMaxProblems];
-  for (int pi = 0; pi < kMaxProblems; ++pi) done[pi] = (pi >= batch.count) || (batch.p[pi].nb < 2);
+  for (int pi = 0; pi < kMaxProblems; ++pi) done[pi] = (pi >= batch.count);
 
+  long long tA = 0, tS1 = 0, tB = 0, tS2 = 0, t0 = 0, t1 = 0;
   for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
     bool all_done = true;
     for (int pi = 0; pi < batch.count; ++pi) all_done = all_done && done[pi];
     if (all_done) break;
     for (int round = 0; round < max_rounds; ++round) {
-      // ---- phase A: diagonalise pair sub-matrices ----
+      // ---- phase A: rotations of this round's block pairs ----
+      t0 = clock64();
       int base = 0;
       for (int pi = 0; pi < batch.count; ++pi) {
         const EigProblem& P = batch.p[pi];
         if (done[pi] || round >= P.nb - 1) continue;
-        for (int item = gwarp - base; item < P.npairs; item += nwarps) {
-          if (item < 0) continue;
+        // one pair per CTA (the whole CTA works on the visit; esm[0..] = warp 0's tile region)
+        for (int item = (int)((blockIdx.x + gridDim.x - base) % gridDim.x); item < P.npairs;
+             item += gridDim.x) {
           int bi, bj;
           rr_pair(P.nb, round, item, bi, bj);
           double off = 0.0;
-          for (int e = lane; e < EP * EP; e += 32) {
+          const bool intra = (round == 0);
+          double* S = esm;
+          double* Qm = esm + EP * ELD;
+          VisitSmem vm{S, Qm, esm + 2 * EP * ELD, reinterpret_cast<int*>(esm + 2 * EP * ELD + 4 * EB)};
+          for (int e = threadIdx.x; e < EP * EP; e += kEigThreads) {
             const int i = e / EP, j = e % EP;
             const double v = P.Ap[(int64_t)pair_index(bi, bj, i) * P.np + pair_index(bi, bj, j)];
-            T[i * ELD + j] = v;
-            if (i != j) off += v * v;  // whole pair sub-matrix: the diagonal blocks must end up diagonal too
+            S[i * ELD + j] = v;
+            const bool cross = (i < EB) != (j < EB);
+            if (cross || (intra && i != j)) off += v * v;
           }
           off = rt::warp_sum(off);
-          __syncwarp();
-          const bool skip = (off <= 1e-34 * P.scal[0]);
+          if (lane == 0) red[warp] = off;
+          __syncthreads();
+          off = 0.0;
+          for (int wq = 0; wq < kEigWarps; ++wq) off += red[wq];
+          const bool skip = (off <= 1e-30 * P.scal[0]);
           if (!skip) {
-            warp_jacobi16(T, Qk, cs, lane);
-            for (int e = lane; e < EP * EP; e += 32)
-              P.J[(int64_t)item * EP * EP + e] = Qk[(e / EP) * ELD + (e % EP)];
-            // the diagonal tile is now diag(T): write it here, phase B skips k == l
-            for (int e = lane; e < EP * EP; e += 32) {
+            cta_visit(vm, intra);
+            for (int e = threadIdx.x; e < EP * EP; e += kEigThreads) {
               const int i = e / EP, j = e % EP;
-              P.Ap[(int64_t)pair_index(bi, bj, i) * P.np + pair_index(bi, bj, j)] =
-                  (i == j) ? T[i * ELD + i] : 0.0;
+              P.J[(int64_t)item * EP * EP + e] = Qm[i * ELD + j];
+              // the pair's own tile is final for this round: phase B skips k == l
+              P.Ap[(int64_t)pair_index(bi, bj, i) * P.np + pair_index(bi, bj, j)] = S[i * ELD + j];
             }
           }
-          if (lane == 0) {
+          if (threadIdx.x == 0) {
             P.skip[item] = skip ? 1 : 0;
             if (off != 0.0) atomicAdd(&P.scal[1 + sweep], off);
           }
-          __syncwarp();
+          __syncthreads();
         }
-        base = (base + P.npairs) % nwarps;
+        base = (base + P.npairs) % gridDim.x;
       }
+      t1 = clock64(); tA += t1 - t0;
       grid.sync();
+      t0 = clock64(); tS1 += t0 - t1;
       // ---- phase B: A_kl <- Q_k^T A_kl Q_l (k != l),  V[:, l] <- V[:, l] Q_l ----
       base = 0;
       for (int pi = 0; pi < batch.count; ++pi) {
@@ -210,8 +279,8 @@ eig_block_jacobi_kernel(EigBatch batch) {
         if (done[pi] || round >= P.nb - 1) continue;
         const int nA = P.npairs * P.npairs;
         const int nV = (P.np / EP) * P.npairs;
-        for (int item = gwarp - base; item < nA + nV; item += nwarps) {
-          if (item < 0) continue;
+        for (int item = (int)((blockIdx.x + gridDim.x * warp + nwarps - base) % nwarps); item < nA + nV;
+             item += nwarps) {
           const bool isV = item >= nA;
           int k, l;
           if (isV) { k = (item - nA) / P.npairs; l = (item - nA) % P.npairs; }
@@ -232,47 +301,89 @@ eig_block_jacobi_kernel(EigBatch batch) {
             if (!isV) Qk[i * ELD + j] = sk ? (i == j ? 1.0 : 0.0) : P.J[(int64_t)k * EP * EP + e];
           }
           __syncwarp();
-          // X = T Ql : lane -> row i = lane/2, cols (lane&1)*8 .. +7
-          const int i = lane >> 1, j0 = (lane & 1) * 8;
-          double x[8];
+          // register-blocked 32x32x32 products: lane -> rows 4*ri..+3, cols 8*cj..+7
+          const int ri = lane >> 2, cj = lane & 3;
+          double x[4][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = 0.0;
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[r][j] = 0.0;
+          // X = T Ql
+#pragma unroll 4
           for (int m = 0; m < EP; ++m) {
-            const double tv = T[i * ELD + m];
+            double a[4], bq[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = fma(tv, Ql[m * ELD + j0 + j], x[j]);
+            for (int r = 0; r < 4; ++r) a[r] = T[(4 * ri + r) * ELD + m];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              const double2 v = *reinterpret_cast<const double2*>(&Ql[m * ELD + 8 * cj + j]);
+              bq[j] = v.x; bq[j + 1] = v.y;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[r][j] = fma(a[r], bq[j], x[r][j]);
           }
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) T[i * ELD + j0 + j] = x[j];
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 8; j += 2)
+              *reinterpret_cast<double2*>(&T[(4 * ri + r) * ELD + 8 * cj + j]) = make_double2(x[r][j], x[r][j + 1]);
           __syncwarp();
           if (!isV) {  // Y = Qk^T X
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = 0.0;
-            for (int m = 0; m < EP; ++m) {
-              const double qv = Qk[m * ELD + i];
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-              for (int j = 0; j < 8; ++j) x[j] = fma(qv, T[m * ELD + j0 + j], x[j]);
+              for (int j = 0; j < 8; ++j) x[r][j] = 0.0;
+#pragma unroll 4
+            for (int m = 0; m < EP; ++m) {
+              double a[4], bq[8];
+#pragma unroll
+              for (int r = 0; r < 4; r += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&Qk[m * ELD + 4 * ri + r]);
+                a[r] = v.x; a[r + 1] = v.y;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(&T[m * ELD + 8 * cj + j]);
+                bq[j] = v.x; bq[j + 1] = v.y;
+              }
+#pragma unroll
+              for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[r][j] = fma(a[r], bq[j], x[r][j]);
             }
           }
-          const int gi = isV ? k * EP + i : pair_index(bik, bjk, i);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) M[(int64_t)gi * P.np + pair_index(bil, bjl, j0 + j)] = x[j];
+          for (int r = 0; r < 4; ++r) {
+            const int i = 4 * ri + r;
+            const int gi = isV ? k * EP + i : pair_index(bik, bjk, i);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) M[(int64_t)gi * P.np + pair_index(bil, bjl, 8 * cj + j)] = x[r][j];
+          }
           __syncwarp();
         }
         base = (base + nA + nV) % nwarps;
       }
+      t1 = clock64(); tB += t1 - t0;
       grid.sync();
+      t0 = clock64(); tS2 += t0 - t1;
     }
     // convergence: off-diagonal mass seen during this sweep (uniform decision: same memory, after sync)
     for (int pi = 0; pi < batch.count; ++pi) {
       if (done[pi]) continue;
       const EigProblem& P = batch.p[pi];
       const double off2 = P.scal[1 + sweep], n2 = P.scal[0];
-      if (off2 <= 1e-28 * n2) done[pi] = true;
+      // mass seen (before annihilation) below 1e-7 ||A||: the rotations of this sweep leave ~1e-14
+      if (off2 <= 1e-14 * n2) done[pi] = true;
     }
   }
 
+  if (batch.prof && threadIdx.x == 0) {
+    batch.prof[blockIdx.x * 4 + 0] = tA; batch.prof[blockIdx.x * 4 + 1] = tS1;
+    batch.prof[blockIdx.x * 4 + 2] = tB; batch.prof[blockIdx.x * 4 + 3] = tS2;
+  }
   // ---- final: sort eigenvalues descending, emit w and V ----
   for (int pi = 0; pi < batch.count; ++pi) {
     const EigProblem& P = batch.p[pi];
@@ -283,8 +394,8 @@ eig_block_jacobi_kernel(EigBatch batch) {
         const double dj = P.Ap[(int64_t)j * P.np + j];
         rank += (dj > di) || (dj == di && j < i);
       }
-      P.w[rank] = di;
-      P.scal[1 + kMaxSweeps + i] = (double)rank;  // reuse scal tail as the permutation
+      P.w[rank] = di * P.scal[kScaleSlot];
+      P.scal[kPermSlot + i] = (double)rank;
     }
   }
   grid.sync();
@@ -292,7 +403,7 @@ eig_block_jacobi_kernel(EigBatch batch) {
     const EigProblem& P = batch.p[pi];
     for (int e = gtid; e < P.n * P.n; e += nthreads) {
       const int i = e / P.n, j = e - i * P.n;
-      const int rank = (int)P.scal[1 + kMaxSweeps + j];
+      const int rank = (int)P.scal[kPermSlot + j];
       P.V_out[(int64_t)i * P.n + rank] = P.Vp[(int64_t)i * P.np + j];
     }
   }
@@ -315,7 +426,7 @@ EigLayout eig_layout(int n) {
   L.off_Vp = o; o += align_up(sizeof(double) * L.np * L.np, 256);
   L.off_J = o; o += align_up(sizeof(double) * L.npairs * EP * EP, 256);
   L.off_skip = o; o += align_up(sizeof(int) * L.npairs, 256);
-  L.off_scal = o; o += align_up(sizeof(double) * (1 + kMaxSweeps + L.np), 256);
+  L.off_scal = o; o += align_up(sizeof(double) * (kPermSlot + L.np), 256);
   L.total = o;
   return L;
 }
@@ -323,11 +434,14 @@ EigLayout eig_layout(int n) {
 size_t eig_ws_bytes(int n) { return eig_layout(n).total; }
 
 // Solve `count` (<= 4) independent problems in one cooperative launch.
+long long* g_eig_prof = nullptr;   // set through rt_eigh_set_profile (debug)
+
 int eig_batch(int count, const double* const* A, const int* n, double* const* w, double* const* V,
               void* const* ws, cudaStream_t s) {
   RT_REQUIRE(count >= 1 && count <= kMaxProblems, "eig_batch: count=%d out of range", count);
   EigBatch b{};
   b.count = count;
+  b.prof = g_eig_prof;
   int total_items = 0;
   for (int i = 0; i < count; ++i) {
     RT_REQUIRE(n[i] >= 1 && n[i] <= 1024, "eig_batch: n=%d out of range", n[i]);
@@ -341,23 +455,26 @@ int eig_batch(int count, const double* const* A, const int* n, double* const* w,
     P.skip = (int*)(base + L.off_skip);
     P.scal = (double*)(base + L.off_scal);
     P.n = n[i]; P.np = L.np; P.nb = L.nb; P.npairs = L.npairs;
-    RT_CHECK_CUDA(cudaMemsetAsync(P.scal, 0, sizeof(double) * (1 + kMaxSweeps + L.np), s));
+    RT_CHECK_CUDA(cudaMemsetAsync(P.scal, 0, sizeof(double) * (kPermSlot + L.np), s));
     total_items += L.npairs * L.npairs + (L.np / EP) * L.npairs;
   }
-  const size_t smem = (size_t)kEigWarps * (3 * EP * ELD + 32) * sizeof(double);
+  const size_t smem = (size_t)kEigWarps * (3 * EP * ELD + 4 * EB) * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     RT_CHECK_CUDA(cudaFuncSetAttribute(eig_block_jacobi_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  int grid = cdiv(total_items, kEigWarps);
-  const int max_grid = sm_count();  // 1 CTA / SM (launch bounds) => co-resident
+  // one warp per phase-B tile if possible (latency matters more than occupancy), capped at 1 CTA / SM
+  // (launch bounds) so the cooperative grid is co-resident
+  int grid = total_items;
+  const int max_grid = sm_count();
   if (grid > max_grid) grid = max_grid;
   if (grid < 1) grid = 1;
   void* args[] = {(void*)&b};
   RT_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)eig_block_jacobi_kernel, dim3(grid),
                                             dim3(kEigThreads), args, smem, s));
+  ++g_launches;
   return 0;
 }
 
@@ -373,3 +490,6 @@ extern "C" int rt_eigh(double* A, int n, double* w, double* V, void* ws, void* s
   void* wss[1] = {ws};
   return rt::eig_batch(1, Ain, &n, wo, Vo, wss, (cudaStream_t)stream);
 }
+
+// Debug: cycle counters per CTA ([grid][4] int64: phase A, sync, phase B, sync), NULL to disable.
+extern "C" int rt_eigh_set_profile(long long* dev_buf) { rt::g_eig_prof = dev_buf; return 0; }

@@ -95,7 +95,8 @@ struct Ctx {
     }
     dim3 grid(cdiv(g.m, GT), cdiv(g.n, GT), g.ksplit > 1 ? g.ksplit : g.batch);
     gemm64_kernel<<<grid, 256, 0, s>>>(g);
-    if (g.ksplit > 1) gemm64_reduce_kernel<<<cdiv(g.m * g.n, 256), 256, 0, s>>>(g);
+    ++rt::g_launches;
+    if (g.ksplit > 1) { gemm64_reduce_kernel<<<cdiv(g.m * g.n, 256), 256, 0, s>>>(g); ++rt::g_launches; }
     if (cudaGetLastError() != cudaSuccess) err = 1;
   }
 
@@ -160,25 +161,25 @@ struct Ctx {
   void to64(const float* x, double* y, int64_t n) {
     if (err) return;
     int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
-    f32_to_f64_kernel<<<blocks, 256, 0, s>>>(x, y, n);
+    f32_to_f64_kernel<<<blocks, 256, 0, s>>>(x, y, n); ++rt::g_launches;
   }
   void to32(const double* x, float* y, int64_t n, double a_host, const double* a_dev) {
     if (err) return;
     int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
-    f64_to_f32_scaled_kernel<<<blocks, 256, 0, s>>>(x, y, n, a_host, a_dev);
+    f64_to_f32_scaled_kernel<<<blocks, 256, 0, s>>>(x, y, n, a_host, a_dev); ++rt::g_launches;
   }
   void axpby(const double* x, const double* y, double* z, int64_t n, double a, const double* a_dev,
              double b, const double* b_dev) {
     if (err) return;
     int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
-    axpby64_kernel<<<blocks, 256, 0, s>>>(x, y, z, n, a, a_dev, b, b_dev);
+    axpby64_kernel<<<blocks, 256, 0, s>>>(x, y, z, n, a, a_dev, b, b_dev); ++rt::g_launches;
   }
   template <typename TA, typename TB>
   void dot(const TA* x, const TB* y, int64_t n, double scale, double* out, int accumulate) {
     if (err) return;
     int blocks = (int)((n + 255) / 256); if (blocks > kDotBlocks) blocks = kDotBlocks; if (blocks < 1) blocks = 1;
     dot_partial_kernel<TA, TB><<<blocks, 256, 0, s>>>(x, y, n, p(L.dot_partial));
-    dot_final_kernel<<<1, 32, 0, s>>>(p(L.dot_partial), blocks, scale, out, accumulate);
+    dot_final_kernel<<<1, 32, 0, s>>>(p(L.dot_partial), blocks, scale, out, accumulate); rt::g_launches += 2;
   }
   int spd(const SpdBatch& b, int count, int nmax) {
     const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + nmax) * sizeof(double);
@@ -189,7 +190,7 @@ struct Ctx {
         rt::set_error("small stage: cannot raise shared memory to %zu", smem); return 1; }
       configured = smem;
     }
-    spd_factor_kernel<<<count, 1024, smem, s>>>(b);
+    spd_factor_kernel<<<count, 1024, smem, s>>>(b); ++rt::g_launches;
     return 0;
   }
 };
@@ -283,7 +284,7 @@ extern "C" int rt_small_grad(const float* core, const float* d_core, const float
   cudaStream_t s = c.s;
   {
     int blocks = (int)((c.L.c + 255) / 256); if (blocks > 1184) blocks = 1184;
-    grad_core_kernel<<<blocks, 256, 0, s>>>(d_core, core, hyper, dS_g, c.L.c);
+    grad_core_kernel<<<blocks, 256, 0, s>>>(d_core, core, hyper, dS_g, c.L.c); ++rt::g_launches;
   }
   // loss_total = bce_sum * inv_count + reg * ||core||^2
   c.axpby(bce_sum, c.p(c.L.coresq), loss_total, 1, inv_count, nullptr, 1.0, hyper + 1);
@@ -329,7 +330,7 @@ extern "C" int rt_small_norm(const float* dS_g, const double* gram_R, const doub
   c.dot<double, double>(gram_R, c.p(c.L.Gm[0]), (int64_t)r0 * r0, 1.0, sq, 1);
   c.dot<double, double>(gram_S, c.p(c.L.Gm[1]), (int64_t)r1 * r1, 1.0, sq, 1);
   if (!sym) c.dot<double, double>(gram_O, c.p(c.L.Gm[2]), (int64_t)r2 * r2, 1.0, sq, 1);
-  norm_finish_kernel<<<1, 32, 0, c.s>>>(sq, hyper, norm_out, alpha_out);
+  norm_finish_kernel<<<1, 32, 0, c.s>>>(sq, hyper, norm_out, alpha_out); ++rt::g_launches;
   return finish(c, "rt_small_norm");
 }
 
@@ -413,7 +414,7 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
   double* Cp = c.T(0);
   {
     int blocks = (int)((c.L.c + 255) / 256); if (blocks > 1184) blocks = 1184;
-    core_minus_lr_kernel<<<blocks, 256, 0, s>>>(core, dS_dir, lr, Cp, c.L.c);
+    core_minus_lr_kernel<<<blocks, 256, 0, s>>>(core, dS_dir, lr, Cp, c.L.c); ++rt::g_launches;
   }
   // Gamma_i = lr^2 Gram_i = L_i L_i^T ; R_i = L_i^T
   SpdBatch b{};
@@ -421,7 +422,7 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
   const int nm = sym ? 2 : 3;
   for (int i = 0; i < nm; ++i) {
     const int n2 = d[i] * d[i];
-    scale_mat_kernel<<<cdiv(n2, 256), 256, 0, s>>>(gram[i], c.p(c.L.Gs[i]), n2, 1.0, lr, 1);
+    scale_mat_kernel<<<cdiv(n2, 256), 256, 0, s>>>(gram[i], c.p(c.L.Gs[i]), n2, 1.0, lr, 1); ++rt::g_launches;
     b.p[i].G = c.p(c.L.Gs[i]); b.p[i].L = c.p(c.L.GL[i]); b.p[i].Linv = c.p(c.L.GLinv[i]);
     b.p[i].Ginv = nullptr; b.p[i].n = d[i];
     nmax = d[i] > nmax ? d[i] : nmax;
@@ -443,7 +444,7 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
       if (j != i) c.unfold_gram(i, Bk[j], d, Bk[j], d[i], Nn[i], n, 1.0, 1.0);
     c.unfold_gram(i, Bk[i], d, Cp, d[i], Nn[i] + (int64_t)d[i] * n, n, 1.0, 0.0);
     c.unfold_gram(i, Bk[i], d, Bk[i], d[i], Nn[i] + (int64_t)d[i] * n + d[i], n, 1.0, 0.0);
-    symmetrize_lower_kernel<<<cdiv(n * n, 256), 256, 0, s>>>(Nn[i], n);
+    symmetrize_lower_kernel<<<cdiv(n * n, 256), 256, 0, s>>>(Nn[i], n); ++rt::g_launches;
   }
   if (sym) c.axpby(Nn[1], Nn[2], Nn[1], 4 * (int64_t)d[1] * d[1], 1.0, nullptr, 1.0, nullptr);
   if (c.err) return finish(c, "rt_small_retract");

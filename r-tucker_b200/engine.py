@@ -16,6 +16,7 @@ r-sized objects are replicated; the only exchanges are all-reduces of [B,r] row 
 scalar and r x r Gram matrices.  ``ops`` is injectable so the sharding logic can be exercised on CPU
 (gloo) by the tests with the oracle's arithmetic; the product always uses the CUDA ops.
 """
+from contextlib import contextmanager
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -53,6 +54,9 @@ class StepEngine:
         self.core = core
         self.sym = bool(sym)
         self.params = list(factors)
+        for prm in [core] + self.params:      # torch.linalg.qr returns column-major Q: kernels want row-major
+            if not prm.data.is_contiguous():
+                prm.data = prm.data.contiguous()
         self.nf = len(self.params)            # 3 (asym) or 2 (sym)
         self.rank = tuple(core.shape)
         self.B = int(batch_size)
@@ -80,6 +84,23 @@ class StepEngine:
         self.loss = None
 
     # -------------------------------------------------------------------------------------------
+    @contextmanager
+    def _stage(self, name):
+        """Optional CUDA-event bracket around a stage (bench.py sets ``self.timers = {}``)."""
+        if getattr(self, "timers", None) is None:
+            yield
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        self.timers.setdefault(name, []).append((e0, e1))
+
+    def stage_ms(self):
+        """Mean milliseconds per call of every bracketed stage (synchronises)."""
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in (self.timers or {}).items()}
+
     def _set_hyper(self, lr, reg, beta, normalize):
         vals = (float(lr), float(reg), float(beta or 0.0), float(normalize or 0.0))
         if vals != self._hyper_vals:
@@ -115,26 +136,33 @@ class StepEngine:
         B = rel_idx.shape[0]
         self._set_hyper(self._hyper_vals[0] if self._hyper_vals else lr_hint, reg, self.beta,
                         normalize_grad if normalize_grad else 0.0)
-        small.prepare(core)
+        with self._stage("small_prepare"):
+            small.prepare(core)
         R, S, O = self._U(0), self._U(1), self._obj()
-        r_rows = ops.gather_rows(R, rel_idx)
-        s_rows = ops.gather_rows(S, sub_idx, self.n_begin)
-        self._allreduce(s_rows)
-        q = ops.query_fwd(core, r_rows, s_rows)
-        qp = small.rows_times_ainv(q, 2)
+        with self._stage("query_fwd"):
+            r_rows = ops.gather_rows(R, rel_idx)
+            s_rows = ops.gather_rows(S, sub_idx, self.n_begin)
+            self._allreduce(s_rows)
+            q = ops.query_fwd(core, r_rows, s_rows)
+            qp = small.rows_times_ainv(q, 2)
         # dO' = G^T (q A_O) lands directly in the object factor's scratch buffer
         k_obj = 2 if not sym else 1
         dOp = self.spare[k_obj]
         bce_sum = torch.empty(1, dtype=f64, device=self.dev)
         H = torch.empty(B, r2, dtype=core.dtype, device=self.dev)
-        ops.score_bce_fwd_bwd(q, qp, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
-                              b_total=B, n_begin=self.n_begin, variant=self.score_variant,
-                              out=(bce_sum, H, dOp))
+        with self._stage("score_bce_fwd_bwd"):
+            ops.score_bce_fwd_bwd(q, qp, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
+                                  b_total=B, n_begin=self.n_begin, variant=self.score_variant,
+                                  out=(bce_sum, H, dOp))
         self._allreduce(H, bce_sum)
-        d_core, ds_rows, dr_rows = ops.query_bwd(core, r_rows, s_rows, H)
+        with self._stage("query_bwd"):
+            d_core, ds_rows, dr_rows = ops.query_bwd(core, r_rows, s_rows, H)
         inv_count = 1.0 / (float(B) * float(self.n_total))
-        dS_g, loss, drA, dsA, P_R, P_S, P_O = small.grad(core, d_core, qp, H, r_rows, s_rows, dr_rows,
-                                                         ds_rows, bce_sum, inv_count, self.hyper)
+        with self._stage("small_grad"):
+            dS_g, loss, drA, dsA, P_R, P_S, P_O = small.grad(core, d_core, qp, H, r_rows, s_rows, dr_rows,
+                                                             ds_rows, bce_sum, inv_count, self.hyper)
+        t_tall = self._stage("tall_skinny_fit")
+        t_tall.__enter__()
         # ---- factor parts of the Riemannian gradient: dV_i = g_i A_i - U_i (U_i^T g_i A_i) ----
         dV_g = [None] * self.nf
         dV_g[0] = ops.apply(self.spare[0], None, None, [(R, P_R)])
@@ -159,8 +187,9 @@ class StepEngine:
                 Mk = torch.cat([ops.gram(self._U(k), self.U_old[k]), ops.gram(self._U(k), self.dV_dir[k])], dim=1)
                 M.append(Mk.contiguous())
             self._allreduce(*[M[k] for k in self._entity_factor_ids()])
-            pS_beta, K, L = small.project(core, self.core_old, self.dS_dir_old, M[0], M[1],
-                                          M[2] if not sym else M[1], self.hyper)
+            with self._stage("small_project"):
+                pS_beta, K, L = small.project(core, self.core_old, self.dS_dir_old, M[0], M[1],
+                                              M[2] if not sym else M[1], self.hyper)
             dS_dir = ops.core_axpby(dS_g, alpha, pS_beta)
             for k in range(self.nf):
                 rk = self.rank[k]
@@ -170,6 +199,7 @@ class StepEngine:
             dS_dir = ops.core_axpby(dS_g, alpha, None)
             for k in range(self.nf):
                 ops.apply(dV_new[k], dV_g[k], alpha, [])
+        t_tall.__exit__(None, None, None)
         self.pending = (dS_dir, dV_new)
         self.loss = loss
         self.rgrad_norm = norm
@@ -185,14 +215,17 @@ class StepEngine:
         dS_dir, dV = self.pending
         core = self.core.data
         # exact fp64 Gram: it feeds the Cholesky that stands in for the reference's QR of [U | W]
-        grams = [ops.gram(v, v, precise=True) for v in dV]
+        with self._stage("retract_gram"):
+            grams = [ops.gram(v, v, precise=True) for v in dV]
         self._allreduce(*[grams[k] for k in self._entity_factor_ids()])
-        core_new, Z1, Z2 = small.retract(core, dS_dir, grams[0], grams[1], grams[2] if not sym else grams[1],
-                                         self.hyper)
+        with self._stage("small_retract_hosvd"):
+            core_new, Z1, Z2 = small.retract(core, dS_dir, grams[0], grams[1],
+                                             grams[2] if not sym else grams[1], self.hyper)
         new_U = []
-        for k in range(self.nf):
-            # spare[k] held dV_g during fit(); it is free again now
-            new_U.append(ops.apply(self.spare[k], None, None, [(self._U(k), Z1[k]), (dV[k], Z2[k])]))
+        with self._stage("retract_apply"):
+            for k in range(self.nf):
+                # spare[k] held dV_g during fit(); it is free again now
+                new_U.append(ops.apply(self.spare[k], None, None, [(self._U(k), Z1[k]), (dV[k], Z2[k])]))
         # ---- rotate state: the current point becomes the "old" point of the kept direction ----
         keep = self.beta is not None
         for k in range(self.nf):

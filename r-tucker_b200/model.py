@@ -69,9 +69,9 @@ class AsymmetricRTuckER(_Base):
             xavier_normal_(self.R.weight)
             xavier_normal_(self.O.weight)
             with torch.no_grad():
-                self.S.weight.data = torch.linalg.qr(self.S.weight)[0]
-                self.O.weight.data = torch.linalg.qr(self.O.weight)[0]
-                self.R.weight.data = torch.linalg.qr(self.R.weight)[0]
+                self.S.weight.data = torch.linalg.qr(self.S.weight)[0].contiguous()
+                self.O.weight.data = torch.linalg.qr(self.O.weight)[0].contiguous()
+                self.R.weight.data = torch.linalg.qr(self.R.weight)[0].contiguous()
 
     def factor_params(self):
         """[R, S, O] in the manifold's mode order (train.py:41)."""
@@ -96,8 +96,8 @@ class SymmetricRTuckER(_Base):
             xavier_normal_(self.E.weight)
             xavier_normal_(self.R.weight)
             with torch.no_grad():
-                self.E.weight.data = torch.linalg.qr(self.E.weight)[0]
-                self.R.weight.data = torch.linalg.qr(self.R.weight)[0]
+                self.E.weight.data = torch.linalg.qr(self.E.weight)[0].contiguous()
+                self.R.weight.data = torch.linalg.qr(self.R.weight)[0].contiguous()
 
     def factor_params(self):
         return [self.R.weight, self.E.weight]
