@@ -216,6 +216,11 @@ int rt_small_retract(const float* core, const float* dS_dir,
 size_t rt_eigh_ws_bytes(int n);
 int rt_eigh(double* A, int n, double* w, double* V, void* ws, void* stream);
 
+/* Known-answer self test of the tcgen05 building blocks: D[128,N] = op(A) op(B)^T in TF32
+ * (a_mn/b_mn select MN-major operands given as [K][M] / [K][N]); used by tests/test_gpu_tc.py. */
+int rt_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn, int flags,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "rt_small_retract": (i32, [vp] * 6 + [i32, i32, i32, i32] + [vp] * 9),
     "rt_eigh_ws_bytes": (sz, [i32]),
     "rt_eigh": (i32, [vp, i32, vp, vp, vp, vp]),
+    "rt_tc_selftest": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
 }
 
 
