@@ -34,8 +34,11 @@ constexpr uint32_t GT_BYTES = (TB / 4) * CS_GT;        // 66048
 constexpr uint32_t HALF_BYTES = (KB / 4) * CS_ROW;     // 16512  (>= (TN/4)*CS_T = 16384)
 constexpr uint32_t STAGE_BYTES = 2 * HALF_BYTES;       // 33024
 constexpr uint32_t OFF_G = 0, OFF_GT = OFF_G + G_BYTES, OFF_STAGE = OFF_GT + GT_BYTES;
-constexpr uint32_t OFF_MASK = OFF_STAGE + 2 * STAGE_BYTES;
-constexpr uint32_t SMEM_BYTES = OFF_MASK + TB * 2 * 8;   // 199,680
+// GEMM1 phase: the whole Q chunk and O tile (all of K) are resident at once, over the G / G^T / stage
+// areas that are idle then: [0, FULL) = Q, [FULL, 2*FULL) = O, FULL = 64 chunks * CS_ROW (r2 <= 256)
+constexpr uint32_t FULL_BYTES = 50 * CS_ROW;             // r2 <= 200 on this path (103,200 B); wider ranks fall back
+constexpr uint32_t OFF_MASK = (OFF_STAGE + 2 * STAGE_BYTES > 2 * FULL_BYTES) ? OFF_STAGE + 2 * STAGE_BYTES : 2 * FULL_BYTES;
+constexpr uint32_t SMEM_BYTES = OFF_MASK + TB * 2 * 8;   // 208,448
 constexpr int HB_LD = 129;                                // epilogue transpose buffer [128][129] floats in the stage area
 static_assert(128 * HB_LD * 4 <= 2 * STAGE_BYTES, "transpose buffer must fit in the stage area");
 constexpr uint32_t TM_D3 = 0, TM_Z = 256, TM_D2 = 256;
@@ -47,43 +50,98 @@ struct TcArgs {
   float t_pos, t_neg, inv_count;
   double* loss_partial; float* H_ws; float* dO;
   int n_tiles, r2p;
+  long long* prof;   // optional [grid][12] cycle counters per phase (debug)
 };
 
-// [rows0, rows0+128) x [col0, col0+32) of src (row-major, ld) -> K-major block, zero padded
+// [rows0, rows0+128) x [col0, col0+32) of src (row-major, ld) -> K-major block, zero padded.
+// All global loads of a thread are issued before the first shared-memory store (latency paid once).
 __device__ __forceinline__ void stage_rows(unsigned char* dst, const float* __restrict__ src, int ld, int row0,
                                            int rows_valid, int col0, int cols_valid, bool vec_ok) {
-  for (int e = threadIdx.x; e < TB * (KB / 4); e += kThreads) {
-    const int row = e >> 3, ch = e & 7;
-    const int gr = row0 + row, gc = col0 + 4 * ch;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row < rows_valid) {
-      const float* p = src + (int64_t)gr * ld + gc;
-      if (vec_ok && gc + 4 <= col0 + cols_valid) {
-        const float4 f = *reinterpret_cast<const float4*>(p);
-        v = make_uint4(to_tf32(f.x), to_tf32(f.y), to_tf32(f.z), to_tf32(f.w));
-      } else {
-        uint32_t t[4];
+  constexpr int IT = TB * (KB / 4) / kThreads;   // 4
+  float4 f[IT];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) t[j] = (gc + j < col0 + cols_valid) ? to_tf32(p[j]) : 0u;
-        v = make_uint4(t[0], t[1], t[2], t[3]);
+  for (int it = 0; it < IT; ++it) {
+    const int e = it * kThreads + threadIdx.x;
+    const int row = e >> 3, ch = e & 7;
+    const int gc = col0 + 4 * ch;
+    f[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows_valid) {
+      const float* p = src + (int64_t)(row0 + row) * ld + gc;
+      if (vec_ok && gc + 4 <= col0 + cols_valid) {
+        f[it] = __ldg(reinterpret_cast<const float4*>(p));
+      } else {
+        if (gc + 0 < col0 + cols_valid) f[it].x = __ldg(p + 0);
+        if (gc + 1 < col0 + cols_valid) f[it].y = __ldg(p + 1);
+        if (gc + 2 < col0 + cols_valid) f[it].z = __ldg(p + 2);
+        if (gc + 3 < col0 + cols_valid) f[it].w = __ldg(p + 3);
       }
     }
-    *reinterpret_cast<uint4*>(dst + (uint32_t)ch * CS_ROW + (uint32_t)(row >> 3) * RS + (uint32_t)(row & 7) * 16u) = v;
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int e = it * kThreads + threadIdx.x;
+    const int row = e >> 3, ch = e & 7;
+    *reinterpret_cast<uint4*>(dst + (uint32_t)ch * CS_ROW + (uint32_t)(row >> 3) * RS + (uint32_t)(row & 7) * 16u) =
+        make_uint4(to_tf32(f[it].x), to_tf32(f[it].y), to_tf32(f[it].z), to_tf32(f[it].w));
+  }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Whole [128 rows][r2 cols] operand (all of K) -> K-major interleaved block: every 16-byte chunk is one
+// cp.async (all in flight at once), then rounded to TF32 in place by the thread that copied it.
+// Requires r2 % 4 == 0 (16-byte aligned rows).  Invalid rows are zero filled.
+__device__ __forceinline__ void stage_full_async(unsigned char* dst, const float* __restrict__ src, int r2, int row0,
+                                                 int rows_valid) {
+  const int nch = r2 >> 2;
+  const int nchp = nch + (nch & 1);       // an MMA k-step consumes two chunks: pad odd chunk counts with zeros
+  const uint32_t d0 = smem_u32(dst);
+  for (int e = threadIdx.x; e < TB * nchp; e += kThreads) {
+    const int row = e / nchp, ch = e - row * nchp;
+    const uint32_t off = (uint32_t)ch * CS_ROW + (uint32_t)(row >> 3) * RS + (uint32_t)(row & 7) * 16u;
+    if (row < rows_valid && ch < nch) cp_async16(d0 + off, src + (int64_t)(row0 + row) * r2 + 4 * ch);
+    else *reinterpret_cast<uint4*>(dst + off) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+__device__ __forceinline__ void round_full_inplace(unsigned char* dst, int r2, int rows_valid) {
+  // same (row, chunk) -> thread mapping as stage_full_async: a thread only touches its own cp.async data
+  const int nch = r2 >> 2;
+  const int nchp = nch + (nch & 1);
+  for (int e = threadIdx.x; e < TB * nchp; e += kThreads) {
+    const int row = e / nchp, ch = e - row * nchp;
+    if (row >= rows_valid || ch >= nch) continue;
+    uint4* p = reinterpret_cast<uint4*>(dst + (uint32_t)ch * CS_ROW + (uint32_t)(row >> 3) * RS + (uint32_t)(row & 7) * 16u);
+    uint4 v = *p;
+    v.x = to_tf32(__uint_as_float(v.x)); v.y = to_tf32(__uint_as_float(v.y));
+    v.z = to_tf32(__uint_as_float(v.z)); v.w = to_tf32(__uint_as_float(v.w));
+    *p = v;
   }
 }
 
 // transposed: dst[c][r] for c in [col0, col0+32), r in [row0, row0+128): K-major along r
 __device__ __forceinline__ void stage_cols_T(unsigned char* dst, const float* __restrict__ src, int ld, int row0,
                                              int rows_valid, int col0, int cols_valid) {
-  for (int e = threadIdx.x; e < KB * (TN / 4); e += kThreads) {
+  constexpr int IT = KB * (TN / 4) / kThreads;   // 4
+  float t[IT][4];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int e = it * kThreads + threadIdx.x;
     const int c = e & 31, rch = e >> 5;
-    uint32_t t[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int r = 4 * rch + j;
-      t[j] = (r < rows_valid && c < cols_valid) ? to_tf32(__ldg(src + (int64_t)(row0 + r) * ld + col0 + c)) : 0u;
+      t[it][j] = (r < rows_valid && c < cols_valid) ? __ldg(src + (int64_t)(row0 + r) * ld + col0 + c) : 0.0f;
     }
-    *reinterpret_cast<uint4*>(dst + (uint32_t)rch * CS_T + (uint32_t)c * 16u) = make_uint4(t[0], t[1], t[2], t[3]);
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    const int e = it * kThreads + threadIdx.x;
+    const int c = e & 31, rch = e >> 5;
+    *reinterpret_cast<uint4*>(dst + (uint32_t)rch * CS_T + (uint32_t)c * 16u) =
+        make_uint4(to_tf32(t[it][0]), to_tf32(t[it][1]), to_tf32(t[it][2]), to_tf32(t[it][3]));
   }
 }
 
@@ -113,6 +171,7 @@ score_tc_kernel(TcArgs a) {
 
   const int r2 = a.r2, r2p = a.r2p;
   const bool vec_ok = (r2 % 4 == 0);
+  const bool full_k = vec_ok && r2 <= 200;   // whole-K staging fits in the idle G / G^T / stage areas
   const int nkb = (r2 + KB - 1) / KB;          // GEMM1 k-blocks
   const int ncb = r2p / KB + ((r2p % KB) ? 1 : 0);   // GEMM2/3 column blocks (last one may be 16 wide)
   const int n_chunks = (a.B + TB - 1) / TB;
@@ -121,6 +180,8 @@ score_tc_kernel(TcArgs a) {
   int used[2] = {0, 0};                          // number of un-waited commits per stage (0 or 1)
   double loss_acc = 0.0;
   bool first_tile = true;
+  long long tp[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tc0 = clock64(), tc1;
+#define RT_TC_PROF(i) do { tc1 = clock64(); tp[i] += tc1 - tc0; tc0 = tc1; } while (0)
 
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int n0 = tile * TN;
@@ -128,7 +189,33 @@ score_tc_kernel(TcArgs a) {
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       const int b0 = chunk * TB;
       const int b_valid = min(TB, a.B - b0);
-      // ================= GEMM1: Z = Q O^T, k-blocked, 2-stage ring =================
+      // ================= GEMM1: Z = Q O^T =================
+      if (full_k) {
+        // whole K resident: one asynchronous staging wave, then all MMAs back to back
+        unsigned char* sQ = smem;
+        unsigned char* sO = smem + FULL_BYTES;
+        stage_full_async(sQ, a.q, r2, b0, b_valid);
+        stage_full_async(sO, a.O, r2, n0, n_valid);
+        RT_TC_PROF(8);    // cp.async issue
+        cp_async_wait_all();
+        RT_TC_PROF(9);    // cp.async wait
+        round_full_inplace(sQ, r2, b_valid);
+        round_full_inplace(sO, r2, n_valid);
+        fence_async_smem();
+        RT_TC_PROF(10);   // in-place TF32 rounding
+        __syncthreads();
+        RT_TC_PROF(11);   // barrier
+        if (tid == 0) {
+          fence_after_sync();
+          const uint32_t aA = smem_u32(sQ), aB = smem_u32(sO);
+          const int ksteps = (r2 + 7) / 8;      // r2 % 8 == 4: the last step's second chunk is the zero pad
+          for (int ks = 0; ks < ksteps; ++ks)
+            mma_tf32(tmem + TM_Z, make_desc(aA + ks * 2 * CS_ROW, CS_ROW, RS), make_desc(aB + ks * 2 * CS_ROW, CS_ROW, RS),
+                     idesc1, ks != 0);
+          mma_commit(&bar_z);
+        }
+      } else {
+      // k-blocked, 2-stage ring (any r2)
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb & 1;
         if (used[s]) { mbar_wait(&bar_stage[s], ph_stage[s]); ph_stage[s] ^= 1u; used[s] = 0; }
@@ -149,6 +236,8 @@ score_tc_kernel(TcArgs a) {
         }
         used[s] = 1;
       }
+      }
+      RT_TC_PROF(0);   // GEMM1 staging + issue
       // ---- sparse positives of this (chunk, tile) as 128-bit row masks ----
       mask[tid] = 0ull;                                   // kThreads == 2 * TB
       __syncthreads();
@@ -169,8 +258,10 @@ score_tc_kernel(TcArgs a) {
       }
       __syncthreads();
       // ================= epilogue 1: Z -> p, loss, G ; G and G^T staged as TF32 =================
+      RT_TC_PROF(1);   // mask
       mbar_wait(&bar_z, ph_z); ph_z ^= 1u;
       fence_after_sync();
+      RT_TC_PROF(2);   // wait for GEMM1
       {
         const int rr = quarter * 32 + lane;              // query row of this thread (TMEM lane)
         const int b = b0 + rr;
@@ -183,34 +274,35 @@ score_tc_kernel(TcArgs a) {
           tmem_ld32(tmem + TM_Z + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cbase, v);
           tmem_ld_wait();
 #pragma unroll
+          // store bases: G^T[n][b] element (cc, rr) sits at gt_base + 16*cc; G[b][n] chunk at g_base + (cc/4)*CS_G
+          unsigned char* gt_base = sGT + (uint32_t)(rr >> 2) * CS_GT + (uint32_t)(rr & 3) * 4u + (uint32_t)cbase * 16u;
+          unsigned char* g_base = sG + (uint32_t)(cbase >> 2) * CS_G + (uint32_t)(rr >> 3) * RS + (uint32_t)(rr & 7) * 16u;
+          const bool row_ok = (b < a.B);
+#pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             uint32_t gq[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const int j = j4 * 4 + jj;
-              const int cc = cbase + j;
-              const bool valid = (b < a.B) && (cc < n_valid);
+              const bool valid = row_ok && (cbase + j < n_valid);
               const bool pos = (mrow >> (cgp * 32 + j)) & 1ull;
               const float z = __uint_as_float(v[j]);
-              const float p = 1.0f / (1.0f + expf(-z));
-              const float lp = fmaxf(logf(p), -100.0f);
-              const float lq = fmaxf(log1pf(-p), -100.0f);
+              // p = sigmoid(z) in fp32 with the reference's saturation semantics (BCELoss on probabilities):
+              // p == 1 -> log(1-p) clamps at -100 and the gradient vanishes; p tiny -> log p clamps at -100.
+              const float e = __expf(-z);
+              const float sden = 1.0f + e;
+              const float p = __fdividef(1.0f, sden);
+              const float lp = fmaxf(-__logf(sden), -100.0f);
+              const float lq = (p == 1.0f) ? -100.0f : fmaxf(lp - z, -100.0f);
               const float t = pos ? a.t_pos : a.t_neg;
-              float g = 0.0f;
-              if (valid) {
-                loss_t -= t * lp + (1.0f - t) * lq;
-                const float pq = (1.0f - p) * p;
-                g = (p - t) / fmaxf(pq, 1e-12f) * a.inv_count * pq;
-              }
+              const float pq = (1.0f - p) * p;
+              float g = (p - t) * a.inv_count;
+              if (pq < 1e-12f) g *= pq * 1e12f;
+              if (valid) loss_t -= t * lp + (1.0f - t) * lq; else g = 0.0f;
               gq[jj] = to_tf32(g);
-              // G^T[n][b]: row n = cc, col b = rr
-              *reinterpret_cast<uint32_t*>(sGT + (uint32_t)(rr >> 2) * CS_GT + (uint32_t)(cc >> 3) * RS +
-                                           (uint32_t)(cc & 7) * 16u + (uint32_t)(rr & 3) * 4u) = gq[jj];
+              *reinterpret_cast<uint32_t*>(gt_base + j * 16) = gq[jj];
             }
-            // G[b][n]: row b = rr, cols cbase + 4*j4 .. +3  -> one 16-byte chunk
-            const int cc0 = cbase + j4 * 4;
-            *reinterpret_cast<uint4*>(sG + (uint32_t)(cc0 >> 2) * CS_G + (uint32_t)(rr >> 3) * RS + (uint32_t)(rr & 7) * 16u) =
-                make_uint4(gq[0], gq[1], gq[2], gq[3]);
+            *reinterpret_cast<uint4*>(g_base + j4 * CS_G) = make_uint4(gq[0], gq[1], gq[2], gq[3]);
           }
         }
         loss_acc += (double)loss_t;
@@ -218,9 +310,10 @@ score_tc_kernel(TcArgs a) {
       fence_before_sync();
       fence_async_smem();
       __syncthreads();
+      RT_TC_PROF(3);   // epilogue 1
       // ================= GEMM2 (H chunk) and GEMM3 (dO tile), column-blocked =================
       for (int cb = 0; cb < ncb; ++cb) {
-        const int s = (nkb + cb) & 1;
+        const int s = cb & 1;
         if (used[s]) { mbar_wait(&bar_stage[s], ph_stage[s]); ph_stage[s] ^= 1u; used[s] = 0; }
         const int cw = min(KB, r2p - cb * KB);             // 32 or 16
         const int cvalid = max(0, min(cw, r2 - cb * KB));
@@ -244,11 +337,13 @@ score_tc_kernel(TcArgs a) {
         }
         used[s] = 1;
       }
+      RT_TC_PROF(4);   // GEMM2/3 staging + issue
       // all MMAs of this chunk done: operands (G, G^T, stages) and D2 are free / ready
       mbar_wait(&bar_d, ph_d); ph_d ^= 1u;
       fence_after_sync();
       for (int s = 0; s < 2; ++s)
         if (used[s]) { mbar_wait(&bar_stage[s], ph_stage[s]); ph_stage[s] ^= 1u; used[s] = 0; }
+      RT_TC_PROF(5);   // wait for GEMM2/3
       // ================= epilogue 2: D2 -> H_ws slice of this CTA (through smem for coalescing) =================
       for (int pass = 0; pass * 128 < r2p; ++pass) {
         const int c0 = pass * 128;
@@ -273,15 +368,26 @@ score_tc_kernel(TcArgs a) {
         __syncthreads();
         const int cols = min(cw, r2 - c0);
         float* Hc = a.H_ws + ((int64_t)blockIdx.x * a.B + b0) * r2 + c0;
-        for (int e = tid; e < b_valid * cols; e += kThreads) {
-          const int rr = e / cols, c = e - rr * cols;
-          float* p = Hc + (int64_t)rr * r2 + c;
-          const float val = hbuf[rr * HB_LD + c];
-          *p = first_tile ? val : (*p + val);
+        // warp w owns rows w, w+8, ...; lanes run along the columns (coalesced); 4 rows in flight
+        for (int rr0 = warp; rr0 < b_valid; rr0 += 4 * (kThreads / 32)) {
+          for (int c = lane; c < cols; c += 32) {
+            float old[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int rr = rr0 + u * (kThreads / 32);
+              old[u] = (!first_tile && rr < b_valid) ? Hc[(int64_t)rr * r2 + c] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int rr = rr0 + u * (kThreads / 32);
+              if (rr < b_valid) Hc[(int64_t)rr * r2 + c] = old[u] + hbuf[rr * HB_LD + c];
+            }
+          }
         }
         __syncthreads();
       }
       fence_after_sync();
+      RT_TC_PROF(6);   // epilogue 2
     }
     // ================= tile epilogue: D3 -> dO rows of this tile =================
     for (int pass = 0; pass * 128 < r2p; ++pass) {
@@ -314,7 +420,10 @@ score_tc_kernel(TcArgs a) {
     }
     fence_after_sync();
     first_tile = false;
+    RT_TC_PROF(7);   // tile epilogue
   }
+  if (a.prof && tid == 0)
+    for (int i = 0; i < 12; ++i) a.prof[blockIdx.x * 12 + i] = tp[i];
   if (first_tile) {   // CTA without a tile: its H slice must still be defined
     float* Hc = a.H_ws + (int64_t)blockIdx.x * a.B * r2;
     for (int64_t e = tid; e < (int64_t)a.B * r2; e += kThreads) Hc[e] = 0.0f;
@@ -345,6 +454,8 @@ __global__ void reduce_loss_tc_kernel(const double* __restrict__ partial, int n,
     out[0] = s;
   }
 }
+
+long long* g_tc_prof = nullptr;
 
 int tc_grid(int n_local) {
   const int n_tiles = rt::cdiv(n_local, TN);
@@ -380,6 +491,7 @@ extern "C" int rt_score_bce_tc(const float* q, const float* qp, const float* O, 
   a.dO = dO;
   a.n_tiles = rt::cdiv(n_local, TN);
   a.r2p = (r2 + 15) / 16 * 16;
+  a.prof = g_tc_prof;
   RT_CHECK_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   score_tc_kernel<<<grid, kThreads, SMEM_BYTES, s>>>(a);
   RT_LAUNCH_CHECK();
@@ -390,3 +502,6 @@ extern "C" int rt_score_bce_tc(const float* q, const float* qp, const float* O, 
   RT_LAUNCH_CHECK();
   return 0;
 }
+
+// Debug: per-CTA cycle counters of score_tc_kernel ([grid][8] int64), NULL to disable.
+extern "C" int rt_score_tc_set_profile(long long* dev_buf) { g_tc_prof = dev_buf; return 0; }
