@@ -83,6 +83,42 @@ __device__ __forceinline__ void rotation(double app, double aqq, double apq, dou
   }
 }
 
+__device__ __forceinline__ void cp_async16_d(double* dst_smem, const double* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n"
+               :: "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_d() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// fp64 tensor-core MMA: D(8x8) += A(8x4) B(4x8); lane l holds A[l>>2][l&3], B[l&3][l>>2], C[l>>2][2*(l&3)+{0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// C(32x32) = op(A) * B for one warp on the fp64 tensor cores.  A element (i, m) is read from
+// As[i * ELD + m] (a_trans = false) or As[m * ELD + i] (a_trans = true); B element (m, j) = Bs[m * ELD + j].
+template <bool A_TRANS>
+__device__ __forceinline__ void warp_mm32(const double* As, const double* Bs, double (&c)[4][4][2], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+    for (int tj = 0; tj < 4; ++tj) { c[ti][tj][0] = 0.0; c[ti][tj][1] = 0.0; }
+#pragma unroll 2
+  for (int kk = 0; kk < EP / 4; ++kk) {
+    double a[4], b[4];
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+      a[ti] = A_TRANS ? As[(4 * kk + t) * ELD + 8 * ti + g] : As[(8 * ti + g) * ELD + 4 * kk + t];
+#pragma unroll
+    for (int tj = 0; tj < 4; ++tj) b[tj] = Bs[(4 * kk + t) * ELD + 8 * tj + g];
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) dmma884(c[ti][tj][0], c[ti][tj][1], a[ti], b[tj]);
+  }
+}
+
 struct VisitSmem {
   double* S;      // [EP][ELD] tile
   double* Q;      // [EP][ELD] accumulated rotations
@@ -293,74 +329,42 @@ eig_block_jacobi_kernel(EigBatch batch) {
           if (!isV) rr_pair(P.nb, round, k, bik, bjk);
           rr_pair(P.nb, round, l, bil, bjl);
           double* M = isV ? P.Vp : P.Ap;
-          for (int e = lane; e < EP * EP; e += 32) {
-            const int i = e / EP, j = e % EP;
+          // ---- tiles -> shared memory: every 16-byte chunk is one cp.async (all in flight together) ----
+          for (int cidx = lane; cidx < EP * (EP / 2); cidx += 32) {
+            const int i = cidx >> 4, jc = (cidx & 15) * 2;            // row, first of two columns
             const int gi = isV ? k * EP + i : pair_index(bik, bjk, i);
-            T[i * ELD + j] = M[(int64_t)gi * P.np + pair_index(bil, bjl, j)];
-            Ql[i * ELD + j] = sl ? (i == j ? 1.0 : 0.0) : P.J[(int64_t)l * EP * EP + e];
-            if (!isV) Qk[i * ELD + j] = sk ? (i == j ? 1.0 : 0.0) : P.J[(int64_t)k * EP * EP + e];
-          }
-          __syncwarp();
-          // register-blocked 32x32x32 products: lane -> rows 4*ri..+3, cols 8*cj..+7
-          const int ri = lane >> 2, cj = lane & 3;
-          double x[4][8];
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[r][j] = 0.0;
-          // X = T Ql
-#pragma unroll 4
-          for (int m = 0; m < EP; ++m) {
-            double a[4], bq[8];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) a[r] = T[(4 * ri + r) * ELD + m];
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              const double2 v = *reinterpret_cast<const double2*>(&Ql[m * ELD + 8 * cj + j]);
-              bq[j] = v.x; bq[j + 1] = v.y;
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) x[r][j] = fma(a[r], bq[j], x[r][j]);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int j = 0; j < 8; j += 2)
-              *reinterpret_cast<double2*>(&T[(4 * ri + r) * ELD + 8 * cj + j]) = make_double2(x[r][j], x[r][j + 1]);
-          __syncwarp();
-          if (!isV) {  // Y = Qk^T X
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) x[r][j] = 0.0;
-#pragma unroll 4
-            for (int m = 0; m < EP; ++m) {
-              double a[4], bq[8];
-#pragma unroll
-              for (int r = 0; r < 4; r += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(&Qk[m * ELD + 4 * ri + r]);
-                a[r] = v.x; a[r + 1] = v.y;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; j += 2) {
-                const double2 v = *reinterpret_cast<const double2*>(&T[m * ELD + 8 * cj + j]);
-                bq[j] = v.x; bq[j + 1] = v.y;
-              }
-#pragma unroll
-              for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[r][j] = fma(a[r], bq[j], x[r][j]);
+            cp_async16_d(&T[i * ELD + jc], M + (int64_t)gi * P.np + pair_index(bil, bjl, jc));
+            if (!sl) cp_async16_d(&Ql[i * ELD + jc], P.J + (int64_t)l * EP * EP + i * EP + jc);
+            else { Ql[i * ELD + jc] = (i == jc) ? 1.0 : 0.0; Ql[i * ELD + jc + 1] = (i == jc + 1) ? 1.0 : 0.0; }
+            if (!isV) {
+              if (!sk) cp_async16_d(&Qk[i * ELD + jc], P.J + (int64_t)k * EP * EP + i * EP + jc);
+              else { Qk[i * ELD + jc] = (i == jc) ? 1.0 : 0.0; Qk[i * ELD + jc + 1] = (i == jc + 1) ? 1.0 : 0.0; }
             }
           }
+          cp_async_wait_all_d();
+          __syncwarp();
+          // ---- X = T Ql ;  Y = Qk^T X  on the fp64 tensor cores ----
+          const int g = lane >> 2, t = lane & 3;
+          double c[4][4][2];
+          warp_mm32<false>(T, Ql, c, lane);
+          if (!isV) {
+            __syncwarp();
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int i = 4 * ri + r;
+            for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+              for (int tj = 0; tj < 4; ++tj)
+                *reinterpret_cast<double2*>(&T[(8 * ti + g) * ELD + 8 * tj + 2 * t]) = make_double2(c[ti][tj][0], c[ti][tj][1]);
+            __syncwarp();
+            warp_mm32<true>(Qk, T, c, lane);
+          }
+#pragma unroll
+          for (int ti = 0; ti < 4; ++ti) {
+            const int i = 8 * ti + g;
             const int gi = isV ? k * EP + i : pair_index(bik, bjk, i);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) M[(int64_t)gi * P.np + pair_index(bil, bjl, 8 * cj + j)] = x[r][j];
+            for (int tj = 0; tj < 4; ++tj)
+              *reinterpret_cast<double2*>(&M[(int64_t)gi * P.np + pair_index(bil, bjl, 8 * tj + 2 * t)]) =
+                  make_double2(c[ti][tj][0], c[ti][tj][1]);
           }
           __syncwarp();
         }
