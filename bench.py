@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--variant", type=int, default=1, help="fused score kernel: 0 = fp32 FFMA (1e-5 parity), 1 = tcgen05 TF32 (2e-3)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="reference steps timed for cpu_baseline (0 = skip)")
     ap.add_argument("--eval-batches", type=int, default=8)
+    ap.add_argument("--no-graphs", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -234,7 +235,7 @@ def main():
             model.O.weight.data = model.O.weight.data[n_begin:n_end].contiguous()
     model.to(dev)
     mod = symmetric if w["sym"] else asymmetric
-    kw = dict(group=group, n_total=N, n_begin=n_begin, score_variant=args.variant)
+    kw = dict(group=group, n_total=N, n_begin=n_begin, score_variant=args.variant, use_graphs=(world == 1 and not args.no_graphs))
     if w["sym"]:
         opt = mod.RGD([model.core, model.E.weight, model.R.weight], w["rank"], LR, **kw)
     else:
@@ -266,12 +267,11 @@ def main():
         opt.fit(FusedLoss(score_fn, SparseTargets(od, xd), LABEL_SMOOTHING, REG), None)
         opt.step()
 
-    # ---- device-resident timing ----
+    # ---- device-resident timing (CUDA graphs replay fit + step; inputs already in HBM) ----
     for i in range(args.warmup):
         one_step(*dev_batches[i])
     eng = opt._engine
     launches0 = lib().rt_launch_count()
-    eng.timers = {}
     clocks = ClockSampler()
     barrier()
     clocks.start()
@@ -282,15 +282,27 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = int(lib().rt_launch_count() - launches0)
-    stage_ms = eng.stage_ms()
-    eng.timers = None
+    launches_eager = int(lib().rt_launch_count() - launches0)
     n_tr = sum(triples[args.warmup:total_steps])
     t_all = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t_all, op=torch.distributed.ReduceOp.MAX)
     ms = float(t_all.item())
     value = n_tr / (ms * 1e-3)
+
+    # ---- per-stage profile pass: same steps launched eagerly with CUDA-event brackets around every stage
+    #      (the graph path cannot be bracketed); also counts the kernels of one step ----
+    prof_steps = min(args.steps, 10)
+    eng.timers = {}
+    l0 = lib().rt_launch_count()
+    barrier()
+    for i in range(prof_steps):
+        one_step(*dev_batches[args.warmup + i])
+    barrier()
+    launches_per_step = int(lib().rt_launch_count() - l0) // prof_steps
+    stage_ms = eng.stage_ms()
+    eng.timers = None
+    launches = launches_per_step * args.steps if launches_eager == 0 else launches_eager
 
     # ---- end to end: host batches in, loss out, every step ----
     h2d = d2h = 0
@@ -366,8 +378,11 @@ def main():
         "eval_queries_per_s": eval_qps,
         "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
+        "gpu_launches_note": "kernels of this library executed in the timed region (%d per step; replayed from 2 CUDA graphs per step when graphs are on)" % launches_per_step,
+        "cuda_graphs": bool(eng.use_graphs and eng._graphs),
         "roofline": roofline,
         "stage_ms": stage_ms,
+        "stage_ms_note": "mean ms per stage over %d eagerly launched steps (CUDA events on the launching stream)" % prof_steps,
         "cpu_baseline": cpu,
         "clocks": clock_info,
     }

@@ -147,6 +147,19 @@ int rt_apply(float* Y, int64_t ldy, int n, int rc,
              int nk, const float* const* X_host, const int64_t* ldx_host, const int* rk_host,
              const double* const* K_host, void* stream);
 
+/* Tensor-core (tcgen05, TF32 with a 3-product hi/lo split => fp32-level accuracy) variants of the two
+ * passes above.  *_supported returns 1 if the shape fits (ranks <= 256); same results as rt_gram(precise=0)
+ * / rt_apply to ~1e-6 relative. */
+int rt_apply_tc_supported(int rc, int nk, const int* rk_host);
+size_t rt_apply_tc_ws_bytes(int rc, int nk, const int* rk_host);
+int rt_apply_tc(float* Y, int64_t ldy, int n, int rc, const float* X0, int64_t ldx0, const double* a0_dev,
+                int nk, const float* const* X_host, const int64_t* ldx_host, const int* rk_host,
+                const double* const* K_host, void* ws, void* stream);
+int rt_gram_tc_supported(int ra, int rb);
+size_t rt_gram_tc_ws_bytes(int n, int ra, int rb);
+int rt_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int n, int ra, int rb,
+               double* out, void* ws, void* stream);
+
 /* ---- (c) N-independent ("small") stage ----------------------------------------------- */
 /*
  * All r-sized arithmetic of one optimiser step, in fp64, on a caller-provided workspace.
@@ -203,13 +216,17 @@ int rt_core_axpby(const float* dS_g, const double* alpha_dev, const float* pS_be
 /*
  * rt_small_retract: the N-independent part of construct().round(rank) (asymmetric/optim.py:106-108):
  *   in : core, dS_dir, Gram_i = dV_dir_i^T dV_dir_i (fp64), hyper (lr)
- *   out: core_new fp32; Z1_i, Z2_i (fp64 [r_i,r_i]) with U_i_new = U_i Z1_i + dV_dir_i Z2_i.
+ *   out: core_new fp32; Z1_i, Z2_i (fp64 [r_i,r_i]) with U_i_new = U_i Z1_i + dV_dir_i Z2_i;
+ *        Mn_i (fp64 [r_i, 2 r_i], may be NULL) = U_i_new^T [U_i | dV_dir_i] = [Z1_i^T | Z2_i^T Gram_i]: the
+ *        transport Grams the next rt_small_project needs, obtained without another N-sized pass
+ *        (exact when U_i^T U_i = I and U_i^T dV_dir_i = 0).
  */
 int rt_small_retract(const float* core, const float* dS_dir,
                      const double* gram_R, const double* gram_S, const double* gram_O,
                      const double* hyper, int r0, int r1, int r2, int sym,
                      float* core_new, double* Z1_R, double* Z2_R, double* Z1_S, double* Z2_S,
-                     double* Z1_O, double* Z2_O, void* small_ws, void* stream);
+                     double* Z1_O, double* Z2_O, double* Mn_R, double* Mn_S, double* Mn_O,
+                     void* small_ws, void* stream);
 
 /* Symmetric eigen-decomposition (block Jacobi, fp64), exposed for testing:
  * A[n,n] (destroyed) -> eigenvalues w[n] descending, eigenvectors V[n,n] (columns). */

@@ -38,6 +38,13 @@ PROTOTYPES = {
     "rt_gram": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, i32, vp, vp]),
     "rt_apply": (i32, [vp, i64, i32, i32, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i64),
                        C.POINTER(i32), C.POINTER(vp), vp]),
+    "rt_apply_tc_supported": (i32, [i32, i32, C.POINTER(i32)]),
+    "rt_apply_tc_ws_bytes": (sz, [i32, i32, C.POINTER(i32)]),
+    "rt_apply_tc": (i32, [vp, i64, i32, i32, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32),
+                          C.POINTER(vp), vp, vp]),
+    "rt_gram_tc_supported": (i32, [i32, i32]),
+    "rt_gram_tc_ws_bytes": (sz, [i32, i32, i32]),
+    "rt_gram_tc": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp]),
     "rt_small_ws_bytes": (sz, [i32, i32, i32, i32]),
     "rt_small_prepare": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "rt_rows_times_ainv": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
@@ -45,7 +52,7 @@ PROTOTYPES = {
     "rt_small_norm": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "rt_small_project": (i32, [vp] * 7 + [i32, i32, i32, i32] + [vp] * 9),
     "rt_core_axpby": (i32, [vp, vp, vp, i32, vp, vp]),
-    "rt_small_retract": (i32, [vp] * 6 + [i32, i32, i32, i32] + [vp] * 9),
+    "rt_small_retract": (i32, [vp] * 6 + [i32, i32, i32, i32] + [vp] * 12),
     "rt_eigh_ws_bytes": (sz, [i32]),
     "rt_eigh": (i32, [vp, i32, vp, vp, vp, vp]),
     "rt_tc_selftest": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),

@@ -77,10 +77,11 @@ struct Ctx {
   double* T(int t) const { return p(L.Tn[t]); }
   int r(int i) const { return L.r[i]; }
 
-  void gemm(Gemm g) {
+  template <typename T>
+  void gemm(GemmT<T> g) {
     if (err) return;
     if (g.m <= 0 || g.n <= 0) return;
-    g.ksplit = 1; g.k_per_split = g.K1 * g.K2; g.partial = p(L.gemm_partial);
+    g.ksplit = 1; g.k_per_split = g.K1 * g.K2; g.partial = reinterpret_cast<T*>(p(L.gemm_partial));
     const int tiles = cdiv(g.m, GT) * cdiv(g.n, GT);
     const int K = g.K1 * g.K2;
     if (g.batch == 1 && tiles < 148 && K >= 8 * GK) {
@@ -94,17 +95,18 @@ struct Ctx {
       }
     }
     dim3 grid(cdiv(g.m, GT), cdiv(g.n, GT), g.ksplit > 1 ? g.ksplit : g.batch);
-    gemm64_kernel<<<grid, 256, 0, s>>>(g);
+    gemm64_kernel<T><<<grid, 256, 0, s>>>(g);
     ++rt::g_launches;
-    if (g.ksplit > 1) { gemm64_reduce_kernel<<<cdiv(g.m * g.n, 256), 256, 0, s>>>(g); ++rt::g_launches; }
+    if (g.ksplit > 1) { gemm64_reduce_kernel<T><<<cdiv(g.m * g.n * 32, 256), 256, 0, s>>>(g); ++rt::g_launches; }
     if (cudaGetLastError() != cudaSuccess) err = 1;
   }
 
   // Y = alpha * (X x_mode M) + beta * Y.  M is (mo x mi) with strides (sm_o, sm_i);
   // X has dims d[] with d[mode] == mi; Y has the same dims except d[mode] -> mo.
-  void mode_prod(int mode, const double* M, int64_t sm_o, int64_t sm_i, int mo, int mi,
-                 const double* X, const int d[3], double* Y, double alpha, double beta) {
-    Gemm g{};
+  template <typename T>
+  void mode_prod(int mode, const T* M, int64_t sm_o, int64_t sm_i, int mo, int mi,
+                 const T* X, const int d[3], T* Y, double alpha, double beta) {
+    GemmT<T> g{};
     g.alpha = alpha; g.beta = beta; g.batch = 1;
     if (mode == 0) {
       const int64_t rest = (int64_t)d[1] * d[2];
@@ -126,9 +128,10 @@ struct Ctx {
 
   // out[mx, my] (row stride ldo) = alpha * X_(mode) Y_(mode)^T + beta * out.
   // X dims dx[], Y dims equal to dx except dy_mode in the contracted-free mode.
-  void unfold_gram(int mode, const double* X, const int dx[3], const double* Y, int my, double* out,
+  template <typename T>
+  void unfold_gram(int mode, const T* X, const int dx[3], const T* Y, int my, T* out,
                    int64_t ldo, double alpha, double beta) {
-    Gemm g{};
+    GemmT<T> g{};
     g.alpha = alpha; g.beta = beta; g.batch = 1;
     g.A = X; g.B = Y; g.C = out; g.m = dx[mode]; g.n = my; g.c_m = ldo; g.c_n = 1;
     if (mode == 0) {
@@ -158,6 +161,17 @@ struct Ctx {
     gemm(g);
   }
 
+  float* Tf(int t) const { return reinterpret_cast<float*>(T(t)); }   // the same temporaries viewed as fp32
+  void to32plain(const double* x, float* y, int64_t n) {
+    if (err) return;
+    int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
+    f64_to_f32_kernel<<<blocks, 256, 0, s>>>(x, y, n); ++rt::g_launches;
+  }
+  void scale32(const float* x, float* y, int64_t n, double a_host, const double* a_dev) {
+    if (err) return;
+    int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
+    scale_f32_kernel<<<blocks, 256, 0, s>>>(x, y, n, a_host, a_dev); ++rt::g_launches;
+  }
   void to64(const float* x, double* y, int64_t n) {
     if (err) return;
     int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
@@ -208,9 +222,10 @@ int finish(Ctx& c, const char* what) {
 //                U1 = D x1 W1a + E1 x1 W1b ;  U2 = E2 x1 W1a ;  out = U1 x2 W2a + U2 x2 W2b.
 // Buffers are caller-provided; allowed aliases: E2 == E1 iff B2 == B1; U2 may reuse E1 when
 // E2 != E1; out may reuse D.
-void grouped_contract(Ctx& c, const double* X, const double* const B[3], const double* const Wa[3],
-                      const double* const Wb[3], const int64_t st_o[3], const int64_t st_i[3],
-                      double* D, double* E1, double* E2, double* U1, double* U2, double* out) {
+template <typename T>
+void grouped_contract(Ctx& c, const T* X, const T* const B[3], const T* const Wa[3],
+                      const T* const Wb[3], const int64_t st_o[3], const int64_t st_i[3],
+                      T* D, T* E1, T* E2, T* U1, T* U2, T* out) {
   const int d[3] = {c.r(0), c.r(1), c.r(2)};
   c.mode_prod(0, Wa[0], st_o[0], st_i[0], d[0], d[0], X, d, D, 1.0, 0.0);
   c.mode_prod(0, Wb[0], st_o[0], st_i[0], d[0], d[0], B[0], d, D, 1.0, 1.0);
@@ -264,8 +279,8 @@ extern "C" int rt_rows_times_ainv(const float* A, int m, int mode, int r0, int r
   Layout L = make_layout(r0, r1, r2, 0);
   const int r = L.r[mode];
   const double* K = (const double*)((char*)small_ws + L.Ainv[mode]);
-  const size_t smem = (size_t)16 * r * sizeof(float);
-  rows_times_mat_kernel<<<cdiv(m, 16), 256, smem, (cudaStream_t)stream>>>(A, m, r, K, C);
+  const size_t smem = (size_t)4 * r * sizeof(float);
+  rows_times_mat_kernel<<<cdiv(m, 4), 256, smem, (cudaStream_t)stream>>>(A, m, r, K, C);
   RT_LAUNCH_CHECK();
   return 0;
 }
@@ -346,40 +361,48 @@ extern "C" int rt_small_project(const float* core, const float* core_old, const 
   const double* M[3] = {M_R, M_S, sym ? M_S : M_O};
   double* Kout[3] = {K_R, K_S, K_O};
   double* Lout[3] = {L_R, L_S, L_O};
-  double* C = c.p(c.L.C64);
-  double* Co = c.T(0);
-  double* Xo = c.T(1);
-  c.to64(core_old, Co, c.L.c);
-  c.to64(dS_old, Xo, c.L.c);
-  const double* Wa[3]; const double* Wb[3]; int64_t st_o[3], st_i[3];
-  for (int i = 0; i < 3; ++i) { Wa[i] = M[i]; Wb[i] = M[i] + d[i]; st_o[i] = 2 * d[i]; st_i[i] = 1; }
-  const double* Cb[3] = {Co, Co, Co};
-  double* D = c.T(2); double* Ta = c.T(3); double* U1 = c.T(4); double* U2 = c.T(5);
-  double* pS = c.T(6);
-  grouped_contract(c, Xo, Cb, Wa, Wb, st_o, st_i, D, Ta, Ta, U1, U2, pS);
-  c.to32(pS, pS_beta, c.L.c, 1.0, hyper + 2);
-  // KC_2 = [U1_(2) ; U2_(2)] C_(2)^T
+  // All O(r^4) contractions of the projection run in fp32 (inputs are the fp32 parameters themselves and
+  // the result only needs fp32 accuracy); the r x r solves with (S_(i)S_(i)^T)^-1 stay in fp64.
+  const float* Cf = core;
+  const float* Co = core_old;
+  const float* Xo = dS_old;
+  float* Mf[3];
+  for (int i = 0; i < 3; ++i) Mf[i] = reinterpret_cast<float*>(c.p(c.L.tmpM[i]));
+  for (int i = 0; i < (sym ? 2 : 3); ++i) c.to32plain(M[i], Mf[i], 2 * (int64_t)d[i] * d[i]);
+  if (sym) Mf[2] = Mf[1];
+  const float* Wa[3]; const float* Wb[3]; int64_t st_o[3], st_i[3];
+  for (int i = 0; i < 3; ++i) { Wa[i] = Mf[i]; Wb[i] = Mf[i] + d[i]; st_o[i] = 2 * d[i]; st_i[i] = 1; }
+  const float* Cb[3] = {Co, Co, Co};
+  float* D = c.Tf(2); float* Ta = c.Tf(3); float* U1 = c.Tf(4); float* U2 = c.Tf(5);
+  float* pS = c.Tf(6);
+  grouped_contract<float>(c, Xo, Cb, Wa, Wb, st_o, st_i, D, Ta, Ta, U1, U2, pS);
+  c.scale32(pS, pS_beta, c.L.c, 1.0, hyper + 2);
+  // KC_i (2 r_i x r_i) in fp32 scratch (the eigenvector slots are idle here), converted to fp64 afterwards
+  float* KCf[3] = {reinterpret_cast<float*>(c.p(c.L.Vf[0])), reinterpret_cast<float*>(c.p(c.L.Vf[1])),
+                   reinterpret_cast<float*>(c.p(c.L.Vf[2]))};
   double* KC[3] = {c.p(c.L.KC[0]), c.p(c.L.KC[1]), c.p(c.L.KC[2])};
-  c.unfold_gram(2, U1, d, C, d[2], KC[2], d[2], 1.0, 0.0);
-  c.unfold_gram(2, U2, d, C, d[2], KC[2] + (int64_t)d[2] * d[2], d[2], 1.0, 0.0);
+  // KC_2 = [U1_(2) ; U2_(2)] C_(2)^T
+  c.unfold_gram<float>(2, U1, d, Cf, d[2], KCf[2], d[2], 1.0, 0.0);
+  c.unfold_gram<float>(2, U2, d, Cf, d[2], KCf[2] + (int64_t)d[2] * d[2], d[2], 1.0, 0.0);
   // KC_1: V1 = D x2 W2a + Ta x2 W2b ; V2 = Ta x2 W2a     (reuse U1/U2 storage after KC_2)
-  double* V1 = U1; double* V2 = U2;
-  c.mode_prod(2, Wa[2], st_o[2], st_i[2], d[2], d[2], D, d, V1, 1.0, 0.0);
-  c.mode_prod(2, Wb[2], st_o[2], st_i[2], d[2], d[2], Ta, d, V1, 1.0, 1.0);
-  c.mode_prod(2, Wa[2], st_o[2], st_i[2], d[2], d[2], Ta, d, V2, 1.0, 0.0);
-  c.unfold_gram(1, V1, d, C, d[1], KC[1], d[1], 1.0, 0.0);
-  c.unfold_gram(1, V2, d, C, d[1], KC[1] + (int64_t)d[1] * d[1], d[1], 1.0, 0.0);
+  float* V1 = U1; float* V2 = U2;
+  c.mode_prod<float>(2, Wa[2], st_o[2], st_i[2], d[2], d[2], D, d, V1, 1.0, 0.0);
+  c.mode_prod<float>(2, Wb[2], st_o[2], st_i[2], d[2], d[2], Ta, d, V1, 1.0, 1.0);
+  c.mode_prod<float>(2, Wa[2], st_o[2], st_i[2], d[2], d[2], Ta, d, V2, 1.0, 0.0);
+  c.unfold_gram<float>(1, V1, d, Cf, d[1], KCf[1], d[1], 1.0, 0.0);
+  c.unfold_gram<float>(1, V2, d, Cf, d[1], KCf[1] + (int64_t)d[1] * d[1], d[1], 1.0, 0.0);
   // KC_0: Ea = Co x1 W1a, Eb = Co x1 W1b, F = Xo x1 W1a + Eb ; Z1 = F x2 W2a + Ea x2 W2b ; Z2 = Ea x2 W2a
-  double* Ea = Ta; double* F = D;
-  c.mode_prod(1, Wa[1], st_o[1], st_i[1], d[1], d[1], Co, d, Ea, 1.0, 0.0);
-  c.mode_prod(1, Wa[1], st_o[1], st_i[1], d[1], d[1], Xo, d, F, 1.0, 0.0);
-  c.mode_prod(1, Wb[1], st_o[1], st_i[1], d[1], d[1], Co, d, F, 1.0, 1.0);
-  double* Z1 = U1; double* Z2 = U2;
-  c.mode_prod(2, Wa[2], st_o[2], st_i[2], d[2], d[2], F, d, Z1, 1.0, 0.0);
-  c.mode_prod(2, Wb[2], st_o[2], st_i[2], d[2], d[2], Ea, d, Z1, 1.0, 1.0);
-  c.mode_prod(2, Wa[2], st_o[2], st_i[2], d[2], d[2], Ea, d, Z2, 1.0, 0.0);
-  c.unfold_gram(0, Z1, d, C, d[0], KC[0], d[0], 1.0, 0.0);
-  c.unfold_gram(0, Z2, d, C, d[0], KC[0] + (int64_t)d[0] * d[0], d[0], 1.0, 0.0);
+  float* Ea = Ta; float* F = D;
+  c.mode_prod<float>(1, Wa[1], st_o[1], st_i[1], d[1], d[1], Co, d, Ea, 1.0, 0.0);
+  c.mode_prod<float>(1, Wa[1], st_o[1], st_i[1], d[1], d[1], Xo, d, F, 1.0, 0.0);
+  c.mode_prod<float>(1, Wb[1], st_o[1], st_i[1], d[1], d[1], Co, d, F, 1.0, 1.0);
+  float* Z1 = U1; float* Z2 = U2;
+  c.mode_prod<float>(2, Wa[2], st_o[2], st_i[2], d[2], d[2], F, d, Z1, 1.0, 0.0);
+  c.mode_prod<float>(2, Wb[2], st_o[2], st_i[2], d[2], d[2], Ea, d, Z1, 1.0, 1.0);
+  c.mode_prod<float>(2, Wa[2], st_o[2], st_i[2], d[2], d[2], Ea, d, Z2, 1.0, 0.0);
+  c.unfold_gram<float>(0, Z1, d, Cf, d[0], KCf[0], d[0], 1.0, 0.0);
+  c.unfold_gram<float>(0, Z2, d, Cf, d[0], KCf[0] + (int64_t)d[0] * d[0], d[0], 1.0, 0.0);
+  for (int i = 0; i < 3; ++i) c.to64(KCf[i], KC[i], 2 * (int64_t)d[i] * d[i]);
   if (sym) c.axpby(KC[1], KC[2], KC[1], 2 * (int64_t)d[1] * d[1], 1.0, nullptr, 1.0, nullptr);
   const int nm = sym ? 2 : 3;
   for (int i = 0; i < nm; ++i) {
@@ -399,8 +422,8 @@ extern "C" int rt_small_project(const float* core, const float* core_old, const 
 extern "C" int rt_small_retract(const float* core, const float* dS_dir, const double* gram_R,
                                 const double* gram_S, const double* gram_O, const double* hyper, int r0,
                                 int r1, int r2, int sym, float* core_new, double* Z1_R, double* Z2_R,
-                                double* Z1_S, double* Z2_S, double* Z1_O, double* Z2_O, void* small_ws,
-                                void* stream) {
+                                double* Z1_S, double* Z2_S, double* Z1_O, double* Z2_O, double* Mn_R,
+                                double* Mn_S, double* Mn_O, void* small_ws, void* stream) {
   RT_REQUIRE(small_ws != nullptr, "rt_small_retract: workspace is NULL");
   Ctx c{make_layout(r0, r1, r2, 0), (char*)small_ws, (cudaStream_t)stream};
   cudaStream_t s = c.s;
@@ -458,17 +481,30 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
   }
   // Y_i = V_i[:, :r_i]  (2r_i x r_i, row stride 2r_i);  W_i = Y_i^T = [Y_ia^T | Y_ib^T]
   const double* Y[3] = {c.p(c.L.Vf[0]), c.p(c.L.Vf[1]), c.p(c.L.Vf[sym ? 1 : 2])};
-  const double* Wa[3]; const double* Wb[3]; int64_t st_o[3], st_i[3];
-  for (int i = 0; i < 3; ++i) {
-    const int64_t n = 2 * d[i];
-    Wa[i] = Y[i];                     // W_ia[o, k] = Y[k, o]      -> strides (1, n)
-    Wb[i] = Y[i] + (int64_t)d[i] * n; // W_ib[o, k] = Y[r + k, o]
-    st_o[i] = 1; st_i[i] = n;
+  // core_new = T x_i Y_i^T through the block structure, in fp32 (the output is fp32): fp32 images of C', B_k
+  // and of Y_i (dense [2 r_i, r_i]) live in the scratch temporaries T4..T7 (8 x c floats) and tmpM.
+  float* CpF = c.Tf(4); float* BkF[3] = {c.Tf(4) + c.L.c, c.Tf(5), c.Tf(5) + c.L.c};
+  c.to32plain(Cp, CpF, c.L.c);
+  for (int i = 0; i < 3; ++i) c.to32plain(Bk[i], BkF[i], c.L.c);
+  float* Yf[3];
+  for (int i = 0; i < 3; ++i) Yf[i] = reinterpret_cast<float*>(c.p(c.L.tmpM[i]));
+  for (int i = 0; i < nm; ++i) {
+    const int total = 2 * d[i] * d[i];
+    f64_to_f32_strided_kernel<<<cdiv(total, 256), 256, 0, s>>>(Y[i], 2 * d[i], Yf[i], d[i], 2 * d[i], d[i]);
+    ++rt::g_launches;
   }
-  const double* Cb[3] = {Bk[0], Bk[1], Bk[2]};
-  // scratch T4..T7: D, E1, E2, U1;  U2 reuses E1 (dead once U1 exists), the result reuses D
-  grouped_contract(c, Cp, Cb, Wa, Wb, st_o, st_i, c.T(4), c.T(5), c.T(6), c.T(7), c.T(5), c.T(4));
-  c.to32(c.T(4), core_new, c.L.c, 1.0, nullptr);
+  if (sym) Yf[2] = Yf[1];
+  const float* Wa[3]; const float* Wb[3]; int64_t st_o[3], st_i[3];
+  for (int i = 0; i < 3; ++i) {
+    Wa[i] = Yf[i];                              // W_ia[o, k] = Y[k, o]      -> strides (1, r_i)
+    Wb[i] = Yf[i] + (int64_t)d[i] * d[i];       // W_ib[o, k] = Y[r_i + k, o]
+    st_o[i] = 1; st_i[i] = d[i];
+  }
+  const float* Cb[3] = {BkF[0], BkF[1], BkF[2]};
+  float* Dn = c.Tf(6); float* E1 = c.Tf(6) + c.L.c; float* E2 = c.Tf(7); float* U1n = c.Tf(7) + c.L.c;
+  // U2 reuses E1 (dead once U1 exists), the result reuses D
+  grouped_contract<float>(c, CpF, Cb, Wa, Wb, st_o, st_i, Dn, E1, E2, U1n, E1, Dn);
+  RT_CHECK_CUDA(cudaMemcpyAsync(core_new, Dn, sizeof(float) * c.L.c, cudaMemcpyDeviceToDevice, s));
   // Z1_i = Y_ia ; Z2_i = -lr * L_i^-T Y_ib
   for (int i = 0; i < nm; ++i) {
     const int64_t n = 2 * d[i];
@@ -476,6 +512,16 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
     c.axpby(c.p(c.L.tmpK[i]), nullptr, Z2[i], (int64_t)d[i] * d[i], 1.0, lr, 0.0, nullptr);
     RT_CHECK_CUDA(cudaMemcpy2DAsync(Z1[i], sizeof(double) * d[i], Y[i], sizeof(double) * n,
                                     sizeof(double) * d[i], d[i], cudaMemcpyDeviceToDevice, s));
+  }
+  // Transport Grams of the NEXT fit() without touching N-sized data: with U^T U = I and
+  // U^T dV = 0,  U_new^T [U | dV] = [Z1^T | Z2^T (dV^T dV)]   (r_i x 2 r_i)
+  double* Mn[3] = {Mn_R, Mn_S, Mn_O};
+  for (int i = 0; i < nm; ++i) {
+    if (!Mn[i]) continue;
+    const int64_t n2 = 2 * d[i];
+    transpose_into_kernel<<<cdiv(d[i] * d[i], 256), 256, 0, s>>>(Z1[i], d[i], Mn[i], n2);
+    ++rt::g_launches;
+    c.matmul(Z2[i], d[i], true, gram[i], d[i], false, Mn[i] + d[i], n2, d[i], d[i], d[i], 1.0, 0.0);
   }
   if (sym && Z1_O && Z1_O != Z1_S) {
     c.axpby(Z1_S, nullptr, Z1_O, (int64_t)d[1] * d[1], 1.0, nullptr, 0.0, nullptr);

@@ -9,8 +9,9 @@ namespace rt {
 namespace small {
 
 // C[m,n] = alpha * sum_{k1<K1,k2<K2} A[m,(k1,k2)] B[(k1,k2),n] + beta * C[m,n]      (batched)
-struct Gemm {
-  const double* A; const double* B; double* C;
+template <typename T>
+struct GemmT {
+  const T* A; const T* B; T* C;
   int m, n, K1, K2;
   int64_t a_m, a_k1, a_k2;
   int64_t b_k1, b_k2, b_n;
@@ -18,58 +19,75 @@ struct Gemm {
   int batch; int64_t a_b, b_b, c_b;
   double alpha, beta;
   int ksplit, k_per_split;  // split over the flattened K (batch == 1 only)
-  double* partial;          // [ksplit][m][n] when ksplit > 1
+  T* partial;               // [ksplit][m][n] when ksplit > 1
 };
+using Gemm = GemmT<double>;
 
 constexpr int GT = 64, GK = 16;
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-gemm64_kernel(Gemm g) {
-  __shared__ double As[GK][GT + 2];
-  __shared__ double Bs[GK][GT + 2];
+gemm64_kernel(GemmT<T> g) {
+  __shared__ T As[GK][GT + 2];
+  __shared__ T Bs[GK][GT + 2];
   const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
   int z = blockIdx.z, split = 0, bidx = 0;
   if (g.ksplit > 1) split = z; else bidx = z;
-  const double* A = g.A + (int64_t)bidx * g.a_b;
-  const double* B = g.B + (int64_t)bidx * g.b_b;
+  const T* A = g.A + (int64_t)bidx * g.a_b;
+  const T* B = g.B + (int64_t)bidx * g.b_b;
   const int K = g.K1 * g.K2;
   const int kbeg = split * g.k_per_split;
   const int kend = (g.ksplit > 1) ? min(K, kbeg + g.k_per_split) : K;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const bool a_lanes_m = (g.a_m == 1);   // lanes along m when m is the contiguous index
   const bool b_lanes_n = (g.b_n == 1);
-  double acc[4][4];
+  T acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k0 = kbeg; k0 < kend; k0 += GK) {
+    for (int j = 0; j < 4; ++j) acc[i][j] = (T)0;
+  // software pipeline: the global loads of chunk k0+GK are in flight while chunk k0 is multiplied
+  T va[(GT * GK) / 256], vb[(GT * GK) / 256];
+  auto load_chunk = [&](int k0) {
 #pragma unroll
     for (int it = 0; it < (GT * GK) / 256; ++it) {
       const int e = it * 256 + threadIdx.x;
       int rr, kk;
       if (a_lanes_m) { kk = e / GT; rr = e % GT; } else { rr = e / GK; kk = e % GK; }
       int k = k0 + kk;
-      double v = 0.0;
+      T v = (T)0;
       if (m0 + rr < g.m && k < kend) {
         const int k1 = k / g.K2, k2 = k - k1 * g.K2;
         v = A[(int64_t)(m0 + rr) * g.a_m + (int64_t)k1 * g.a_k1 + (int64_t)k2 * g.a_k2];
       }
-      As[kk][rr] = v;
+      va[it] = v;
       int cc, kb;
       if (b_lanes_n) { kb = e / GT; cc = e % GT; } else { cc = e / GK; kb = e % GK; }
       k = k0 + kb;
-      v = 0.0;
+      v = (T)0;
       if (n0 + cc < g.n && k < kend) {
         const int k1 = k / g.K2, k2 = k - k1 * g.K2;
         v = B[(int64_t)k1 * g.b_k1 + (int64_t)k2 * g.b_k2 + (int64_t)(n0 + cc) * g.b_n];
       }
-      Bs[kb][cc] = v;
+      vb[it] = v;
+    }
+  };
+  if (kbeg < kend) load_chunk(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += GK) {
+#pragma unroll
+    for (int it = 0; it < (GT * GK) / 256; ++it) {
+      const int e = it * 256 + threadIdx.x;
+      int rr, kk, cc, kb;
+      if (a_lanes_m) { kk = e / GT; rr = e % GT; } else { rr = e / GK; kk = e % GK; }
+      if (b_lanes_n) { kb = e / GT; cc = e % GT; } else { cc = e / GK; kb = e % GK; }
+      As[kk][rr] = va[it];
+      Bs[kb][cc] = vb[it];
     }
     __syncthreads();
+    if (k0 + GK < kend) load_chunk(k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      double a[4], b[4];
+      T a[4], b[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
 #pragma unroll
@@ -92,21 +110,27 @@ gemm64_kernel(Gemm g) {
       if (g.ksplit > 1) {
         g.partial[((int64_t)split * g.m + mm) * g.n + nn] = acc[i][j];
       } else {
-        double* c = g.C + (int64_t)bidx * g.c_b + (int64_t)mm * g.c_m + (int64_t)nn * g.c_n;
-        *c = g.alpha * acc[i][j] + (g.beta != 0.0 ? g.beta * (*c) : 0.0);
+        T* c = g.C + (int64_t)bidx * g.c_b + (int64_t)mm * g.c_m + (int64_t)nn * g.c_n;
+        *c = (T)g.alpha * acc[i][j] + (g.beta != 0.0 ? (T)g.beta * (*c) : (T)0);
       }
     }
   }
 }
 
-__global__ void gemm64_reduce_kernel(Gemm g) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output element: lanes stride over the splits, shuffle-tree sum (fixed order)
+template <typename T>
+__global__ void gemm64_reduce_kernel(GemmT<T> g) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (e >= g.m * g.n) return;
   const int mm = e / g.n, nn = e - mm * g.n;
-  double s = 0.0;
-  for (int k = 0; k < g.ksplit; ++k) s += g.partial[(int64_t)k * g.m * g.n + e];
-  double* c = g.C + (int64_t)mm * g.c_m + (int64_t)nn * g.c_n;
-  *c = g.alpha * s + (g.beta != 0.0 ? g.beta * (*c) : 0.0);
+  T s = (T)0;
+  for (int k = lane; k < g.ksplit; k += 32) s += g.partial[(int64_t)k * g.m * g.n + e];
+  s = rt::warp_sum(s);
+  if (lane == 0) {
+    T* c = g.C + (int64_t)mm * g.c_m + (int64_t)nn * g.c_n;
+    *c = (T)g.alpha * s + (g.beta != 0.0 ? (T)g.beta * (*c) : (T)0);
+  }
 }
 
 // ---- elementwise helpers ----------------------------------------------------------------
@@ -146,6 +170,26 @@ __global__ void grad_core_kernel(const float* __restrict__ d_core, const float* 
     out[i] = fmaf(two_reg, core[i], d_core[i]);
 }
 
+__global__ void f64_to_f32_kernel(const double* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = (float)x[i];
+}
+// dst[i, j] (ld ldd) = (float) src[i, j] (ld lds) for i < rows, j < cols
+__global__ void f64_to_f32_strided_kernel(const double* __restrict__ src, int64_t lds, float* __restrict__ dst,
+                                          int64_t ldd, int rows, int cols) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * cols) return;
+  const int i = e / cols, j = e - i * cols;
+  dst[(int64_t)i * ldd + j] = (float)src[(int64_t)i * lds + j];
+}
+// y(f32) = a * x(f32), a = a_host * (a_dev ? *a_dev : 1)
+__global__ void scale_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, double a_host,
+                                 const double* __restrict__ a_dev) {
+  const float a = (float)(a_host * (a_dev ? *a_dev : 1.0));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = a * x[i];
+}
+
 // Deterministic two-stage sum of squares / dot product.  stage 1: grid partials; stage 2: 1 block.
 template <typename TA, typename TB>
 __global__ void dot_partial_kernel(const TA* __restrict__ x, const TB* __restrict__ y, int64_t n,
@@ -177,26 +221,36 @@ __global__ void dot_final_kernel(const double* __restrict__ partial, int n, doub
 __global__ void __launch_bounds__(256)
 rows_times_mat_kernel(const float* __restrict__ A, int m, int r, const double* __restrict__ K,
                       float* __restrict__ C) {
-  extern __shared__ float rows[];  // [16][r]
-  const int b0 = blockIdx.x * 16;
-  for (int e = threadIdx.x; e < 16 * r; e += 256) {
+  extern __shared__ float rows[];  // [RPB][r]
+  constexpr int RPB = 4;
+  const int b0 = blockIdx.x * RPB;
+  for (int e = threadIdx.x; e < RPB * r; e += 256) {
     const int rr = e / r, cc = e - rr * r;
     rows[e] = (b0 + rr < m) ? A[(int64_t)(b0 + rr) * r + cc] : 0.0f;
   }
   __syncthreads();
   for (int j = threadIdx.x; j < r; j += 256) {
-    double acc[16];
+    double acc[RPB];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+    for (int i = 0; i < RPB; ++i) acc[i] = 0.0;
+#pragma unroll 4
     for (int k = 0; k < r; ++k) {
       const double kv = K[(int64_t)k * r + j];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = fma((double)rows[i * r + k], kv, acc[i]);
+      for (int i = 0; i < RPB; ++i) acc[i] = fma((double)rows[i * r + k], kv, acc[i]);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < RPB; ++i)
       if (b0 + i < m) C[(int64_t)(b0 + i) * r + j] = (float)acc[i];
   }
+}
+
+// dst[a, b] (row stride ldd) = src[b, a]  for an n x n matrix
+__global__ void transpose_into_kernel(const double* __restrict__ src, int n, double* __restrict__ dst, int64_t ldd) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * n) return;
+  const int a = e / n, b = e - a * n;
+  dst[(int64_t)a * ldd + b] = src[(int64_t)b * n + a];
 }
 
 // lower -> full symmetric
@@ -270,16 +324,13 @@ spd_factor_kernel(SpdBatch batch) {
       col[i] = v;
     }
     __syncthreads();
-    // trailing update: rows i > k, cols k < j <= i
-    const int mrem = n - k - 1;
-    const int cnt = mrem * (mrem + 1) / 2;
-    for (int e = tid; e < cnt; e += nt) {
-      int ii = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-      while (ii * (ii + 1) / 2 > e) --ii;
-      while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
-      const int jj = e - ii * (ii + 1) / 2;
-      const int i = k + 1 + ii, j = k + 1 + jj;
-      Lp[pk(i, j)] -= col[i] * col[j];
+    // trailing update: rows i > k, cols k < j <= i  (warp w takes rows k+1+w, +32, ...; lanes run along j)
+    {
+      const int w = tid >> 5, ln = tid & 31, nw = nt >> 5;
+      for (int i = k + 1 + w; i < n; i += nw) {
+        const double ci = col[i];
+        for (int j = k + 1 + ln; j <= i; j += 32) Lp[pk(i, j)] -= ci * col[j];
+      }
     }
     __syncthreads();
   }

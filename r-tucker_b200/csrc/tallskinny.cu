@@ -271,10 +271,19 @@ extern "C" int rt_core_axpby(const float* dS_g, const double* alpha_dev, const f
   return 0;
 }
 
+// register-tiled FP32 kernels (tallskinny_v2.cu): the default for the non-precise Gram and for apply
+extern "C" size_t rt_gram_v2_ws_bytes(int n, int ra, int rb);
+extern "C" int rt_gram_v2(const float* A, int64_t lda, const float* B, int64_t ldb, int n, int ra, int rb,
+                          double* out, void* ws, void* stream);
+extern "C" int rt_apply_v2(float* Y, int64_t ldy, int n, int rc, const float* X0, int64_t ldx0, const double* a0_dev,
+                           int nk, const float* const* X_host, const int64_t* ldx_host, const int* rk_host,
+                           const double* const* K_host, void* stream);
+
 extern "C" size_t rt_gram_ws_bytes(int n, int ra, int rb) {
   if (n <= 0 || ra <= 0 || rb <= 0) return 0;
   GramPlan p = gram_plan(n, ra, rb);
-  return (size_t)p.nsplit * ra * rb * sizeof(double);
+  const size_t v1 = (size_t)p.nsplit * ra * rb * sizeof(double), v2 = rt_gram_v2_ws_bytes(n, ra, rb);
+  return v1 > v2 ? v1 : v2;
 }
 
 extern "C" int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb, int n, int ra,
@@ -287,6 +296,7 @@ extern "C" int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb,
     return 0;
   }
   RT_REQUIRE(ws != nullptr, "rt_gram: workspace is NULL");
+  if (!precise) return rt_gram_v2(A, lda, B, ldb, n, ra, rb, out, ws, stream);
   GramPlan p = gram_plan(n, ra, rb);
   dim3 grid(p.tiles_a * p.tiles_b, p.nsplit);
   if (precise)
@@ -310,6 +320,7 @@ extern "C" int rt_apply(float* Y, int64_t ldy, int n, int rc, const float* X0, i
   RT_REQUIRE(nk >= 0 && nk <= kMaxTerms, "rt_apply: nk=%d out of range (max %d)", nk, kMaxTerms);
   RT_REQUIRE(X0 != nullptr || nk > 0, "rt_apply: nothing to compute");
   if (n == 0) return 0;
+  if (true) return rt_apply_v2(Y, ldy, n, rc, X0, ldx0, a0_dev, nk, X_host, ldx_host, rk_host, K_host, stream);
   ApplyArgs a;
   a.nk = nk;
   for (int k = 0; k < kMaxTerms; ++k) {

@@ -72,14 +72,27 @@ class StepEngine:
         self.hyper = torch.zeros(4, dtype=f64, device=dev)
         self._hyper_host = None
         self._hyper_vals = None
-        # per-factor buffers (allocated lazily in the factor's shape)
-        self.U_old = [None] * self.nf
-        self.spare = [torch.empty_like(p.data) for p in self.params]
-        self.dV_dir = [None] * self.nf        # direction kept from the previous step (old point)
-        self.dV_new = [torch.empty_like(p.data) for p in self.params]
-        self.core_old = None
-        self.dS_dir_old = None
+        # Every state buffer has a FIXED address for the life of the engine (the step is CUDA-graph
+        # capturable): the parameters are updated by device copies, not by rotating storage.
+        keep = momentum_beta is not None
+        self.spare = [torch.empty_like(p.data) for p in self.params]      # Euclidean gradient / new point
+        self.dV_new = [torch.empty_like(p.data) for p in self.params]     # direction produced by fit()
+        self.dS_dir = torch.empty_like(core.data)
+        self.U_old = [torch.empty_like(p.data) if keep else None for p in self.params]
+        self.dV_dir = [torch.empty_like(p.data) if keep else None for p in self.params]   # kept direction (old point)
+        self.core_old = torch.empty_like(core.data) if keep else None
+        self.dS_dir_old = torch.empty_like(core.data) if keep else None
+        self.M_next = [torch.empty(r, 2 * r, dtype=f64, device=dev) if keep else None for r in self.rank]
+        if self.sym:
+            self.M_next[2] = self.M_next[1]
+        self.loss_buf = torch.zeros(1, dtype=f64, device=dev)
+        self.norm_buf = torch.zeros(1, dtype=f64, device=dev)
         self.has_old = False
+        # CUDA graphs (single GPU, CUDA ops only): captured after the first eager step
+        self.use_graphs = False
+        self._graphs = {}
+        self._static_in = None
+        self._eager_steps = 0
         self.pending = None                    # (dS_dir, [dV]) produced by fit(), consumed by step()
         self.loss = None
 
@@ -182,29 +195,28 @@ class StepEngine:
         use_momentum = self.beta is not None and self.has_old
         dV_new = self.dV_new
         if use_momentum:
-            M = []
-            for k in range(self.nf):
-                Mk = torch.cat([ops.gram(self._U(k), self.U_old[k]), ops.gram(self._U(k), self.dV_dir[k])], dim=1)
-                M.append(Mk.contiguous())
-            self._allreduce(*[M[k] for k in self._entity_factor_ids()])
+            # transport Grams M_k = U_k^T [U_old_k | dV_dir_k]: produced by the previous retraction from its
+            # own small matrices (no N-sized pass, no all-reduce: replicated); see rt_small_retract
+            M = self.M_next
             with self._stage("small_project"):
                 pS_beta, K, L = small.project(core, self.core_old, self.dS_dir_old, M[0], M[1],
                                               M[2] if not sym else M[1], self.hyper)
-            dS_dir = ops.core_axpby(dS_g, alpha, pS_beta)
+            dS_dir = ops.core_axpby(dS_g, alpha, pS_beta, out=self.dS_dir)
             for k in range(self.nf):
                 rk = self.rank[k]
                 ops.apply(dV_new[k], dV_g[k], alpha,
                           [(self.U_old[k], K[k][:rk]), (self.dV_dir[k], K[k][rk:]), (self._U(k), L[k])])
         else:
-            dS_dir = ops.core_axpby(dS_g, alpha, None)
+            dS_dir = ops.core_axpby(dS_g, alpha, None, out=self.dS_dir)
             for k in range(self.nf):
                 ops.apply(dV_new[k], dV_g[k], alpha, [])
         t_tall.__exit__(None, None, None)
         self.pending = (dS_dir, dV_new)
-        self.loss = loss
-        self.rgrad_norm = norm
-        self.debug = dict(q=q, H=H, dS_g=dS_g, dV_g=dV_g, alpha=alpha, bce_sum=bce_sum)
-        return norm
+        self.loss_buf.copy_(loss)
+        self.norm_buf.copy_(norm)
+        self.loss = self.loss_buf
+        self.rgrad_norm = self.norm_buf
+        return self.norm_buf
 
     # -------------------------------------------------------------------------------------------
     def step(self, lr):
@@ -219,32 +231,87 @@ class StepEngine:
             grams = [ops.gram(v, v, precise=True) for v in dV]
         self._allreduce(*[grams[k] for k in self._entity_factor_ids()])
         with self._stage("small_retract_hosvd"):
-            core_new, Z1, Z2 = small.retract(core, dS_dir, grams[0], grams[1],
-                                             grams[2] if not sym else grams[1], self.hyper)
+            core_new, Z1, Z2, _ = small.retract(core, dS_dir, grams[0], grams[1],
+                                                grams[2] if not sym else grams[1], self.hyper,
+                                                transport_out=self.M_next if self.beta is not None else None)
         new_U = []
         with self._stage("retract_apply"):
             for k in range(self.nf):
                 # spare[k] held dV_g during fit(); it is free again now
                 new_U.append(ops.apply(self.spare[k], None, None, [(self._U(k), Z1[k]), (dV[k], Z2[k])]))
-        # ---- rotate state: the current point becomes the "old" point of the kept direction ----
+        # ---- the current point becomes the "old" point of the kept direction; parameters written back
+        #      in place (reference: p.data.add_(new - p), optim.py:111-114) ----
         keep = self.beta is not None
-        for k in range(self.nf):
-            prev_U = self.params[k].data
-            self.params[k].data = new_U[k]
-            recycled = self.U_old[k] if self.U_old[k] is not None else torch.empty_like(prev_U)
+        with self._stage("write_back"):
+            for k in range(self.nf):
+                if keep:
+                    self.U_old[k].copy_(self.params[k].data)
+                    self.dV_dir[k].copy_(dV[k])
+                self.params[k].data.copy_(new_U[k])
             if keep:
-                self.U_old[k] = prev_U
-                self.spare[k] = recycled
-                prev_dir = self.dV_dir[k] if self.dV_dir[k] is not None else torch.empty_like(prev_U)
-                self.dV_dir[k] = dV[k]
-                self.dV_new[k] = prev_dir
-            else:
-                self.spare[k] = prev_U
-        prev_core = self.core.data
-        self.core.data = core_new
-        if keep:
-            self.core_old = prev_core
-            self.dS_dir_old = dS_dir
-            self.has_old = True
+                self.core_old.copy_(self.core.data)
+                self.dS_dir_old.copy_(dS_dir)
+                self.has_old = True
+            self.core.data.copy_(core_new)
         self.pending = None
-        return core_new
+        return self.core.data
+
+    # -------------------------------------------------------------------------------------------
+    # CUDA-graph front end: same arithmetic, replayed from two captured graphs (fit, step).
+    def _graphs_ok(self):
+        return (self.use_graphs and self.group is None and self.dev.type == "cuda" and self.ops is cuda_ops
+                and getattr(self, "timers", None) is None)
+
+    def fit_auto(self, rel_idx, sub_idx, targets: SparseTargets, label_smoothing, reg, lr_hint=0.0,
+                 normalize_grad=1.0):
+        """fit() through a captured CUDA graph once the state machine is in steady state."""
+        steady = self._eager_steps >= 1 and (self.beta is None or self.has_old)
+        if not (self._graphs_ok() and steady):
+            return self.fit(rel_idx, sub_idx, targets, label_smoothing, reg, lr_hint, normalize_grad)
+        B, nnz = rel_idx.shape[0], targets.idx.shape[0]
+        si = self._static_in
+        if si is None or si["B"] != B or si["cap"] < nnz:
+            cap = max(2 * nnz, 4 * B, 1024)
+            i32 = torch.int32
+            si = dict(B=B, cap=cap, rel=torch.zeros(B, dtype=i32, device=self.dev),
+                      sub=torch.zeros(B, dtype=i32, device=self.dev),
+                      off=torch.zeros(B + 1, dtype=i32, device=self.dev),
+                      idx=torch.zeros(cap, dtype=i32, device=self.dev))
+            self._static_in = si
+            self._graphs = {k: v for k, v in self._graphs.items() if k[0] != "fit"}
+        si["rel"].copy_(rel_idx, non_blocking=True)
+        si["sub"].copy_(sub_idx, non_blocking=True)
+        si["off"].copy_(targets.off, non_blocking=True)
+        si["idx"][:nnz].copy_(targets.idx, non_blocking=True)
+        self._set_hyper(self._hyper_vals[0], reg, self.beta, normalize_grad if normalize_grad else 0.0)
+        key = ("fit", B, float(label_smoothing))
+        g = self._graphs.get(key)
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.fit(si["rel"], si["sub"], SparseTargets(si["off"], si["idx"]), label_smoothing, reg,
+                         lr_hint, normalize_grad)
+            self._graphs[key] = g
+        g.replay()
+        self.pending = (self.dS_dir, self.dV_new)
+        self.loss, self.rgrad_norm = self.loss_buf, self.norm_buf
+        return self.norm_buf
+
+    def step_auto(self, lr):
+        steady = self._eager_steps >= 1 and (self.beta is None or self.has_old)
+        if not (self._graphs_ok() and steady):
+            out = self.step(lr)
+            self._eager_steps += 1
+            return out
+        assert self.pending is not None, "step() called before fit()"
+        hv = self._hyper_vals
+        self._set_hyper(lr, hv[1], hv[2], hv[3])
+        g = self._graphs.get(("step",))
+        if g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.step(lr)
+            self._graphs[("step",)] = g
+        g.replay()
+        self.pending = None
+        return self.core.data

@@ -127,20 +127,29 @@ def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None,
 
 
 # ---------------------------------------------------------------- (c) tall-skinny
-def gram(A, B, out=None, ws=None, precise=False):
+USE_TENSOR_CORES = False   # opt-in: tall-skinny passes on tcgen05 (3xTF32, ~3e-6 accuracy) instead of fp32 FFMA (~3e-7)
+
+
+def gram(A, B, out=None, ws=None, precise=False, tc=None):
     """out[ra,rb] (f64) = A^T B over the rows (precise: exact fp64 accumulation)."""
     require_cuda(A, B)
     n, ra = A.shape
     rb = B.shape[1]
     assert B.shape[0] == n and A.stride(1) == 1 and B.stride(1) == 1
     out = out if out is not None else torch.empty(ra, rb, dtype=f64, device=A.device)
+    tc = USE_TENSOR_CORES if tc is None else tc
+    if tc and not precise and n >= 1024 and lib().rt_gram_tc_supported(ra, rb):
+        ws = _ws(lib().rt_gram_tc_ws_bytes(n, ra, rb), A.device)
+        check(lib().rt_gram_tc(ptr(A), A.stride(0), ptr(B), B.stride(0), n, ra, rb, ptr(_c(out, f64)), ptr(ws),
+                               stream_ptr()), "rt_gram_tc")
+        return out
     ws = ws if ws is not None else _ws(lib().rt_gram_ws_bytes(n, ra, rb), A.device)
     check(lib().rt_gram(ptr(A), A.stride(0), ptr(B), B.stride(0), n, ra, rb, ptr(_c(out, f64)),
                         int(bool(precise)), ptr(ws), stream_ptr()), "rt_gram")
     return out
 
 
-def apply(Y, X0, a0_dev, terms):
+def apply(Y, X0, a0_dev, terms, tc=None):
     """Y = a0*X0 + sum_k X_k @ K_k;  terms = [(X_k f32 [n,rk], K_k f64 [rk,rc]), ...]."""
     require_cuda(Y, X0, a0_dev, *[t for pair in terms for t in pair])
     n, rc = Y.shape
@@ -151,6 +160,12 @@ def apply(Y, X0, a0_dev, terms):
     Kp = (C.c_void_p * max(nk, 1))(*[_c(k, f64).data_ptr() for _, k in terms])
     for x, k in terms:
         assert x.dtype == f32 and x.stride(1) == 1 and k.shape == (x.shape[1], rc) and x.shape[0] == n
+    tc = USE_TENSOR_CORES if tc is None else tc
+    if tc and nk >= 1 and n >= 1024 and lib().rt_apply_tc_supported(rc, nk, rk):
+        ws = _ws(lib().rt_apply_tc_ws_bytes(rc, nk, rk), Y.device)
+        check(lib().rt_apply_tc(ptr(Y), Y.stride(0), n, rc, ptr(X0), X0.stride(0) if X0 is not None else 0,
+                                ptr(a0_dev), nk, Xp, ld, rk, Kp, ptr(ws), stream_ptr()), "rt_apply_tc")
+        return Y
     check(lib().rt_apply(ptr(Y), Y.stride(0), n, rc, ptr(X0), X0.stride(0) if X0 is not None else 0,
                          ptr(a0_dev), nk, Xp, ld, rk, Kp, stream_ptr()), "rt_apply")
     return Y
@@ -222,18 +237,19 @@ class SmallStage:
               "rt_small_project")
         return pS, K, L
 
-    def retract(self, core, dS_dir, gram_R, gram_S, gram_O, hyper):
+    def retract(self, core, dS_dir, gram_R, gram_S, gram_O, hyper, transport_out=None):
         dev, (r0, r1, r2) = self.device, self._r()
         core_new = torch.empty_like(core)
         Z1 = [torch.empty(r, r, dtype=f64, device=dev) for r in (r0, r1, r2)]
         Z2 = [torch.empty(r, r, dtype=f64, device=dev) for r in (r0, r1, r2)]
+        Mn = list(transport_out) if transport_out is not None else [None, None, None]
         if self.sym:
-            Z1[2], Z2[2] = Z1[1], Z2[1]
+            Z1[2], Z2[2], Mn[2] = Z1[1], Z2[1], Mn[1]
         check(lib().rt_small_retract(ptr(core), ptr(dS_dir), ptr(gram_R), ptr(gram_S), ptr(gram_O),
                                      ptr(hyper), r0, r1, r2, self.sym, ptr(core_new), ptr(Z1[0]), ptr(Z2[0]),
-                                     ptr(Z1[1]), ptr(Z2[1]), ptr(Z1[2]), ptr(Z2[2]), ptr(self.ws),
-                                     stream_ptr()), "rt_small_retract")
-        return core_new, Z1, Z2
+                                     ptr(Z1[1]), ptr(Z2[1]), ptr(Z1[2]), ptr(Z2[2]), ptr(Mn[0]), ptr(Mn[1]),
+                                     ptr(Mn[2]), ptr(self.ws), stream_ptr()), "rt_small_retract")
+        return core_new, Z1, Z2, Mn
 
 
 def eigh(A):

@@ -35,7 +35,7 @@ class _RiemannianBase(Optimizer):
     uses_momentum = False
 
     def __init__(self, params, rank, max_lr, momentum_beta: Optional[float] = None, group=None,
-                 n_total=None, n_begin=0, score_variant=0, ops=None):
+                 n_total=None, n_begin=0, score_variant=0, ops=None, use_graphs=False):
         self.rank = rank
         self.max_lr = max_lr
         self.lr = max_lr
@@ -48,6 +48,7 @@ class _RiemannianBase(Optimizer):
         self.momentum = None
         self.loss = None
         self._engine = None
+        self._use_graphs = bool(use_graphs)
         self._engine_kw = dict(group=group, n_total=n_total, n_begin=n_begin, score_variant=score_variant,
                                ops=ops)
 
@@ -64,6 +65,7 @@ class _RiemannianBase(Optimizer):
             core, factors = self._manifold_params()
             self._engine = StepEngine(core, factors, self.symmetric, max(B, 1),
                                       self.momentum_beta if self.uses_momentum else None, **self._engine_kw)
+            self._engine.use_graphs = self._use_graphs
         elif B > self._engine.small.B:
             eng = self._engine
             eng.small = eng.ops.SmallStage(eng.rank, B, eng.sym, eng.dev)
@@ -78,8 +80,8 @@ class _RiemannianBase(Optimizer):
                 "in place of the reference's loss lambda: there is no autodiff / dense-target path.")
         sf = loss_fn.score_fn
         eng = self._get_engine(sf.relation_idx.shape[0])
-        norm = eng.fit(sf.relation_idx, sf.subject_idx, loss_fn.targets, loss_fn.label_smoothing,
-                       loss_fn.reg_coeff, lr_hint=self.param_groups[0]["lr"], normalize_grad=normalize_grad)
+        norm = eng.fit_auto(sf.relation_idx, sf.subject_idx, loss_fn.targets, loss_fn.label_smoothing,
+                            loss_fn.reg_coeff, lr_hint=self.param_groups[0]["lr"], normalize_grad=normalize_grad)
         self.loss = eng.loss.float().reshape(())
         self.direction = eng.pending
         return norm.float().reshape(())
@@ -89,7 +91,7 @@ class _RiemannianBase(Optimizer):
         """X <- retraction(X - lr * direction)  (reference: optim.py ``step``)."""
         if self._engine is None or self._engine.pending is None:
             raise RuntimeError("step() must follow fit()")
-        self._engine.step(self.param_groups[0]["lr"])
+        self._engine.step_auto(self.param_groups[0]["lr"])
 
 
 class AsymRGD(_RiemannianBase):

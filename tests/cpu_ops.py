@@ -84,8 +84,11 @@ def apply(Y, X0, a0_dev, terms):
 
 
 def core_axpby(dS_g, alpha_dev, pS_beta, out=None):
-    res = float(alpha_dev) * dS_g + (pS_beta if pS_beta is not None else 0)
-    return res.to(dS_g.dtype)
+    res = (float(alpha_dev) * dS_g + (pS_beta if pS_beta is not None else 0)).to(dS_g.dtype)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def chol_psd(G, tol=1e-12):
@@ -189,7 +192,7 @@ class SmallStage:
             L.append((-(M[k] @ Kk)).contiguous())
         return (beta * pS).to(core.dtype), K, L
 
-    def retract(self, core, dS_dir, gram_R, gram_S, gram_O, hyper):
+    def retract(self, core, dS_dir, gram_R, gram_S, gram_O, hyper, transport_out=None):
         r, lr = self.r, float(hyper[0])
         grams = [gram_R, gram_S, gram_S if self.sym else gram_O]
         C = self.C
@@ -222,4 +225,8 @@ class SmallStage:
         core_new = _grouped_contract(Cp, Bk, Wa, Wb)[0]
         Z1 = [Y[k][:r[k]].contiguous() for k in range(3)]
         Z2 = [(-lr * (Linvs[k].T @ Y[k][r[k]:])).contiguous() for k in range(3)]
-        return core_new.to(core.dtype), Z1, Z2
+        if transport_out is not None:
+            for k in range(3):
+                if transport_out[k] is not None and not (self.sym and k == 2):
+                    transport_out[k].copy_(torch.cat([Z1[k].T, Z2[k].T @ grams[k]], dim=1))
+        return core_new.to(core.dtype), Z1, Z2, transport_out

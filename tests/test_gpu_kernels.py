@@ -302,3 +302,38 @@ def test_score_bce_tcgen05(cuda_device, B, N, r2, ls, scale):
     assert relerr(dO, dO_ref) < TC_REL, relerr(dO, dO_ref)
     loss2, H2, dO2 = ops.score_bce_fwd_bwd(q.to(dev), qp.to(dev), O.to(dev), off.to(dev), idx.to(dev), ls, variant=1)
     assert torch.equal(H, H2) and torch.equal(dO, dO2) and torch.equal(loss, loss2)      # deterministic
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 (3xTF32) variants of the tall-skinny passes: fp32-level accuracy required
+@pytest.mark.parametrize("n,ra,rb", [(4097, 200, 200), (40943, 200, 200), (5000, 20, 20), (3000, 10, 40), (2048, 256, 64), (70001, 130, 200)])
+def test_gram_tcgen05(cuda_device, n, ra, rb):
+    from rtucker_b200 import ops
+    g = torch.Generator().manual_seed(n + ra + 3)
+    A = torch.randn(n, ra, generator=g)
+    Bm = torch.randn(n, rb, generator=g) + 0.3
+    ref = A.double().T @ Bm.double()
+    out = ops.gram(A.to(cuda_device), Bm.to(cuda_device), tc=True)
+    assert relerr(out, ref) < 5e-6, relerr(out, ref)
+    assert torch.equal(out, ops.gram(A.to(cuda_device), Bm.to(cuda_device), tc=True))
+
+
+@pytest.mark.parametrize("n,rc,rks", [(4097, 200, [200, 200, 200]), (40943, 200, [200, 200]), (3000, 20, [20]),
+                                      (1500, 10, [10, 10]), (2500, 64, [33, 17, 64, 5])])
+def test_apply_tcgen05(cuda_device, n, rc, rks):
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(n + rc + 5)
+    X0 = torch.randn(n, rc, generator=g)
+    a0 = torch.tensor([0.37], dtype=torch.float64)
+    terms = [(torch.randn(n, rk, generator=g), torch.randn(rk, rc, generator=g, dtype=torch.float64)) for rk in rks]
+    ref = a0 * X0.double() + sum(x.double() @ k for x, k in terms)
+    Y = torch.empty(n, rc, device=dev)
+    ops.apply(Y, X0.to(dev), a0.to(dev), [(x.to(dev), k.to(dev)) for x, k in terms], tc=True)
+    assert relerr(Y, ref) < 5e-6, relerr(Y, ref)
+    Y2 = X0.to(dev).clone()                      # in place on X0, no scalar
+    ops.apply(Y2, Y2, None, [(x.to(dev), k.to(dev)) for x, k in terms], tc=True)
+    assert relerr(Y2, X0.double() + sum(x.double() @ k for x, k in terms)) < 5e-6
+    Y3 = torch.empty(n, rc, device=dev)          # no X0 at all
+    ops.apply(Y3, None, None, [(x.to(dev), k.to(dev)) for x, k in terms], tc=True)
+    assert relerr(Y3, sum(x.double() @ k for x, k in terms)) < 5e-6

@@ -153,3 +153,45 @@ def test_step_parity_tcgen05_variant(cuda_device):
         x_dev = A.Point(pc.data.double().cpu(), [p.data.double().cpu() for p in pf], sym)
         pr = probes(x_ref, torch.Generator().manual_seed(it))
         assert float((pr(x_dev) - pr(x_ref)).norm() / pr(x_ref).norm()) < 2e-3
+
+
+@pytest.mark.parametrize("sym,beta", [(False, 0.8), (True, None)])
+def test_cuda_graph_replay_is_bitwise_identical_to_eager(cuda_device, sym, beta):
+    """The optimiser front end captures fit() and step() in CUDA graphs after the first eager step; the
+    kernels are deterministic, so the graphed trajectory must equal the eager one bit for bit."""
+    from rtucker_b200 import asymmetric, symmetric
+    from rtucker_b200.engine import SparseTargets
+    from rtucker_b200.optim import FusedLoss
+    dev = cuda_device
+    N, M, rank, B = 2000, 12, (6, 40, 40), 128
+    mod = symmetric if sym else asymmetric
+
+    def run(use_graphs):
+        torch.manual_seed(5)
+        model = mod.R_TuckER((N, M), rank)
+        model.init(None)
+        with torch.no_grad():
+            model.core.mul_(800.0)
+        model.to(dev)
+        params = [model.core, model.E.weight, model.R.weight] if sym else \
+            [model.core, model.S.weight, model.R.weight, model.O.weight]
+        opt = (mod.RSGDwithMomentum(params, rank, 50.0, beta, use_graphs=use_graphs) if beta is not None
+               else mod.RGD(params, rank, 50.0, use_graphs=use_graphs))
+        g = torch.Generator().manual_seed(9)
+        out = []
+        for it in range(6):
+            rel, sub, off, idx = make_batch(N, M, B, g, max_obj=3 + it % 3)     # nnz varies between batches
+            loss_fn = FusedLoss(model(sub.to(dev), rel.to(dev)), SparseTargets(off.int().to(dev), idx.int().to(dev)), 0.1, 1e-9)
+            nrm = opt.fit(loss_fn, None)
+            opt.param_groups[0]["lr"] = 50.0 + it          # the learning rate lives in device memory
+            opt.step()
+            out.append((float(opt.loss.cpu()), float(nrm.cpu())))
+        torch.cuda.synchronize()
+        return out, [p.data.clone() for p in params], opt
+
+    eager, p_eager, _ = run(False)
+    graphed, p_graph, opt = run(True)
+    assert len(opt._engine._graphs) == 2                  # fit + step were captured
+    assert eager == graphed
+    for a, b in zip(p_eager, p_graph):
+        assert torch.equal(a, b)
