@@ -60,16 +60,15 @@ __device__ __forceinline__ int pair_index(int bi, int bj, int i) {  // i in [0, 
   return (i < EB) ? bi * EB + i : bj * EB + (i - EB);
 }
 
-// Rotation parameters for the pivot (app, aqq, apq).  The ANGLE is evaluated in fp32 (MUFU + FFMA,
-// a short dependent chain); (c, s) is then re-normalised in fp64 so the rotation is orthogonal to
-// ~1e-21.  An fp32-accurate angle leaves a residual of ~1e-7 |apq| instead of an exact zero, which only
-// replaces the last quadratic step of the Jacobi iteration by one more sweep.
-__device__ __forceinline__ void rotation(double app, double aqq, double apq, double& c, double& s) {
+// Rotation for the pivot with diagonal difference d = a_qq - a_pp and off-diagonal a = a_pq (fp32).  The ANGLE
+// is evaluated in fp32 (MUFU + FFMA, a short dependent chain); (c, s) is then re-normalised in fp64 so the
+// rotation is orthogonal to ~1e-15.  An fp32-accurate angle leaves a residual of ~1e-7 |a_pq| instead of an
+// exact zero, which only replaces the last quadratic step of the Jacobi iteration by one more sweep.
+__device__ __forceinline__ void rotation(float d, float a, double& c, double& s) {
   c = 1.0;
   s = 0.0;
-  if (apq * apq > 1e-34) {   // entries are scaled to <= 1: keeps the fp32 chain inside float range
-    const float d = (float)(aqq - app), a = (float)apq;
-    // tan(2 theta) = 2 apq / d:  cos(2 theta) = |d| / h,  h = sqrt(d^2 + 4 apq^2)
+  if (a * a > 1e-34f) {   // entries are scaled to <= 1: keeps the fp32 chain inside float range
+    // tan(2 theta) = 2 a / d:  cos(2 theta) = |d| / h,  h = sqrt(d^2 + 4 a^2)
     const float x = fmaf(d, d, 4.0f * a * a);
     const float rh = rsqrtf(x);
     const float y = fmaf(0.5f * fabsf(d), rh, 0.5f);       // cos^2(theta) in [0.5, 1]
@@ -119,87 +118,170 @@ __device__ __forceinline__ void warp_mm32(const double* As, const double* Bs, do
   }
 }
 
+// The tile that STEERS the rotations lives in fp32 (shifted by the mean diagonal so that diagonal
+// differences keep their accuracy); only the accumulated rotation Q and the (c, s) pairs are fp64.
+// Phase B re-derives every tile, including the pair's own, as Q_k^T A_kl Q_l in fp64, so the
+// transformation applied to the matrix is an exact orthogonal similarity whatever the angles are.
+constexpr int ELDF = EP + 1;
 struct VisitSmem {
-  double* S;      // [EP][ELD] tile
-  double* Q;      // [EP][ELD] accumulated rotations
-  double* cs;     // [2][EB][2]  (c, s), double buffered over inner rounds
+  float* S[2];    // [EP][ELDF] steering tile, double buffered: round r reads S[r&1], writes S[(r+1)&1]
+  double* Q;      // [EP][ELD] accumulated rotations (fp64)
+  double* cs;     // [2][EB][2]  (c, s) of the rotations, double buffered over inner rounds
+  float* csf;     // [2][EB][2]  fp32 copies
   int* pq;        // [2][EB][2]  (p, q)
+  int* pid;       // [2][EP]     pair id of every tile index in that round
 };
 
-__device__ __forceinline__ void set_pairs(const VisitSmem& m, int buf, int t, bool intra_pass) {
+__device__ __forceinline__ void pair_of(int t, int tid, bool intra_pass, int& p, int& q) {
+  if (intra_pass) {
+    rr_pair(EB, t, tid % (EB / 2), p, q);
+    const int o = (tid < EB / 2) ? 0 : EB;
+    p += o; q += o;
+  } else {
+    p = tid;
+    q = EB + (tid + t) % EB;
+  }
+}
+
+__device__ __forceinline__ void publish(const VisitSmem& m, int nb, int tid, int p, int q, double c, double s) {
+  m.pq[(nb * EB + tid) * 2 + 0] = p; m.pq[(nb * EB + tid) * 2 + 1] = q;
+  m.pid[nb * EP + p] = tid; m.pid[nb * EP + q] = tid;
+  m.cs[(nb * EB + tid) * 2 + 0] = c; m.cs[(nb * EB + tid) * 2 + 1] = s;
+  m.csf[(nb * EB + tid) * 2 + 0] = (float)c; m.csf[(nb * EB + tid) * 2 + 1] = (float)s;
+}
+
+// rotations of the FIRST inner round, from the tile itself
+__device__ __forceinline__ void first_pairs(const VisitSmem& m, bool intra_pass) {
   const int tid = threadIdx.x;
   if (tid < EB) {
     int p, q;
-    if (intra_pass) {
-      rr_pair(EB, t, tid % (EB / 2), p, q);
-      const int o = (tid < EB / 2) ? 0 : EB;
-      p += o; q += o;
-    } else {
-      p = tid;
-      q = EB + (tid + t) % EB;
-    }
-    m.pq[(buf * EB + tid) * 2 + 0] = p;
-    m.pq[(buf * EB + tid) * 2 + 1] = q;
+    pair_of(0, tid, intra_pass, p, q);
+    const float* S = m.S[0];
     double c, s;
-    rotation(m.S[p * ELD + p], m.S[q * ELD + q], m.S[p * ELD + q], c, s);
-    m.cs[(buf * EB + tid) * 2 + 0] = c;
-    m.cs[(buf * EB + tid) * 2 + 1] = s;
+    rotation(S[q * ELDF + q] - S[p * ELDF + p], S[p * ELDF + q], c, s);
+    publish(m, 0, tid, p, q, c, s);
   }
 }
 
-// S <- R^T S R for the EB disjoint rotations of buffer `buf` (one 2x2 block per thread)
-__device__ __forceinline__ void update_S(const VisitSmem& m, int buf) {
-  const double* cs = m.cs + buf * EB * 2;
-  const int* pq = m.pq + buf * EB * 2;
-  for (int blk = threadIdx.x; blk < EB * EB; blk += kEigThreads) {
-    const int k = blk / EB, l = blk % EB;
-    const double ck = cs[k * 2], sk = cs[k * 2 + 1], cl = cs[l * 2], sl = cs[l * 2 + 1];
-    const int p = pq[k * 2], q = pq[k * 2 + 1], u = pq[l * 2], v = pq[l * 2 + 1];
-    const double m00 = m.S[p * ELD + u], m01 = m.S[p * ELD + v];
-    const double m10 = m.S[q * ELD + u], m11 = m.S[q * ELD + v];
-    const double t00 = ck * m00 - sk * m10, t01 = ck * m01 - sk * m11;
-    const double t10 = sk * m00 + ck * m10, t11 = sk * m01 + ck * m11;
-    m.S[p * ELD + u] = cl * t00 - sl * t01; m.S[p * ELD + v] = sl * t00 + cl * t01;
-    m.S[q * ELD + u] = cl * t10 - sl * t11; m.S[q * ELD + v] = sl * t10 + cl * t11;
+// Rotations of round r+1, computed by lanes 0..EB-1 of warp 0 WHILE the other warps apply round r:
+// the pivot entries of S_{r+1} = J_r^T S_r J_r are closed-form in S_r (read-only this round) and the
+// rotations of round r:  S'[i,j] = sum_{a in pair(i)} sum_{b in pair(j)} J[a,i] J[b,j] S[a,b].
+__device__ __forceinline__ void next_pairs(const VisitSmem& m, int buf, int t_next, bool intra_next) {
+  const int tid = threadIdx.x;
+  if (tid < EB) {
+    int p, q;
+    pair_of(t_next, tid, intra_next, p, q);
+    const float* S = m.S[buf];
+    const float* cs = m.csf + buf * EB * 2;
+    const int* pq = m.pq + buf * EB * 2;
+    const int* pid = m.pid + buf * EP;
+    const int kp = pid[p], kq = pid[q];
+    const int a1 = pq[kp * 2], a2 = pq[kp * 2 + 1], b1 = pq[kq * 2], b2 = pq[kq * 2 + 1];
+    const float cp = cs[kp * 2], sp = cs[kp * 2 + 1], cq = cs[kq * 2], sq = cs[kq * 2 + 1];
+    // column p of J_r is wa1 e_a1 + wa2 e_a2, column q is wb1 e_b1 + wb2 e_b2
+    const float wa1 = (p == a1) ? cp : sp, wa2 = (p == a1) ? -sp : cp;
+    const float wb1 = (q == b1) ? cq : sq, wb2 = (q == b1) ? -sq : cq;
+    const float saa = wa1 * (wa1 * S[a1 * ELDF + a1] + wa2 * S[a1 * ELDF + a2]) +
+                      wa2 * (wa1 * S[a2 * ELDF + a1] + wa2 * S[a2 * ELDF + a2]);
+    const float sbb = wb1 * (wb1 * S[b1 * ELDF + b1] + wb2 * S[b1 * ELDF + b2]) +
+                      wb2 * (wb1 * S[b2 * ELDF + b1] + wb2 * S[b2 * ELDF + b2]);
+    const float sab = wa1 * (wb1 * S[a1 * ELDF + b1] + wb2 * S[a1 * ELDF + b2]) +
+                      wa2 * (wb1 * S[a2 * ELDF + b1] + wb2 * S[a2 * ELDF + b2]);
+    double c, s;
+    rotation(sbb - saa, sab, c, s);
+    publish(m, buf ^ 1, tid, p, q, c, s);
   }
 }
 
-__device__ __forceinline__ void update_Q(const VisitSmem& m, int buf, int first_thread) {
-  const double* cs = m.cs + buf * EB * 2;
-  const int* pq = m.pq + buf * EB * 2;
+// S[buf^1] <- R^T S[buf] R (fp32) and Q <- Q R (fp64) for the EB disjoint rotations of `buf`; executed by the
+// threads first_thread .. kEigThreads-1 (warp 0 is busy with the next rotations).  Every thread first LOADS
+// all of its work, then computes, then stores, so the independent chains overlap.
+__device__ __forceinline__ void apply_round(const VisitSmem& m, int buf, int first_thread) {
+  const double* __restrict__ cs = m.cs + buf * EB * 2;
+  const float* __restrict__ csf = m.csf + buf * EB * 2;
+  const int* __restrict__ pq = m.pq + buf * EB * 2;
+  const float* __restrict__ Si = m.S[buf];
+  float* __restrict__ So = m.S[buf ^ 1];
+  double* __restrict__ Q = m.Q;
   const int nthr = kEigThreads - first_thread;
-  for (int it = threadIdx.x - first_thread; it < EP * EB; it += nthr) {
-    if (it < 0) break;
-    const int row = it / EB, l = it % EB;
-    const double cl = cs[l * 2], sl = cs[l * 2 + 1];
-    const int u = pq[l * 2], v = pq[l * 2 + 1];
-    const double qu = m.Q[row * ELD + u], qv = m.Q[row * ELD + v];
-    m.Q[row * ELD + u] = cl * qu - sl * qv;
-    m.Q[row * ELD + v] = sl * qu + cl * qv;
+  const int t0 = threadIdx.x - first_thread;
+  if (t0 < 0) return;
+  constexpr int NB = 2, NQ = 3;
+  static_assert(EB * EB <= NB * (kEigThreads - 32) && EP * EB <= NQ * (kEigThreads - 32), "work split");
+  int p[NB], q[NB], u[NB], v[NB];
+  float ck[NB], sk[NB], cl[NB], sl[NB], m00[NB], m01[NB], m10[NB], m11[NB];
+  bool okb[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int blk = t0 + i * nthr;
+    okb[i] = blk < EB * EB;
+    const int k = okb[i] ? blk / EB : 0, l = okb[i] ? blk % EB : 0;
+    ck[i] = csf[k * 2]; sk[i] = csf[k * 2 + 1]; cl[i] = csf[l * 2]; sl[i] = csf[l * 2 + 1];
+    p[i] = pq[k * 2]; q[i] = pq[k * 2 + 1]; u[i] = pq[l * 2]; v[i] = pq[l * 2 + 1];
+    m00[i] = Si[p[i] * ELDF + u[i]]; m01[i] = Si[p[i] * ELDF + v[i]];
+    m10[i] = Si[q[i] * ELDF + u[i]]; m11[i] = Si[q[i] * ELDF + v[i]];
+  }
+  int qr[NQ], qu_i[NQ], qv_i[NQ];
+  double qc[NQ], qs[NQ], qu[NQ], qv[NQ];
+  bool okq[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int it = t0 + i * nthr;
+    okq[i] = it < EP * EB;
+    qr[i] = okq[i] ? it / EB : 0;
+    const int l = okq[i] ? it % EB : 0;
+    qc[i] = cs[l * 2]; qs[i] = cs[l * 2 + 1];
+    qu_i[i] = pq[l * 2]; qv_i[i] = pq[l * 2 + 1];
+    qu[i] = Q[qr[i] * ELD + qu_i[i]]; qv[i] = Q[qr[i] * ELD + qv_i[i]];
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const float t00 = ck[i] * m00[i] - sk[i] * m10[i], t01 = ck[i] * m01[i] - sk[i] * m11[i];
+    const float t10 = sk[i] * m00[i] + ck[i] * m10[i], t11 = sk[i] * m01[i] + ck[i] * m11[i];
+    m00[i] = cl[i] * t00 - sl[i] * t01; m01[i] = sl[i] * t00 + cl[i] * t01;
+    m10[i] = cl[i] * t10 - sl[i] * t11; m11[i] = sl[i] * t10 + cl[i] * t11;
+  }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const double a = qc[i] * qu[i] - qs[i] * qv[i], bb = qs[i] * qu[i] + qc[i] * qv[i];
+    qu[i] = a; qv[i] = bb;
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    if (okb[i]) {
+      So[p[i] * ELDF + u[i]] = m00[i]; So[p[i] * ELDF + v[i]] = m01[i];
+      So[q[i] * ELDF + u[i]] = m10[i]; So[q[i] * ELDF + v[i]] = m11[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    if (okq[i]) { Q[qr[i] * ELD + qu_i[i]] = qu[i]; Q[qr[i] * ELD + qv_i[i]] = qv[i]; }
   }
 }
 
 // One visit of a block pair by the whole CTA: (first round of a sweep only) one cyclic pass over the
 // pairs INSIDE each of the two blocks, then one pass over the EB*EB cross pairs, as rounds of EB
 // disjoint rotations.  Over a sweep every index pair of the matrix is rotated exactly once: this is
-// cyclic Jacobi whose rotations are applied to the rest of the matrix tile-wise in phase B.
-// Pipeline per inner round: [S update] | sync | [warp 0: next rotations  ||  warps 1..: Q update] | sync.
+// cyclic Jacobi whose rotations are applied to the matrix tile-wise in phase B.
+// Pipeline, ONE barrier per inner round:  warp 0 derives the rotations of round r+1 from S_r and the
+// rotations of round r, while warps 1.. apply round r (S_r -> S_{r+1} in fp32, Q <- Q R_r in fp64).
 __device__ void cta_visit(const VisitSmem& m, bool intra) {
   const int tid = threadIdx.x;
   for (int e = tid; e < EP * EP; e += kEigThreads) m.Q[(e / EP) * ELD + (e % EP)] = (e / EP == e % EP) ? 1.0 : 0.0;
   const int n_intra = intra ? EB - 1 : 0;
   const int total = n_intra + EB;
-  set_pairs(m, 0, 0, n_intra > 0);
+  first_pairs(m, n_intra > 0);
   __syncthreads();
   for (int r = 0; r < total; ++r) {
     const int buf = r & 1;
-    update_S(m, buf);
-    __syncthreads();
-    if (r + 1 < total) {
-      const int rn = r + 1;
-      if (tid < 32) set_pairs(m, buf ^ 1, rn < n_intra ? rn : rn - n_intra, rn < n_intra);
+    if (tid < 32) {
+      if (r + 1 < total) {
+        const int rn = r + 1;
+        next_pairs(m, buf, rn < n_intra ? rn : rn - n_intra, rn < n_intra);
+      }
+    } else {
+      apply_round(m, buf, 32);
     }
-    update_Q(m, buf, 32);
     __syncthreads();
   }
 }
@@ -216,7 +298,7 @@ eig_block_jacobi_kernel(EigBatch batch) {
   double* T = esm + warp * (3 * EP * ELD + 4 * EB);  // per-warp: T, Qk, Ql, cs
   double* Qk = T + EP * ELD;
   double* Ql = Qk + EP * ELD;
-  __shared__ double red[kEigWarps];
+  __shared__ double red[kEigWarps], red2[kEigWarps];
 
   // ---- phase 0: scale factor, padded copies, V = I, norms ----
   for (int pi = 0; pi < batch.count; ++pi) {
@@ -272,30 +354,41 @@ eig_block_jacobi_kernel(EigBatch batch) {
           rr_pair(P.nb, round, item, bi, bj);
           double off = 0.0;
           const bool intra = (round == 0);
-          double* S = esm;
-          double* Qm = esm + EP * ELD;
-          VisitSmem vm{S, Qm, esm + 2 * EP * ELD, reinterpret_cast<int*>(esm + 2 * EP * ELD + 4 * EB)};
+          // shared-memory map of a visit (inside the phase-B tile regions, idle now):
+          //   Q fp64 [EP][ELD] | cs fp64 [2][EB][2] | S fp32 2 x [EP][ELDF] | csf fp32 [2][EB][2] | pq, pid int
+          double* Qm = esm;
+          double* csd = esm + EP * ELD;
+          float* Sf0 = reinterpret_cast<float*>(csd + 4 * EB);
+          float* Sf1 = Sf0 + EP * ELDF;
+          float* csf = Sf1 + EP * ELDF;
+          int* pqi = reinterpret_cast<int*>(csf + 4 * EB);
+          VisitSmem vm{{Sf0, Sf1}, Qm, csd, csf, pqi, pqi + 4 * EB};
+          double dsum = 0.0;
           for (int e = threadIdx.x; e < EP * EP; e += kEigThreads) {
             const int i = e / EP, j = e % EP;
             const double v = P.Ap[(int64_t)pair_index(bi, bj, i) * P.np + pair_index(bi, bj, j)];
-            S[i * ELD + j] = v;
             const bool cross = (i < EB) != (j < EB);
             if (cross || (intra && i != j)) off += v * v;
+            if (i == j) dsum += v;
           }
           off = rt::warp_sum(off);
-          if (lane == 0) red[warp] = off;
+          dsum = rt::warp_sum(dsum);
+          if (lane == 0) { red[warp] = off; red2[warp] = dsum; }
           __syncthreads();
-          off = 0.0;
-          for (int wq = 0; wq < kEigWarps; ++wq) off += red[wq];
+          off = 0.0; dsum = 0.0;
+          for (int wq = 0; wq < kEigWarps; ++wq) { off += red[wq]; dsum += red2[wq]; }
           const bool skip = (off <= 1e-30 * P.scal[0]);
           if (!skip) {
-            cta_visit(vm, intra);
+            const double mu = dsum / EP;       // the steering tile holds A - mu I (rotations do not see the shift)
             for (int e = threadIdx.x; e < EP * EP; e += kEigThreads) {
               const int i = e / EP, j = e % EP;
-              P.J[(int64_t)item * EP * EP + e] = Qm[i * ELD + j];
-              // the pair's own tile is final for this round: phase B skips k == l
-              P.Ap[(int64_t)pair_index(bi, bj, i) * P.np + pair_index(bi, bj, j)] = S[i * ELD + j];
+              const double v = P.Ap[(int64_t)pair_index(bi, bj, i) * P.np + pair_index(bi, bj, j)];
+              Sf0[i * ELDF + j] = (float)(i == j ? v - mu : v);
             }
+            __syncthreads();
+            cta_visit(vm, intra);
+            for (int e = threadIdx.x; e < EP * EP; e += kEigThreads)
+              P.J[(int64_t)item * EP * EP + e] = Qm[(e / EP) * ELD + (e % EP)];
           }
           if (threadIdx.x == 0) {
             P.skip[item] = skip ? 1 : 0;
@@ -321,7 +414,6 @@ eig_block_jacobi_kernel(EigBatch batch) {
           int k, l;
           if (isV) { k = (item - nA) / P.npairs; l = (item - nA) % P.npairs; }
           else { k = item / P.npairs; l = item % P.npairs; }
-          if (!isV && k == l) continue;
           const bool sk = isV ? true : (P.skip[k] != 0);
           const bool sl = P.skip[l] != 0;
           if (sk && sl) continue;
