@@ -344,6 +344,9 @@ def main():
         barrier()
         eval_qps = BATCH * len(ebs) / (e0.elapsed_time(e1) * 1e-3)
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the fused score kernel ----

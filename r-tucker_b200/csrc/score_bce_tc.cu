@@ -39,8 +39,8 @@ constexpr uint32_t OFF_G = 0, OFF_GT = OFF_G + G_BYTES, OFF_STAGE = OFF_GT + GT_
 constexpr uint32_t FULL_BYTES = 50 * CS_ROW;             // r2 <= 200 on this path (103,200 B); wider ranks fall back
 constexpr uint32_t OFF_MASK = (OFF_STAGE + 2 * STAGE_BYTES > 2 * FULL_BYTES) ? OFF_STAGE + 2 * STAGE_BYTES : 2 * FULL_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_MASK + TB * 2 * 8;   // 208,448
-constexpr int HB_LD = 129;                                // epilogue transpose buffer [128][129] floats in the stage area
-static_assert(128 * HB_LD * 4 <= 2 * STAGE_BYTES, "transpose buffer must fit in the stage area");
+constexpr int HB_LD = 132;                                // epilogue transpose buffer [128][132] floats (16-byte aligned rows) in the stage area
+static_assert(OFF_STAGE + 128 * HB_LD * 4 <= OFF_MASK, "transpose buffer must fit between the stage area start and the masks");
 constexpr uint32_t TM_D3 = 0, TM_Z = 256, TM_D2 = 256;
 
 struct TcArgs {
@@ -51,6 +51,11 @@ struct TcArgs {
   double* loss_partial; float* H_ws; float* dO;
   int n_tiles, r2p;
   long long* prof;   // optional [grid][12] cycle counters per phase (debug)
+  // packed operand images (pre-rounded to TF32, already in the shared-memory layout), see pack_*_kernel
+  const unsigned char* Opk1; const unsigned char* Qpk1;   // [tile | chunk][full_bytes]        K-major, all of K
+  const unsigned char* Opk2; const unsigned char* Qpk2;   // [tile | chunk][ncb][TBLK_BYTES]   transposed blocks
+  uint32_t full_bytes;
+  int packed, ncb;
 };
 
 // [rows0, rows0+128) x [col0, col0+32) of src (row-major, ld) -> K-major block, zero padded.
@@ -145,10 +150,58 @@ __device__ __forceinline__ void stage_cols_T(unsigned char* dst, const float* __
   }
 }
 
+constexpr uint32_t TBLK_BYTES = (TN / 4) * CS_T;    // one transposed 32-column block image (16,384 B)
+
+// ---- operand pre-packing (once per launch): global fp32 -> TF32-rounded shared-memory images ----
+// K-major full-K image of rows [128*blk, +128) of src[n_rows][r2]
+__global__ void __launch_bounds__(256)
+pack_rows_kernel(const float* __restrict__ src, int n_rows, int r2, unsigned char* __restrict__ dst, uint32_t full_bytes) {
+  const int row0 = blockIdx.x * TB;
+  const int nch = r2 >> 2, nchp = nch + (nch & 1);
+  unsigned char* img = dst + (size_t)blockIdx.x * full_bytes;
+  for (int e = threadIdx.x; e < TB * nchp; e += 256) {
+    const int row = e / nchp, ch = e - row * nchp;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + row < n_rows && ch < nch) {
+      const float4 f = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(row0 + row) * r2 + 4 * ch));
+      v = make_uint4(to_tf32(f.x), to_tf32(f.y), to_tf32(f.z), to_tf32(f.w));
+    }
+    *reinterpret_cast<uint4*>(img + (uint32_t)ch * CS_ROW + (uint32_t)(row >> 3) * RS + (uint32_t)(row & 7) * 16u) = v;
+  }
+}
+// transposed 32-column block images: dst[blk][cb][c][r] = src[128*blk + r][32*cb + c]
+__global__ void __launch_bounds__(256)
+pack_cols_kernel(const float* __restrict__ src, int n_rows, int r2, int ncb, unsigned char* __restrict__ dst) {
+  const int row0 = blockIdx.x * TN, cb = blockIdx.y;
+  unsigned char* img = dst + ((size_t)blockIdx.x * ncb + cb) * TBLK_BYTES;
+  for (int e = threadIdx.x; e < KB * (TN / 4); e += 256) {
+    const int c = e & 31, rch = e >> 5;
+    uint32_t t[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = row0 + 4 * rch + j, col = cb * KB + c;
+      t[j] = (r < n_rows && col < r2) ? to_tf32(__ldg(src + (int64_t)r * r2 + col)) : 0u;
+    }
+    *reinterpret_cast<uint4*>(img + (uint32_t)rch * CS_T + (uint32_t)c * 16u) = make_uint4(t[0], t[1], t[2], t[3]);
+  }
+}
+
+// ---- TMA bulk copy (global -> shared), completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               :: "r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_split(unsigned char* dst, const unsigned char* src, uint32_t bytes, uint64_t* bar) {
+  for (uint32_t o = 0; o < bytes; o += 32768u) bulk_g2s(dst + o, src + o, min(32768u, bytes - o), bar);
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 score_tc_kernel(TcArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_stage[2], bar_z, bar_d;
+  __shared__ uint64_t bar_stage[2], bar_z, bar_d, bar_ld, bar_full[2];
   __shared__ uint32_t tmem_slot;
   __shared__ double red[kThreads / 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -161,6 +214,7 @@ score_tc_kernel(TcArgs a) {
 
   if (tid == 0) {
     mbar_init(&bar_stage[0], 1); mbar_init(&bar_stage[1], 1); mbar_init(&bar_z, 1); mbar_init(&bar_d, 1);
+    mbar_init(&bar_ld, 1); mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
@@ -176,7 +230,7 @@ score_tc_kernel(TcArgs a) {
   const int ncb = r2p / KB + ((r2p % KB) ? 1 : 0);   // GEMM2/3 column blocks (last one may be 16 wide)
   const int n_chunks = (a.B + TB - 1) / TB;
   const uint32_t idesc1 = make_idesc_tf32(TB, TN, false, false);
-  uint32_t ph_stage[2] = {0u, 0u}, ph_z = 0u, ph_d = 0u;
+  uint32_t ph_stage[2] = {0u, 0u}, ph_z = 0u, ph_d = 0u, ph_ld = 0u, ph_full[2] = {0u, 0u};
   int used[2] = {0, 0};                          // number of un-waited commits per stage (0 or 1)
   double loss_acc = 0.0;
   bool first_tile = true;
@@ -190,7 +244,26 @@ score_tc_kernel(TcArgs a) {
       const int b0 = chunk * TB;
       const int b_valid = min(TB, a.B - b0);
       // ================= GEMM1: Z = Q O^T =================
-      if (full_k) {
+      if (a.packed) {
+        // both operands (all of K) arrive as two TMA bulk copies of ready-made images; one thread drives it
+        unsigned char* sQ = smem;
+        unsigned char* sO = smem + FULL_BYTES;
+        if (tid == 0) {
+          fence_async_smem();      // earlier generic-proxy accesses of this memory (G, G^T, hbuf) are ordered first
+          mbar_expect_tx(&bar_ld, 2u * a.full_bytes);
+          bulk_g2s_split(sQ, a.Qpk1 + (size_t)chunk * a.full_bytes, a.full_bytes, &bar_ld);
+          bulk_g2s_split(sO, a.Opk1 + (size_t)tile * a.full_bytes, a.full_bytes, &bar_ld);
+          mbar_wait(&bar_ld, ph_ld);
+          fence_after_sync();
+          const uint32_t aA = smem_u32(sQ), aB = smem_u32(sO);
+          const int ksteps = (r2 + 7) / 8;
+          for (int ks = 0; ks < ksteps; ++ks)
+            mma_tf32(tmem + TM_Z, make_desc(aA + ks * 2 * CS_ROW, CS_ROW, RS), make_desc(aB + ks * 2 * CS_ROW, CS_ROW, RS),
+                     idesc1, ks != 0);
+          mma_commit(&bar_z);
+        }
+        ph_ld ^= 1u;
+      } else if (full_k) {
         // whole K resident: one asynchronous staging wave, then all MMAs back to back
         unsigned char* sQ = smem;
         unsigned char* sO = smem + FULL_BYTES;
@@ -273,7 +346,6 @@ score_tc_kernel(TcArgs a) {
           uint32_t v[32];
           tmem_ld32(tmem + TM_Z + ((uint32_t)(quarter * 32) << 16) + (uint32_t)cbase, v);
           tmem_ld_wait();
-#pragma unroll
           // store bases: G^T[n][b] element (cc, rr) sits at gt_base + 16*cc; G[b][n] chunk at g_base + (cc/4)*CS_G
           unsigned char* gt_base = sGT + (uint32_t)(rr >> 2) * CS_GT + (uint32_t)(rr & 3) * 4u + (uint32_t)cbase * 16u;
           unsigned char* g_base = sG + (uint32_t)(cbase >> 2) * CS_G + (uint32_t)(rr >> 3) * RS + (uint32_t)(rr & 7) * 16u;
@@ -312,6 +384,51 @@ score_tc_kernel(TcArgs a) {
       __syncthreads();
       RT_TC_PROF(3);   // epilogue 1
       // ================= GEMM2 (H chunk) and GEMM3 (dO tile), column-blocked =================
+      if (a.packed) {
+        // one thread runs a 2-stage TMA ring over the transposed 32-column blocks of O^T and Q'^T
+        if (tid == 0) {
+          fence_after_sync();
+          auto fill = [&](int cb) {
+            const int s = cb & 1;
+            mbar_expect_tx(&bar_full[s], 2u * TBLK_BYTES);
+            bulk_g2s(sStage[s], a.Opk2 + ((size_t)tile * ncb + cb) * TBLK_BYTES, TBLK_BYTES, &bar_full[s]);
+            bulk_g2s(sStage[s] + HALF_BYTES, a.Qpk2 + ((size_t)chunk * ncb + cb) * TBLK_BYTES, TBLK_BYTES, &bar_full[s]);
+          };
+          fence_async_smem();
+          fill(0);
+          if (ncb > 1) fill(1);
+          const uint32_t aG = smem_u32(sG), aGT = smem_u32(sGT);
+          for (int cb = 0; cb < ncb; ++cb) {
+            const int s = cb & 1;
+            mbar_wait(&bar_full[s], ph_full[s]); ph_full[s] ^= 1u;
+            fence_after_sync();
+            const int cw = min(KB, r2p - cb * KB);
+            const uint32_t idn = make_idesc_tf32(128, cw, false, false);
+            const uint32_t aOT = smem_u32(sStage[s]), aQT = aOT + HALF_BYTES;
+            for (int ks = 0; ks < TN / 8; ++ks)
+              mma_tf32(tmem + TM_D2 + cb * KB, make_desc(aG + ks * 2 * CS_G, CS_G, RS),
+                       make_desc(aOT + ks * 2 * CS_T, CS_T, RS), idn, ks != 0);
+            for (int ks = 0; ks < TB / 8; ++ks)
+              mma_tf32(tmem + TM_D3 + cb * KB, make_desc(aGT + ks * 2 * CS_GT, CS_GT, RS),
+                       make_desc(aQT + ks * 2 * CS_T, CS_T, RS), idn, (chunk | ks) != 0);
+            mma_commit(&bar_stage[s]);
+            if (cb + 2 < ncb) {            // refill this stage once its MMAs have consumed it
+              mbar_wait(&bar_stage[s], ph_stage[s]); ph_stage[s] ^= 1u;
+              fill(cb + 2);
+            } else {
+              used[s] = 1;                  // drained below together with bar_d
+            }
+          }
+          mma_commit(&bar_d);
+        } else {
+          // keep the phase bookkeeping of the other threads in step with thread 0
+          for (int cb = 0; cb < ncb; ++cb) {
+            const int s = cb & 1;
+            ph_full[s] ^= 1u;
+            if (cb + 2 < ncb) ph_stage[s] ^= 1u; else used[s] = 1;
+          }
+        }
+      } else
       for (int cb = 0; cb < ncb; ++cb) {
         const int s = cb & 1;
         if (used[s]) { mbar_wait(&bar_stage[s], ph_stage[s]); ph_stage[s] ^= 1u; used[s] = 0; }
@@ -369,6 +486,29 @@ score_tc_kernel(TcArgs a) {
         const int cols = min(cw, r2 - c0);
         float* Hc = a.H_ws + ((int64_t)blockIdx.x * a.B + b0) * r2 + c0;
         // warp w owns rows w, w+8, ...; lanes run along the columns (coalesced); 4 rows in flight
+        if (vec_ok) {
+          const int c4n = cols >> 2;                 // float4 per row (r2 % 4 == 0 => cols % 4 == 0)
+          for (int rr0 = warp; rr0 < b_valid; rr0 += 4 * (kThreads / 32)) {
+            for (int c4 = lane; c4 < c4n; c4 += 32) {
+              float4 old[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int rr = rr0 + u * (kThreads / 32);
+                old[u] = (!first_tile && rr < b_valid) ? *reinterpret_cast<const float4*>(Hc + (int64_t)rr * r2 + 4 * c4)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int rr = rr0 + u * (kThreads / 32);
+                if (rr < b_valid) {
+                  const float4 hv = *reinterpret_cast<const float4*>(&hbuf[rr * HB_LD + 4 * c4]);
+                  *reinterpret_cast<float4*>(Hc + (int64_t)rr * r2 + 4 * c4) =
+                      make_float4(old[u].x + hv.x, old[u].y + hv.y, old[u].z + hv.z, old[u].w + hv.w);
+                }
+              }
+            }
+          }
+        } else
         for (int rr0 = warp; rr0 < b_valid; rr0 += 4 * (kThreads / 32)) {
           for (int c = lane; c < cols; c += 32) {
             float old[4];
@@ -412,6 +552,14 @@ score_tc_kernel(TcArgs a) {
       fence_before_sync();
       __syncthreads();
       const int cols = min(cw, r2 - c0);
+      if (vec_ok) {
+        const int c4n = cols >> 2;
+        for (int e = tid; e < n_valid * c4n; e += kThreads) {
+          const int rr = e / c4n, c4 = e - rr * c4n;
+          *reinterpret_cast<float4*>(a.dO + (int64_t)(n0 + rr) * r2 + c0 + 4 * c4) =
+              *reinterpret_cast<const float4*>(&hbuf[rr * HB_LD + 4 * c4]);
+        }
+      } else
       for (int e = tid; e < n_valid * cols; e += kThreads) {
         const int rr = e / cols, c = e - rr * cols;
         a.dO[(int64_t)(n0 + rr) * r2 + c0 + c] = hbuf[rr * HB_LD + c];
@@ -467,10 +615,32 @@ int tc_grid(int n_local) {
 
 }  // namespace
 
-extern "C" size_t rt_score_bce_tc_ws_bytes(int B, int n_local, int r2) {
-  const int grid = tc_grid(n_local);
-  return rt::align_up((size_t)grid * B * r2 * sizeof(float), 256) + (size_t)grid * sizeof(double);
+struct TcLayout {
+  int grid, n_tiles, n_chunks, ncb, packed;
+  uint32_t full_bytes;
+  size_t off_loss, off_Opk1, off_Qpk1, off_Opk2, off_Qpk2, total;
+};
+static TcLayout tc_layout(int B, int n_local, int r2) {
+  TcLayout L;
+  L.grid = tc_grid(n_local);
+  L.n_tiles = rt::cdiv(n_local, TN);
+  L.n_chunks = rt::cdiv(B, TB);
+  const int r2p = (r2 + 15) / 16 * 16;
+  L.ncb = r2p / KB + ((r2p % KB) ? 1 : 0);
+  L.packed = (r2 % 4 == 0 && r2 <= 200) ? 1 : 0;
+  const int nch = r2 >> 2, nchp = nch + (nch & 1);
+  L.full_bytes = (uint32_t)nchp * CS_ROW;
+  size_t o = rt::align_up((size_t)L.grid * B * r2 * sizeof(float), 256);
+  L.off_loss = o; o += rt::align_up((size_t)L.grid * sizeof(double), 256);
+  L.off_Opk1 = o; if (L.packed) o += rt::align_up((size_t)L.n_tiles * L.full_bytes, 256);
+  L.off_Qpk1 = o; if (L.packed) o += rt::align_up((size_t)L.n_chunks * L.full_bytes, 256);
+  L.off_Opk2 = o; if (L.packed) o += rt::align_up((size_t)L.n_tiles * L.ncb * TBLK_BYTES, 256);
+  L.off_Qpk2 = o; if (L.packed) o += rt::align_up((size_t)L.n_chunks * L.ncb * TBLK_BYTES, 256);
+  L.total = o;
+  return L;
 }
+
+extern "C" size_t rt_score_bce_tc_ws_bytes(int B, int n_local, int r2) { return tc_layout(B, n_local, r2).total; }
 
 extern "C" int rt_score_bce_tc(const float* q, const float* qp, const float* O, int B, int r2, int n_begin,
                                int n_local, int n_total, int b_total, const int32_t* tgt_off,
@@ -478,7 +648,9 @@ extern "C" int rt_score_bce_tc(const float* q, const float* qp, const float* O, 
                                float* dO, void* ws, void* stream) {
   RT_REQUIRE(r2 >= 1 && r2 <= 256, "rt_score_bce_tc: r2=%d out of range (1..256)", r2);
   cudaStream_t s = (cudaStream_t)stream;
-  const int grid = tc_grid(n_local);
+  const TcLayout L = tc_layout(B, n_local, r2);
+  const int grid = L.grid;
+  char* base = (char*)ws;
   TcArgs a{};
   a.q = q; a.qp = qp ? qp : q; a.O = O;
   a.B = B; a.r2 = r2; a.n_begin = n_begin; a.n_local = n_local;
@@ -487,11 +659,24 @@ extern "C" int rt_score_bce_tc(const float* q, const float* qp, const float* O, 
   a.t_pos = (1.0f - label_smoothing) + a.t_neg;
   a.inv_count = (float)(1.0 / ((double)b_total * (double)n_total));
   a.H_ws = (float*)ws;
-  a.loss_partial = (double*)((char*)ws + rt::align_up((size_t)grid * B * r2 * sizeof(float), 256));
+  a.loss_partial = (double*)(base + L.off_loss);
   a.dO = dO;
-  a.n_tiles = rt::cdiv(n_local, TN);
+  a.n_tiles = L.n_tiles;
   a.r2p = (r2 + 15) / 16 * 16;
   a.prof = g_tc_prof;
+  a.packed = L.packed; a.ncb = L.ncb; a.full_bytes = L.full_bytes;
+  if (L.packed && n_local > 0) {
+    a.Opk1 = (unsigned char*)(base + L.off_Opk1); a.Qpk1 = (unsigned char*)(base + L.off_Qpk1);
+    a.Opk2 = (unsigned char*)(base + L.off_Opk2); a.Qpk2 = (unsigned char*)(base + L.off_Qpk2);
+    pack_rows_kernel<<<L.n_tiles, 256, 0, s>>>(O, n_local, r2, (unsigned char*)a.Opk1, L.full_bytes);
+    RT_LAUNCH_CHECK();
+    pack_rows_kernel<<<L.n_chunks, 256, 0, s>>>(q, B, r2, (unsigned char*)a.Qpk1, L.full_bytes);
+    RT_LAUNCH_CHECK();
+    pack_cols_kernel<<<dim3(L.n_tiles, L.ncb), 256, 0, s>>>(O, n_local, r2, L.ncb, (unsigned char*)a.Opk2);
+    RT_LAUNCH_CHECK();
+    pack_cols_kernel<<<dim3(L.n_chunks, L.ncb), 256, 0, s>>>(a.qp, B, r2, L.ncb, (unsigned char*)a.Qpk2);
+    RT_LAUNCH_CHECK();
+  }
   RT_CHECK_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   score_tc_kernel<<<grid, kThreads, SMEM_BYTES, s>>>(a);
   RT_LAUNCH_CHECK();
