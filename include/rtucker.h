@@ -118,7 +118,9 @@ int rt_query_bwd(const float* core, const float* r_rows, const float* s_rows, co
  *   dO = G^T qp     [n_local, r2]      (qp = q for the raw partial; pass q.A to fold a right factor)
  * O holds global entity rows [n_begin, n_begin+n_local); tgt_idx holds GLOBAL entity ids.
  * loss_sum is a double[1] (un-normalised sum over the shard; divide by B_total*n_total).
- * variant: 0 = fp32 FFMA (parity path), 1 = tcgen05 TF32 tensor cores (looser tolerance).
+ * variant: 0 = fp32 FFMA (parity path), 1 = tcgen05 TF32 tensor cores (looser tolerance),
+ *          2 = warp-specialised tcgen05 kernel with power-of-two-scaled fp16 operands (same 11 significant
+ *              bits as TF32, stated tolerance 2e-3); qp must be NULL or q (dO = G^T q).
  */
 size_t rt_score_bce_ws_bytes(int B, int n_local, int r2, int variant);
 int rt_score_bce_fwd_bwd(const float* q, const float* qp, const float* O,
@@ -126,6 +128,13 @@ int rt_score_bce_fwd_bwd(const float* q, const float* qp, const float* O,
                          const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
                          double* loss_sum, float* H, float* dO,
                          int variant, void* ws, void* stream);
+/* Variant 2 called directly.  o_absmax_hint > 0 promises max |O| <= hint (1.0 for the orthonormal factors of a
+ * point on the manifold) and saves the pass that measures it; <= 0 measures it on the device. */
+int rt_score_bce_v3_supported(int r2);
+size_t rt_score_bce_v3_ws_bytes(int B, int n_local, int r2);
+int rt_score_bce_v3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
+                    int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
+                    float o_absmax_hint, double* loss_sum, float* H, float* dO, void* ws, void* stream);
 
 /* ---- (c) tall-skinny passes over the N x r factors ----------------------------------- */
 /* out[ra, rb] (fp64) = A[n, :ra]^T  B[n, :rb]   (deterministic two-stage reduction).
@@ -172,6 +181,9 @@ int rt_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int n, 
 size_t rt_small_ws_bytes(int r0, int r1, int r2, int B);
 int rt_small_prepare(const float* core, int r0, int r1, int r2, int sym,
                      void* small_ws, void* stream);
+/* Byte offset inside small_ws of the fp64 matrix A_mode [r_mode, r_mode] written by rt_small_prepare (so the
+ * caller can hand it to rt_apply as a right factor). */
+size_t rt_small_ainv_offset(int mode, int r0, int r1, int r2);
 /* C[m,n] = A[m,k] . (fp64 K from small_ws slot `which`: 0,1,2 = Ainv_0..2), fp32 in/out.  */
 int rt_rows_times_ainv(const float* A, int m, int mode, int r0, int r1, int r2,
                        float* C, void* small_ws, void* stream);
@@ -237,6 +249,11 @@ int rt_eigh(double* A, int n, double* w, double* V, void* ws, void* stream);
  * (a_mn/b_mn select MN-major operands given as [K][M] / [K][N]); used by tests/test_gpu_tc.py. */
 int rt_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn, int flags,
                    void* stream);
+/* Same with fp16 operands (kind::f16), the building block of variant 2; and a known-answer test of the
+ * shared->global bulk copies: out[0:n] = a (bulk store) then out += b (bulk fp32 add-reduction at the L2). */
+int rt_tc_selftest16(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn, int flags,
+                     void* stream);
+int rt_bulk_reduce_selftest(const float* a, const float* b, float* out, int n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "rt_gram_tc": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp]),
     "rt_small_ws_bytes": (sz, [i32, i32, i32, i32]),
     "rt_small_prepare": (i32, [vp, i32, i32, i32, i32, vp, vp]),
+    "rt_small_ainv_offset": (sz, [i32, i32, i32, i32]),
     "rt_rows_times_ainv": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "rt_small_grad": (i32, [vp] * 9 + [f64, vp, i32, i32, i32, i32, i32] + [vp] * 9),
     "rt_small_norm": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
@@ -56,6 +57,11 @@ PROTOTYPES = {
     "rt_eigh_ws_bytes": (sz, [i32]),
     "rt_eigh": (i32, [vp, i32, vp, vp, vp, vp]),
     "rt_tc_selftest": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "rt_tc_selftest16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "rt_bulk_reduce_selftest": (i32, [vp, vp, vp, i32, vp]),
+    "rt_score_bce_v3_supported": (i32, [i32]),
+    "rt_score_bce_v3_ws_bytes": (sz, [i32, i32, i32]),
+    "rt_score_bce_v3": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, f32, vp, vp, vp, vp, vp]),
 }
 
 

@@ -404,8 +404,16 @@ extern "C" int rt_score_bce_tc(const float* q, const float* qp, const float* O, 
                                const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
                                double* loss_sum, float* H, float* dO, void* ws, void* stream);
 
+// warp-specialised fp16 tcgen05 variant (score_bce_v3.cu)
+extern "C" int rt_score_bce_v3_supported(int r2);
+extern "C" size_t rt_score_bce_v3_ws_bytes(int B, int n_local, int r2);
+extern "C" int rt_score_bce_v3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
+                               int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
+                               float o_absmax_hint, double* loss_sum, float* H, float* dO, void* ws, void* stream);
+
 extern "C" size_t rt_score_bce_ws_bytes(int B, int n_local, int r2, int variant) {
   if (variant == 1) return rt_score_bce_tc_ws_bytes(B, n_local, r2);
+  if (variant == 2) return rt_score_bce_v3_ws_bytes(B, n_local, r2);
   Plan p = make_plan(n_local, r2, false);
   return rt::align_up((size_t)p.grid * B * r2 * sizeof(float), 256) + (size_t)p.grid * sizeof(double);
 }
@@ -421,6 +429,12 @@ extern "C" int rt_score_bce_fwd_bwd(const float* q, const float* qp, const float
   if (variant == 1)
     return rt_score_bce_tc(q, qp, O, B, r2, n_begin, n_local, n_total, b_total, tgt_off, tgt_idx,
                            label_smoothing, loss_sum, H, dO, ws, stream);
+  if (variant == 2) {
+    RT_REQUIRE(qp == nullptr || qp == q, "rt_score_bce_fwd_bwd: variant 2 computes dO = G^T q only (pass qp = NULL and "
+               "fold the right factor into the following rt_apply)");
+    return rt_score_bce_v3(q, O, B, r2, n_begin, n_local, n_total, b_total, tgt_off, tgt_idx, label_smoothing, 0.0f,
+                           loss_sum, H, dO, ws, stream);
+  }
   RT_REQUIRE(variant == 0, "rt_score_bce_fwd_bwd: unknown variant %d", variant);
   cudaStream_t s = (cudaStream_t)stream;
   Plan p = make_plan(n_local, r2, false);

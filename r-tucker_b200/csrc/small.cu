@@ -272,6 +272,11 @@ extern "C" int rt_small_prepare(const float* core, int r0, int r1, int r2, int s
   return finish(c, "rt_small_prepare");
 }
 
+extern "C" size_t rt_small_ainv_offset(int mode, int r0, int r1, int r2) {
+  if (mode < 0 || mode > 2) return (size_t)-1;
+  return make_layout(r0, r1, r2, 0).Ainv[mode];
+}
+
 extern "C" int rt_rows_times_ainv(const float* A, int m, int mode, int r0, int r1, int r2, float* C,
                                   void* small_ws, void* stream) {
   RT_REQUIRE(mode >= 0 && mode < 3 && m >= 0, "rt_rows_times_ainv: bad arguments");

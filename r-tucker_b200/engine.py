@@ -163,10 +163,19 @@ class StepEngine:
         dOp = self.spare[k_obj]
         bce_sum = torch.empty(1, dtype=f64, device=self.dev)
         H = torch.empty(B, r2, dtype=core.dtype, device=self.dev)
+        # variant 2 (warp-specialised fp16 tcgen05 kernel) returns dO = G^T q; the right factor A_O is folded into
+        # the projection apply below (dO_raw lands in the not-yet-used direction buffer)
+        fold_a = self.score_variant == 2 and getattr(ops, "HAS_SCORE_V3", False) and ops.score_v3_supported(r2)
+        dO_raw = self.dV_new[k_obj] if fold_a else None
         with self._stage("score_bce_fwd_bwd"):
-            ops.score_bce_fwd_bwd(q, qp, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
-                                  b_total=B, n_begin=self.n_begin, variant=self.score_variant,
-                                  out=(bce_sum, H, dOp))
+            if fold_a:
+                ops.score_bce_fwd_bwd(q, None, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
+                                      b_total=B, n_begin=self.n_begin, variant=2, out=(bce_sum, H, dO_raw),
+                                      o_absmax=1.0)     # factors of a point on the manifold are orthonormal
+            else:
+                ops.score_bce_fwd_bwd(q, qp, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
+                                      b_total=B, n_begin=self.n_begin, variant=min(self.score_variant, 1),
+                                      out=(bce_sum, H, dOp))
         self._allreduce(H, bce_sum)
         with self._stage("query_bwd"):
             d_core, ds_rows, dr_rows = ops.query_bwd(core, r_rows, s_rows, H)
@@ -183,9 +192,11 @@ class StepEngine:
         if not sym:
             dV_g[1] = ops.apply(self.spare[1], None, None, [(S, P_S)])
             ops.scatter_rows_add(dV_g[1], sub_idx, dsA, self.n_begin)
-            dV_g[2] = ops.apply(dOp, dOp, None, [(O, P_O)])
+            dV_g[2] = (ops.apply(dOp, None, None, [(dO_raw, small.ainv(2)), (O, P_O)]) if fold_a else
+                       ops.apply(dOp, dOp, None, [(O, P_O)]))
         else:
-            dV_g[1] = ops.apply(dOp, dOp, None, [(S, P_S)])
+            dV_g[1] = (ops.apply(dOp, None, None, [(dO_raw, small.ainv(2)), (S, P_S)]) if fold_a else
+                       ops.apply(dOp, dOp, None, [(S, P_S)]))
             ops.scatter_rows_add(dV_g[1], sub_idx, dsA, self.n_begin)
         # ---- norm of the Riemannian gradient ----
         grams = [ops.gram(v, v) for v in dV_g]

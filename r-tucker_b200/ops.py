@@ -5,7 +5,7 @@ import ctypes as C
 
 import torch
 
-from ._lib import check, lib, ptr, require_cuda, stream_ptr
+from ._lib import RTuckerError, check, lib, ptr, require_cuda, stream_ptr
 
 f32, f64, i32 = torch.float32, torch.float64, torch.int32
 
@@ -103,10 +103,36 @@ def query_bwd(core, r_rows, s_rows, H, ws=None):
 
 
 # ---------------------------------------------------------------- (b) fused score + BCE + backward
+HAS_SCORE_V3 = True   # this ops module implements variant 2 (the CPU stand-in of the tests does not)
+
+
+def score_v3_supported(r2):
+    return bool(lib().rt_score_bce_v3_supported(int(r2)))
+
 def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None, b_total=None,
-                      n_begin=0, variant=0, out=None, ws=None):
-    """Returns (loss_sum[1] f64 -- un-normalised, H [B,r2], dO [n_local,r2])."""
+                      n_begin=0, variant=0, out=None, ws=None, o_absmax=None):
+    """Returns (loss_sum[1] f64 -- un-normalised, H [B,r2], dO [n_local,r2]).
+    variant 2 (warp-specialised fp16 tcgen05 kernel) computes dO = G^T q: qp must be None; ``o_absmax`` is an
+    optional promise max|O| <= o_absmax (1.0 for orthonormal factors) that saves the measuring pass."""
     require_cuda(q, qp, O, tgt_off, tgt_idx)
+    if variant == 2:
+        if qp is not None and qp is not q:
+            raise RTuckerError("score_bce_fwd_bwd(variant=2) computes dO = G^T q: pass qp=None")
+        B, r2 = q.shape
+        n_local = O.shape[0]
+        n_total = n_local if n_total is None else n_total
+        b_total = B if b_total is None else b_total
+        dev = q.device
+        if out is None:
+            out = (torch.empty(1, dtype=f64, device=dev), torch.empty(B, r2, dtype=f32, device=dev),
+                   torch.empty(n_local, r2, dtype=f32, device=dev))
+        loss, H, dO = out
+        ws = ws if ws is not None else _ws(lib().rt_score_bce_v3_ws_bytes(B, n_local, r2), dev)
+        check(lib().rt_score_bce_v3(ptr(_c(q, f32)), ptr(_c(O, f32)), B, r2, n_begin, n_local, n_total, b_total,
+                                    ptr(_c(tgt_off, i32)), ptr(_c(tgt_idx, i32)), float(label_smoothing),
+                                    float(o_absmax or 0.0), ptr(loss), ptr(H), ptr(dO), ptr(ws), stream_ptr()),
+              "rt_score_bce_v3")
+        return loss, H, dO
     B, r2 = q.shape
     n_local = O.shape[0]
     n_total = n_local if n_total is None else n_total
@@ -194,6 +220,12 @@ class SmallStage:
     def prepare(self, core):
         check(lib().rt_small_prepare(ptr(_c(core, f32)), *self._r(), self.sym, ptr(self.ws), stream_ptr()),
               "rt_small_prepare")
+
+    def ainv(self, mode):
+        """fp64 view [r_mode, r_mode] of A_mode inside the workspace (valid after prepare())."""
+        r = self._r()[mode]
+        off = int(lib().rt_small_ainv_offset(mode, *self._r()))
+        return self.ws[off:off + 8 * r * r].view(f64).view(r, r)
 
     def rows_times_ainv(self, A, mode):
         out = torch.empty_like(A)
