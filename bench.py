@@ -191,7 +191,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="wn18rr", choices=list(WORKLOADS))
-    ap.add_argument("--variant", type=int, default=1, help="fused score kernel: 0 = fp32 FFMA (1e-5 parity), 1 = tcgen05 TF32 (2e-3)")
+    ap.add_argument("--variant", type=int, default=2,
+                    help="fused score kernel: 0 = fp32 FFMA (1e-5 parity), 1 = tcgen05 TF32 (2e-3), "
+                         "2 = warp-specialised tcgen05 with scaled fp16 operands (2e-3)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="reference steps timed for cpu_baseline (0 = skip)")
     ap.add_argument("--eval-batches", type=int, default=8)
     ap.add_argument("--no-graphs", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
@@ -360,7 +362,9 @@ def main():
     flops = 6.0 * BATCH * (n_end - n_begin) * r2
     score_ms = stage_ms.get("score_bce_fwd_bwd")
     achieved = flops / (score_ms * 1e-3) / 1e12 if score_ms else None
-    roofline = {"kernel": "score_kernel (fused 1-N score + BCE + backward, variant %d)" % args.variant,
+    roofline = {"kernel": "fused 1-N score + BCE + backward, variant %d (%s)" % (
+                    args.variant, {0: "score_kernel, fp32 FFMA", 1: "score_tc_kernel, tcgen05 TF32",
+                                   2: "score_v3_kernel, warp-specialised tcgen05 kind::f16 + its pack / reduce launches"}[args.variant]),
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf if achieved else None, "traffic": None, "peak_source": peak_src,
                 "algorithmic_flops_per_launch": flops, "ms_per_launch": score_ms}

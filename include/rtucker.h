@@ -135,6 +135,8 @@ size_t rt_score_bce_v3_ws_bytes(int B, int n_local, int r2);
 int rt_score_bce_v3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
                     int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
                     float o_absmax_hint, double* loss_sum, float* H, float* dO, void* ws, void* stream);
+/* Debug: per-CTA, per-role (producer, MMA issuer, epilogue, flush) cycle counters [grid][4][10] int64; NULL = off. */
+int rt_score_v3_set_profile(long long* dev_buf);
 
 /* ---- (c) tall-skinny passes over the N x r factors ----------------------------------- */
 /* out[ra, rb] (fp64) = A[n, :ra]^T  B[n, :rb]   (deterministic two-stage reduction).

@@ -37,9 +37,9 @@ constexpr int TB = 128;                 // queries per chunk
 constexpr int kEpiWarps = 8, kFlushWarps = 4;
 constexpr int kWarps = 2 + kEpiWarps + kFlushWarps;
 constexpr int kThreads = kWarps * 32;   // 448
-constexpr int kFlushBar = 1;            // named barrier of the flush warps
+constexpr int kMaxCachedChunks = 4;     // query chunks whose target lists an epilogue thread keeps in registers
 constexpr uint32_t QCS = TB * 16;       // byte stride between 8-column blocks of a Q chunk image (and of G)
-constexpr uint32_t STG_BYTES = 8192;    // one flush staging piece: [4 column quads][128 rows][16 B]
+constexpr uint32_t STG_BYTES = 4096;    // per flush warp: one [32 rows][32 cols] fp32 block of the dO tile (transposition)
 constexpr float G_SCALE = 1024.0f;      // G is stored as (p - t) * 2^10 in fp16; 1/(B N) is applied at the flush
 constexpr int R2P_MAX = 208;
 
@@ -54,32 +54,50 @@ struct V3Args {
   double* loss_partial;       // [grid]
   float* dO;                  // [n_local][r2]
   uint32_t OB, QB;
-  int wait_groups;            // bulk groups that may stay in flight before a region of H_ws is touched again
+  long long* prof;            // optional [grid][4 roles][10] cycle counters (debug, rt_score_v3_set_profile)
+};
+
+template <bool ENABLED>
+struct ProfT {
+  long long t0, acc[10];
+  bool on;
+  __device__ __forceinline__ void start(bool o) {
+    on = o;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) acc[i] = 0;
+    if (on) t0 = clock64();
+  }
+  __device__ __forceinline__ void lap(int i) {
+    if (on) { const long long t = clock64(); acc[i] += t - t0; t0 = t; }
+  }
+  __device__ __forceinline__ void dump(long long* dst) {
+    if (on) {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) dst[i] = acc[i];
+    }
+  }
+};
+template <>
+struct ProfT<false> {
+  static constexpr bool on = false;
+  __device__ __forceinline__ void start(bool) {}
+  __device__ __forceinline__ void lap(int) {}
+  __device__ __forceinline__ void dump(long long*) {}
 };
 
 __device__ __forceinline__ void bulk_g2s_split(unsigned char* dst, const unsigned char* src, uint32_t bytes, uint64_t* bar) {
   for (uint32_t o = 0; o < bytes; o += 32768u) bulk_g2s(dst + o, src + o, min(32768u, bytes - o), bar);
 }
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-  asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(count) : "memory");
-}
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" :: "l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
-__device__ __forceinline__ void bulk_wait_at_most(int n) {   // complete all but (at most) the n most recent groups
-  if (n >= 48) bulk_wait<48>();
-  else if (n >= 24) bulk_wait<24>();
-  else if (n >= 12) bulk_wait<12>();
-  else if (n >= 6) bulk_wait<6>();
-  else if (n >= 3) bulk_wait<3>();
-  else if (n >= 1) bulk_wait<1>();
-  else bulk_wait<0>();
-}
-
 template <int TN>
 struct Cfg {
   static constexpr int CH = TN / 2;                       // entity columns per epilogue warp
@@ -91,10 +109,11 @@ struct Cfg {
   static_assert(Z_COL + TN <= 512, "TMEM budget");
 };
 
-template <int TN>
+template <int TN, bool PROF>
 __global__ void __launch_bounds__(kThreads, 1)
 score_v3_kernel(V3Args a) {
   using C = Cfg<TN>;
+  using Prof = ProfT<PROF>;
   constexpr int CH = C::CH;
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t ofull[2], oempty[2], qfull[2], qempty[2], zfull, zfree, gfull, gfree, d2full, d2free, d3full, d3free;
@@ -125,9 +144,12 @@ score_v3_kernel(V3Args a) {
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
+      Prof pf; pf.start(a.prof != nullptr);
       auto load_O = [&](int lt, int tile) {
         const int s = lt & 1;
+        pf.lap(2);
         if (lt >= 2) mbar_wait(&oempty[s], ((lt >> 1) + 1) & 1);
+        pf.lap(0);
         mbar_expect_tx(&ofull[s], a.OB);
         bulk_g2s_split(sO[s], a.Opk + (size_t)tile * a.OB, a.OB, &ofull[s]);
       };
@@ -136,12 +158,16 @@ score_v3_kernel(V3Args a) {
       for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++lt) {
         for (int c = 0; c < n_chunks; ++c, ++pair) {
           const int s = pair & 1;
+          pf.lap(2);
           if (pair >= 2) mbar_wait(&qempty[s], ((pair >> 1) + 1) & 1);
+          pf.lap(1);
           mbar_expect_tx(&qfull[s], a.QB);
           bulk_g2s_split(sQ[s], a.Qpk + (size_t)c * a.QB, a.QB, &qfull[s]);
           if (c == 0 && tile + tile_step < a.n_tiles) load_O(lt + 1, tile + tile_step);
         }
       }
+      pf.lap(2);
+      if (PROF && a.prof) pf.dump(a.prof + ((size_t)blockIdx.x * 4 + 0) * 10);
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
@@ -151,44 +177,56 @@ score_v3_kernel(V3Args a) {
       const uint32_t idesc3 = make_idesc_f16(128, r2p, true, true);
       const uint32_t aG = smem_u32(sG);
       const int ks1 = r2p / 16;
+      Prof pf; pf.start(a.prof != nullptr);
       // GEMM2 + GEMM3 of pair pp = (tile lt, chunk c) whose operands sit in stages (os, qs)
       auto g23 = [&](int pp, int lt, int c, int os, int qs) {
         mbar_wait(&gfull, pp & 1);
-        if (pp > 0) mbar_wait(&d2free, (pp - 1) & 1);
+        pf.lap(4);
+        if (c == 0 && lt > 0) mbar_wait(&d3free, (lt - 1) & 1);
+        pf.lap(7);
         fence_after_sync();
         const uint32_t aO = smem_u32(sO[os]), aQ = smem_u32(sQ[qs]);
+        for (int ks = 0; ks < TB / 16; ++ks)        // D3[n, c] += sum_b G[b, n] Q[b, c]
+          mma_f16(tmem + C::D3_COL, make_desc(aG + ks * 256, 128, QCS), make_desc(aQ + ks * 256, 128, QCS),
+                  idesc3, (c | ks) != 0);
+        mma_commit(&qempty[qs]);                     // the Q stage is free as early as possible: its refill is the
+        if (c == n_chunks - 1) mma_commit(&d3full);  // longest latency of the pipeline
+        pf.lap(8);
+        if (pp > 0) { mbar_wait(&d2free, (pp - 1) & 1); fence_after_sync(); }
+        pf.lap(5);
         for (int ks = 0; ks < TN / 16; ++ks)        // D2[b, c] = sum_n G[b, n] O[n, c]
           mma_f16(tmem + C::D2_COL, make_desc(aG + ks * 2 * QCS, QCS, 128), make_desc(aO + ks * 256, 128, C::OCS),
                   idesc2, ks != 0);
         mma_commit(&d2full);
-        if (c == 0 && lt > 0) { mbar_wait(&d3free, (lt - 1) & 1); fence_after_sync(); }
-        for (int ks = 0; ks < TB / 16; ++ks)        // D3[n, c] += sum_b G[b, n] Q[b, c]
-          mma_f16(tmem + C::D3_COL, make_desc(aG + ks * 256, 128, QCS), make_desc(aQ + ks * 256, 128, QCS),
-                  idesc3, (c | ks) != 0);
         mma_commit(&gfree);
-        mma_commit(&qempty[qs]);
-        if (c == n_chunks - 1) { mma_commit(&d3full); mma_commit(&oempty[os]); }
+        if (c == n_chunks - 1) mma_commit(&oempty[os]);
+        pf.lap(6);
       };
       int pair = 0, lt = 0;
       int pv = 0, pv_lt = 0, pv_c = 0, pv_os = 0, pv_qs = 0;
       for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++lt) {
         const int os = lt & 1;
         mbar_wait(&ofull[os], (lt >> 1) & 1);
+        pf.lap(0);
         for (int c = 0; c < n_chunks; ++c, ++pair) {
           const int qs = pair & 1;
           mbar_wait(&qfull[qs], (pair >> 1) & 1);
+          pf.lap(1);
           if (pair > 0) mbar_wait(&zfree, (pair - 1) & 1);
+          pf.lap(2);
           fence_after_sync();
           const uint32_t aO = smem_u32(sO[os]), aQ = smem_u32(sQ[qs]);
           for (int ks = 0; ks < ks1; ++ks)          // Z[b, n] = sum_k Q[b, k] O[n, k]
             mma_f16(tmem + C::Z_COL, make_desc(aQ + ks * 2 * QCS, QCS, 128), make_desc(aO + ks * 2 * C::OCS, C::OCS, 128),
                     idesc1, ks != 0);
           mma_commit(&zfull);
+          pf.lap(3);
           if (pv) g23(pair - 1, pv_lt, pv_c, pv_os, pv_qs);
           pv = 1; pv_lt = lt; pv_c = c; pv_os = os; pv_qs = qs;
         }
       }
       if (pv) g23(pair - 1, pv_lt, pv_c, pv_os, pv_qs);
+      if (PROF && a.prof) pf.dump(a.prof + ((size_t)blockIdx.x * 4 + 1) * 10);
     }
   } else if (warp < 2 + kEpiWarps) {
     // ============================== epilogue: Z -> loss, G ==============================
@@ -197,29 +235,59 @@ score_v3_kernel(V3Args a) {
     const int r = quarter * 32 + lane;            // query row within the chunk
     const float sQ = a.scal[0], sO = a.scal[1];
     const float zs = 1.0f / (sQ * sO);            // Z = raw * zs (exact: powers of two)
-    const float nk = -zs * 1.4426950408889634f;   // e^{-z} = 2^{raw * nk}
-    const float raw_lim = 15.0f * sQ * sO;        // |z| < 15: no saturation anywhere (p != 1, p (1-p) > 1e-12)
+    const float nk = -zs * 1.4426950408889634f;   // e^{-z} = 2^x, x = raw * nk
+    // fast path window: y = x - 8 with |y| < 32, i.e. z in (-27.7, 16.6): p != 1 and p (1 - p) > 1e-12, so none of
+    // the reference's saturation branches is taken (the generic path below handles everything else)
     const float gneg = -a.t_neg * G_SCALE;
+    // target lists of this thread's rows (one per chunk) stay in registers: bounds + the first two entries
+    int ce0[kMaxCachedChunks], ce1[kMaxCachedChunks], ci0[kMaxCachedChunks], ci1[kMaxCachedChunks];
+#pragma unroll
+    for (int c = 0; c < kMaxCachedChunks; ++c) {
+      const int b = c * TB + r;
+      ce0[c] = ce1[c] = 0; ci0[c] = ci1[c] = -1;
+      if (c < n_chunks && b < a.B) {
+        ce0[c] = a.off[b]; ce1[c] = a.off[b + 1];
+        if (ce1[c] > ce0[c]) ci0[c] = a.idx[ce0[c]];
+        if (ce1[c] > ce0[c] + 1) ci1[c] = a.idx[ce0[c] + 1];
+      }
+    }
     double loss_acc = 0.0;
     int pair = 0;
+    Prof pf; pf.start(PROF && a.prof != nullptr && warp == 2 && lane == 0);
     for (int tile = first_tile; tile < a.n_tiles; tile += tile_step) {
       const int n0 = tile * TN;
       const int cols_valid = min(CH, a.n_local - n0 - half * CH);     // may be <= 0 on the last tile
       const int nbase = a.n_begin + n0 + half * CH;
+#pragma unroll 1
       for (int c = 0; c < n_chunks; ++c, ++pair) {
         const int b = c * TB + r;
         const bool row_ok = b < a.B;
         // sparse positives of (row, this warp's columns) as a bit mask
         unsigned long long mask = 0ull;
-        if (row_ok) {
-          const int e1 = a.off[b + 1];
-          for (int e = a.off[b]; e < e1; ++e) {
-            const int o = a.idx[e] - nbase;
-            if (o >= 0 && o < CH) mask |= 1ull << o;
+        {
+          int e0 = 0, e1 = 0, i0 = -1, i1 = -1;
+          if (c < kMaxCachedChunks) {
+#pragma unroll
+            for (int cc = 0; cc < kMaxCachedChunks; ++cc)
+              if (cc == c) { e0 = ce0[cc]; e1 = ce1[cc]; i0 = ci0[cc]; i1 = ci1[cc]; }
+          } else if (row_ok) {
+            e0 = a.off[b]; e1 = a.off[b + 1];
+            if (e1 > e0) i0 = a.idx[e0];
+            if (e1 > e0 + 1) i1 = a.idx[e0 + 1];
+          }
+          unsigned o = (unsigned)(i0 - nbase);
+          if (i0 >= 0 && o < (unsigned)CH) mask |= 1ull << o;
+          o = (unsigned)(i1 - nbase);
+          if (i1 >= 0 && o < (unsigned)CH) mask |= 1ull << o;
+          for (int e = e0 + 2; e < e1; ++e) {        // long lists (hub queries): the rest comes from memory
+            o = (unsigned)(a.idx[e] - nbase);
+            if (o < (unsigned)CH) mask |= 1ull << o;
           }
         }
+        pf.lap(0);
         mbar_wait(&zfull, pair & 1);
         __syncwarp();
+        pf.lap(1);
         fence_after_sync();
         uint32_t v[CH];
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(C::Z_COL + half * CH);
@@ -229,26 +297,32 @@ score_v3_kernel(V3Args a) {
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&zfree);        // Z may be overwritten by GEMM1 of the next pair
+        pf.lap(2);
         uint32_t gp[CH / 2];
-        float A1 = 0.0f, A2 = 0.0f, Ls = 0.0f;
+        float A1 = 0.0f, Y2 = 0.0f, Ls = 0.0f;
+        int nfast = 0;
 #pragma unroll
         for (int g = 0; g < CH / 16; ++g) {
-          float zm = 0.0f;
+          float y[16];
+          float ym = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) zm = fmaxf(zm, fabsf(__uint_as_float(v[16 * g + j])));
+          for (int j = 0; j < 16; ++j) {
+            y[j] = fmaf(__uint_as_float(v[16 * g + j]), nk, -8.0f);
+            ym = fmaxf(ym, fabsf(y[j]));
+          }
           const unsigned mg = (unsigned)(mask >> (16 * g)) & 0xffffu;
-          const bool fast = row_ok && mg == 0u && zm < raw_lim && (16 * g + 16 <= cols_valid);
+          const bool fast = row_ok && mg == 0u && ym < 32.0f && (16 * g + 16 <= cols_valid);
           if (fast) {
+            nfast += 16;
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               float gq[2];
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
-                const float raw = __uint_as_float(v[16 * g + j + u]);
-                const float s = 1.0f + ex2_approx(raw * nk);
+                const float s = fmaf(ex2_approx(y[j + u]), 256.0f, 1.0f);    // 1 + e^{-z}
                 const float p = rcp_approx(s);
                 A1 += lg2_approx(s);
-                A2 += raw;
+                Y2 += y[j + u];
                 gq[u] = fmaf(p, G_SCALE, gneg);
               }
               gp[(16 * g + j) >> 1] = pack_half2(gq[0], gq[1]);
@@ -281,9 +355,14 @@ score_v3_kernel(V3Args a) {
             }
           }
         }
-        // loss of the fast groups: sum ln(1 + e^{-z}) + (1 - t_neg) z
-        loss_acc += (double)(0.6931471805599453f * A1 + (1.0f - a.t_neg) * zs * A2 + Ls);
+        // loss of the fast groups: sum ln(1 + e^{-z}) + (1 - t_neg) z  with  z = -(y + 8) ln 2
+        {
+          const float zsum = -0.6931471805599453f * (Y2 + 8.0f * (float)nfast);
+          loss_acc += (double)(0.6931471805599453f * A1 + (1.0f - a.t_neg) * zsum + Ls);
+        }
+        pf.lap(3);
         if (pair > 0) mbar_wait(&gfree, (pair - 1) & 1);     // GEMM2/3 of the previous pair no longer read G
+        pf.lap(4);
         {
           unsigned char* gdst = sG + (uint32_t)((half * CH) >> 3) * QCS + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
 #pragma unroll
@@ -293,89 +372,107 @@ score_v3_kernel(V3Args a) {
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&gfull);
+        pf.lap(5);
       }
     }
+    if (PROF && pf.on) pf.dump(a.prof + ((size_t)blockIdx.x * 4 + 2) * 10);
     const double wsum = rt::warp_sum(loss_acc);
     if (lane == 0) red[warp - 2] = wsum;
   } else {
-    // ============================== flush: D2 -> H partial, D3 -> dO ==============================
+    // ============================== flush: D2 -> H partial of this CTA, D3 -> dO ==============================
+    // H partial: thread (row r) owns H_ws[cta][chunk][quad][r][0..3]; the CTA's first tile stores, later tiles add
+    // with red.global.add.v4.f32 (same thread, same address, program order: deterministic).  TMEM loads of the
+    // next 32 columns are in flight while the current ones are written.
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const bool leader = (warp == 2 + kEpiWarps) && lane == 0;
     const float sQ = a.scal[0], sO = a.scal[1];
     const float hscale = a.inv_count / (G_SCALE * sO);
     const float dscale = a.inv_count / (G_SCALE * sQ);
     const uint32_t lanebits = (uint32_t)(quarter * 32) << 16;
-    const int ng = r2p / 16;
+    const int np = (r2p + 31) / 32;               // 32-column pieces (the last one may hold 16 columns)
     const bool vec_ok = (a.r2 % 4 == 0);
-    int pair = 0, lt = 0, stg = 0;
+    unsigned char* stg = sStg + (warp - (2 + kEpiWarps)) * STG_BYTES;
+    int pair = 0, lt = 0;
+    Prof pf; pf.start(PROF && a.prof != nullptr && warp == 2 + kEpiWarps && lane == 0);
+    auto ld_piece = [&](uint32_t col0, int h, uint32_t (&v)[32]) {
+      if (32 * h + 32 <= r2p) tmem_ld32(tmem + lanebits + col0 + 32u * h, v);
+      else tmem_ld16(tmem + lanebits + col0 + 32u * h, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+    };
     for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++lt) {
       const int n0 = tile * TN;
       const int n_valid = min(TN, a.n_local - n0);
       for (int c = 0; c < n_chunks; ++c, ++pair) {
-        float* Hdst = a.H_ws + ((size_t)blockIdx.x * n_chunks + c) * ((size_t)r2p * TB);
+        float* hrow = a.H_ws + ((size_t)blockIdx.x * n_chunks + c) * ((size_t)r2p * TB) + (size_t)r * 4;
+        auto st_piece = [&](int h, const uint32_t (&v)[32]) {
+          const int nq = (32 * h + 32 <= r2p) ? 8 : 4;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < nq) {
+              float* dst = hrow + (size_t)(8 * h + j) * (TB * 4);
+              const float x0 = __uint_as_float(v[4 * j]) * hscale, x1 = __uint_as_float(v[4 * j + 1]) * hscale;
+              const float x2 = __uint_as_float(v[4 * j + 2]) * hscale, x3 = __uint_as_float(v[4 * j + 3]) * hscale;
+              if (lt == 0) *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+              else red_add_v4(dst, x0, x1, x2, x3);
+            }
+          }
+        };
         mbar_wait(&d2full, pair & 1);
         __syncwarp();
+        pf.lap(0);
         fence_after_sync();
-        for (int h = 0; h < ng; ++h) {
-          uint32_t v[16];
-          tmem_ld16(tmem + lanebits + (uint32_t)(C::D2_COL + 16 * h), v);
+        uint32_t va[32], vb[32];
+        ld_piece(C::D2_COL, 0, va);
+        for (int h = 0; h < np; h += 2) {
           tmem_ld_wait();
-          if (h == ng - 1) {
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d2free);       // D2 may be overwritten by GEMM2 of the next pair
-          }
-          if (leader) {
-            bulk_wait_read<1>();                       // the piece staged two rounds ago has left shared memory
-            bulk_wait_at_most(a.wait_groups);          // earlier traffic to this region of H_ws is complete
-          }
-          named_bar_sync(kFlushBar, kFlushWarps * 32);
-          unsigned char* sp = sStg + stg * STG_BYTES;
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(sp + j * 2048 + r * 16) =
-                make_float4(__uint_as_float(v[4 * j]) * hscale, __uint_as_float(v[4 * j + 1]) * hscale,
-                            __uint_as_float(v[4 * j + 2]) * hscale, __uint_as_float(v[4 * j + 3]) * hscale);
-          fence_async_smem();
-          named_bar_sync(kFlushBar, kFlushWarps * 32);
-          if (leader) {
-            float* dst = Hdst + (size_t)h * (STG_BYTES / 4);
-            if (lt == 0) bulk_s2g(dst, sp, STG_BYTES); else bulk_s2g_add_f32(dst, sp, STG_BYTES);
-            bulk_commit();
-          }
-          stg ^= 1;
+          if (h + 1 < np) ld_piece(C::D2_COL, h + 1, vb);
+          else { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(&d2free); }
+          st_piece(h, va);
+          if (h + 1 >= np) break;
+          tmem_ld_wait();
+          if (h + 2 < np) ld_piece(C::D2_COL, h + 2, va);
+          else { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(&d2free); }
+          st_piece(h + 1, vb);
         }
+        pf.lap(1);
       }
-      // ---- tile epilogue: D3 -> dO rows of this tile ----
+      // ---- tile epilogue: D3 -> dO rows of this tile (transposed through shared memory: 128-byte row segments) ----
       mbar_wait(&d3full, lt & 1);
       __syncwarp();
+      pf.lap(7);
       fence_after_sync();
-      for (int g = 0; g < ng; ++g) {
-        uint32_t v[16];
-        tmem_ld16(tmem + lanebits + (uint32_t)(C::D3_COL + 16 * g), v);
+      for (int h = 0; h < np; ++h) {
+        uint32_t v[32];
+        ld_piece(C::D3_COL, h, v);
         tmem_ld_wait();
-        if (r < n_valid) {
-          float* drow = a.dO + (size_t)(n0 + r) * a.r2 + 16 * g;
-          if (vec_ok) {
+        if (h == np - 1) { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(&d3free); }
+        const int ncol = min(32, r2p - 32 * h);
+        if (vec_ok) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (16 * g + 4 * j < a.r2)
-                *reinterpret_cast<float4*>(drow + 4 * j) =
-                    make_float4(__uint_as_float(v[4 * j]) * dscale, __uint_as_float(v[4 * j + 1]) * dscale,
-                                __uint_as_float(v[4 * j + 2]) * dscale, __uint_as_float(v[4 * j + 3]) * dscale);
-          } else {
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(__uint_as_float(v[4 * j]) * dscale, __uint_as_float(v[4 * j + 1]) * dscale,
+                            __uint_as_float(v[4 * j + 2]) * dscale, __uint_as_float(v[4 * j + 3]) * dscale);
+          __syncwarp();
+          const int ch = lane & 7;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (16 * g + j < a.r2) drow[j] = __uint_as_float(v[j]) * dscale;
+          for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + (lane >> 3);
+            const int col = 32 * h + 4 * ch;
+            const float4 x = *reinterpret_cast<const float4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
+            if (quarter * 32 + row < n_valid && 4 * ch < ncol && col < a.r2)
+              *reinterpret_cast<float4*>(a.dO + (size_t)(n0 + quarter * 32 + row) * a.r2 + col) = x;
           }
+          __syncwarp();
+        } else if (r < n_valid) {
+          float* drow = a.dO + (size_t)(n0 + r) * a.r2 + 32 * h;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncol && 32 * h + j < a.r2) drow[j] = __uint_as_float(v[j]) * dscale;
         }
       }
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&d3free);
+      pf.lap(8);
     }
-    if (leader) bulk_wait<0>();
+    if (PROF && pf.on) pf.dump(a.prof + ((size_t)blockIdx.x * 4 + 3) * 10);
   }
   fence_before_sync();
   __syncthreads();
@@ -404,10 +501,68 @@ __device__ __forceinline__ float scale_for(float amax) {
   e = max(-100, min(100, e));
   return ldexpf(1.0f, e);
 }
-__global__ void scales_kernel(const unsigned* __restrict__ absbits, float o_hint, float* __restrict__ scal) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    scal[0] = scale_for(__uint_as_float(absbits[0]));
-    scal[1] = scale_for(o_hint > 0.0f ? o_hint : __uint_as_float(absbits[1]));
+// Scale of q from its absolute maximum (every CTA measures it redundantly: q is a few hundred KB and L2 resident,
+// so no second launch or atomic is needed), scale of O from the hint or from absbits[0] (absmax_kernel), then the
+// fp16 images of the query chunks (CTA i packs the image elements i, i + gridDim, ...).
+__global__ void __launch_bounds__(512)
+prep_q_kernel(const float* __restrict__ q, int B, int r2, int ncb, int n_chunks, const unsigned* __restrict__ absbits,
+              float o_hint, float* __restrict__ scal, unsigned char* __restrict__ Qpk, uint32_t QB) {
+  __shared__ float wmax[16];
+  __shared__ float s_scale;
+  float m = 0.0f;
+  const size_t n = (size_t)B * r2;
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+    const size_t n4 = n >> 2;
+#pragma unroll 8
+    for (size_t i = threadIdx.x; i < n4; i += 512) {
+      const float4 v = __ldg(q4 + i);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+  } else {
+#pragma unroll 8
+    for (size_t i = threadIdx.x; i < n; i += 512) m = fmaxf(m, fabsf(__ldg(q + i)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = 0.0f;
+    for (int w = 0; w < 16; ++w) mm = fmaxf(mm, wmax[w]);
+    s_scale = scale_for(mm);
+    if (blockIdx.x == 0) {
+      scal[0] = s_scale;
+      scal[1] = scale_for(o_hint > 0.0f ? o_hint : __uint_as_float(absbits[0]));
+    }
+  }
+  __syncthreads();
+  const float sc = s_scale;
+  const bool vec_ok = (r2 % 4 == 0);
+  const int per = TB * ncb;
+  for (int e = blockIdx.x * 512 + threadIdx.x; e < n_chunks * per; e += gridDim.x * 512) {
+    const int chunk = e / per, w = e - chunk * per;
+    const int row = w / ncb, cb = w - row * ncb;
+    const int b = chunk * TB + row;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.0f;
+    if (b < B) {
+      const float* p = q + (size_t)b * r2 + 8 * cb;
+      if (vec_ok && 8 * cb + 8 <= r2) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(p)), y = __ldg(reinterpret_cast<const float4*>(p + 4));
+        f[0] = x.x; f[1] = x.y; f[2] = x.z; f[3] = x.w; f[4] = y.x; f[5] = y.y; f[6] = y.z; f[7] = y.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (8 * cb + j < r2) f[j] = __ldg(p + j);
+      }
+    }
+    uint4 o;
+    o.x = pack_half2(f[0] * sc, f[1] * sc); o.y = pack_half2(f[2] * sc, f[3] * sc);
+    o.z = pack_half2(f[4] * sc, f[5] * sc); o.w = pack_half2(f[6] * sc, f[7] * sc);
+    *reinterpret_cast<uint4*>(Qpk + (size_t)chunk * QB + (uint32_t)cb * QCS + (uint32_t)(row >> 3) * 128u +
+                              (uint32_t)(row & 7) * 16u) = o;
   }
 }
 
@@ -444,36 +599,50 @@ pack16_kernel(const float* __restrict__ src, int n_rows, int r2, int rows_per, i
   }
 }
 
-// H[b][c] = sum over the CTAs' partial slices (fixed order: deterministic); one thread per (b, column quad)
-__global__ void reduce_H_v3_kernel(const float* __restrict__ H_ws, int nparts, int n_chunks, int r2p, int B, int r2,
-                                   float* __restrict__ H) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// H[b][c] = sum over the CTAs' partial slices, loss = sum of the CTAs' partial sums; both in a fixed order
+// (deterministic).  Block = 32 positions (b, column quad) x 8 slices of the part index; block 0 also sums the loss.
+__global__ void __launch_bounds__(256)
+reduce_H_v3_kernel(const float* __restrict__ H_ws, int nparts, int n_chunks, int r2p, int B, int r2,
+                   float* __restrict__ H, const double* __restrict__ loss_partial, double* __restrict__ loss_out) {
+  __shared__ float4 part[8][32];
+  const int px = threadIdx.x & 31, ks = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + px;
   const int nq = r2p / 4;
-  if (i >= n_chunks * nq * TB) return;
+  const bool in = i < n_chunks * nq * TB;
   const int bl = i % TB, q = (i / TB) % nq, c = i / (TB * nq);
-  const int b = c * TB + bl;
-  if (b >= B) return;
   const size_t slice = (size_t)r2p * TB;
-  const float* p = H_ws + (size_t)c * slice + ((size_t)q * TB + bl) * 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 8
-  for (int k = 0; k < nparts; ++k) {
-    const float4 v = *reinterpret_cast<const float4*>(p + (size_t)k * n_chunks * slice);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  if (in) {
+    const float* p = H_ws + (size_t)c * slice + ((size_t)q * TB + bl) * 4;
+#pragma unroll 4
+    for (int k = ks; k < nparts; k += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(p + (size_t)k * n_chunks * slice);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
   }
-  float* o = H + (size_t)b * r2 + 4 * q;
-  if (4 * q + 0 < r2) o[0] = s.x;
-  if (4 * q + 1 < r2) o[1] = s.y;
-  if (4 * q + 2 < r2) o[2] = s.z;
-  if (4 * q + 3 < r2) o[3] = s.w;
-}
-__global__ void reduce_loss_v3_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int i = 0; i < n; ++i) s += partial[i];
-    out[0] = s;
+  part[ks][px] = s;
+  __syncthreads();
+  if (ks == 0 && in) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { const float4 v = part[k][px]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    const int b = c * TB + bl;
+    if (b < B) {
+      float* o = H + (size_t)b * r2 + 4 * q;
+      if (4 * q + 0 < r2) o[0] = s.x;
+      if (4 * q + 1 < r2) o[1] = s.y;
+      if (4 * q + 2 < r2) o[2] = s.z;
+      if (4 * q + 3 < r2) o[3] = s.w;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    double t = 0.0;
+    for (int k = threadIdx.x; k < nparts; k += 32) t += loss_partial[k];
+    t = rt::warp_sum(t);            // xor-butterfly: the same association on every lane and every run
+    if (threadIdx.x == 0) loss_out[0] = t;
   }
 }
+
+long long* g_v3_prof = nullptr;
 
 struct V3Layout {
   int TN, r2p, ncb, n_tiles, n_chunks, grid;
@@ -492,7 +661,7 @@ V3Layout v3_layout(int B, int n_local, int r2) {
   L.OB = (uint32_t)L.ncb * L.TN * 16u;
   L.QB = (uint32_t)L.ncb * QCS;
   // G3 reads 16 n-blocks of G whatever TN is: keep 32 KB addressable behind sG
-  const uint32_t tail = (uint32_t)(L.TN / 8) * QCS + 2 * STG_BYTES;
+  const uint32_t tail = (uint32_t)(L.TN / 8) * QCS + kFlushWarps * STG_BYTES;
   L.smem = 2 * L.OB + 2 * L.QB + (tail < 16 * QCS ? 16 * QCS : tail);
   size_t o = rt::align_up((size_t)L.grid * L.n_chunks * L.r2p * TB * sizeof(float), 256);
   L.off_loss = o; o += rt::align_up((size_t)L.grid * sizeof(double), 256);
@@ -538,33 +707,33 @@ extern "C" int rt_score_bce_v3(const float* q, const float* O, int B, int r2, in
   a.loss_partial = (double*)(base + L.off_loss);
   a.dO = dO;
   a.OB = L.OB; a.QB = L.QB;
-  a.wait_groups = L.n_chunks * (L.r2p / 16) - 1;
+  a.prof = g_v3_prof;
 
-  RT_CHECK_CUDA(cudaMemsetAsync(absbits, 0, 2 * sizeof(unsigned), s));
-  absmax_kernel<<<32, 256, 0, s>>>(q, (size_t)B * r2, absbits);
-  RT_LAUNCH_CHECK();
   if (!(o_absmax_hint > 0.0f)) {
-    absmax_kernel<<<4 * rt::sm_count(), 256, 0, s>>>(O, (size_t)n_local * r2, absbits + 1);
+    RT_CHECK_CUDA(cudaMemsetAsync(absbits, 0, sizeof(unsigned), s));
+    absmax_kernel<<<4 * rt::sm_count(), 256, 0, s>>>(O, (size_t)n_local * r2, absbits);
     RT_LAUNCH_CHECK();
   }
-  scales_kernel<<<1, 32, 0, s>>>(absbits, o_absmax_hint, (float*)a.scal);
-  RT_LAUNCH_CHECK();
-  pack16_kernel<<<L.n_chunks, 256, 0, s>>>(q, B, r2, TB, L.ncb, a.scal, 0, (unsigned char*)a.Qpk, L.QB);
+  prep_q_kernel<<<8 * L.n_chunks, 512, 0, s>>>(q, B, r2, L.ncb, L.n_chunks, absbits, o_absmax_hint, (float*)a.scal,
+                                   (unsigned char*)a.Qpk, L.QB);
   RT_LAUNCH_CHECK();
   pack16_kernel<<<L.n_tiles, 256, 0, s>>>(O, n_local, r2, L.TN, L.ncb, a.scal, 1, (unsigned char*)a.Opk, L.OB);
   RT_LAUNCH_CHECK();
-  if (L.TN == 96) {
-    RT_CHECK_CUDA(cudaFuncSetAttribute(score_v3_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    score_v3_kernel<96><<<L.grid, kThreads, L.smem, s>>>(a);
-  } else {
-    RT_CHECK_CUDA(cudaFuncSetAttribute(score_v3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-    score_v3_kernel<128><<<L.grid, kThreads, L.smem, s>>>(a);
-  }
+#define RT_V3_LAUNCH(TN_, PROF_)                                                                                   \
+  do {                                                                                                            \
+    RT_CHECK_CUDA(cudaFuncSetAttribute(score_v3_kernel<TN_, PROF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)L.smem));                                                             \
+    score_v3_kernel<TN_, PROF_><<<L.grid, kThreads, L.smem, s>>>(a);                                              \
+  } while (0)
+  if (L.TN == 96) { if (a.prof) RT_V3_LAUNCH(96, true); else RT_V3_LAUNCH(96, false); }
+  else            { if (a.prof) RT_V3_LAUNCH(128, true); else RT_V3_LAUNCH(128, false); }
+#undef RT_V3_LAUNCH
   RT_LAUNCH_CHECK();
   const int cnt = L.n_chunks * (L.r2p / 4) * TB;
-  reduce_H_v3_kernel<<<(cnt + 255) / 256, 256, 0, s>>>(a.H_ws, L.grid, L.n_chunks, L.r2p, B, r2, H);
-  RT_LAUNCH_CHECK();
-  reduce_loss_v3_kernel<<<1, 32, 0, s>>>(a.loss_partial, L.grid, loss_sum);
+  reduce_H_v3_kernel<<<(cnt + 31) / 32, 256, 0, s>>>(a.H_ws, L.grid, L.n_chunks, L.r2p, B, r2, H, a.loss_partial, loss_sum);
   RT_LAUNCH_CHECK();
   return 0;
 }
+
+// Debug: per-CTA, per-role cycle counters of score_v3_kernel ([grid][4][10] int64), NULL to disable.
+extern "C" int rt_score_v3_set_profile(long long* dev_buf) { g_v3_prof = dev_buf; return 0; }

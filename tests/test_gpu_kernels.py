@@ -305,6 +305,94 @@ def test_score_bce_tcgen05(cuda_device, B, N, r2, ls, scale):
 
 
 # ------------------------------------------------------------------------------------------------
+# Variant 2: warp-specialised tcgen05 kernel with power-of-two-scaled fp16 operands (11 significant bits like
+# TF32), fp32 accumulation in tensor memory.  Same stated bound as the TF32 kernel.  dO = G^T q (no qp).
+def test_tcgen05_fp16_building_blocks(cuda_device):
+    """K-major and MN-major views of one interleaved fp16 image feed kind::f16 MMAs exactly (small integers);
+    shared->global bulk store followed by a bulk fp32 add-reduction is exact."""
+    from rtucker_b200._lib import check, lib, ptr, stream_ptr
+    dev = cuda_device
+    g = torch.Generator().manual_seed(11)
+    for N, K in ((208, 128), (96, 208), (16, 16)):
+        for a_mn in (0, 1):
+            for b_mn in (0, 1):
+                A = torch.randint(-3, 4, (128, K), generator=g).float().to(dev)
+                B = torch.randint(-3, 4, (N, K), generator=g).float().to(dev)
+                Ain = A.t().contiguous() if a_mn else A
+                Bin = B.t().contiguous() if b_mn else B
+                D = torch.zeros(128, N, device=dev)
+                check(lib().rt_tc_selftest16(ptr(Ain), ptr(Bin), ptr(D), N, K, a_mn, b_mn, 0, stream_ptr()), "selftest16")
+                torch.cuda.synchronize()
+                assert torch.equal(D, A @ B.t()), (N, K, a_mn, b_mn)
+    a, b = torch.randn(2048, generator=g).to(dev), torch.randn(2048, generator=g).to(dev)
+    o = torch.zeros(2048, device=dev)
+    check(lib().rt_bulk_reduce_selftest(ptr(a), ptr(b), ptr(o), 2048, stream_ptr()), "bulk")
+    torch.cuda.synchronize()
+    assert torch.equal(o, a + b)
+
+
+@pytest.mark.parametrize("B,N,r2,ls,scale,hint", [
+    (128, 128, 32, 0.1, 1.0, None), (128, 1000, 200, 0.1, 1.0, None), (512, 4099, 200, 0.1, 2.0, None),
+    (100, 777, 20, 0.1, 1.0, None), (512, 14541, 20, 0.0, 3.0, None), (300, 2000, 100, 0.1, 1.0, None),
+    (1, 5, 3, 0.1, 1.0, None), (130, 97, 7, 0.1, 1.0, None), (512, 3001, 208, 0.1, 1.0, 8.0), (600, 500, 176, 0.1, 1.0, None),
+])
+def test_score_bce_v3(cuda_device, B, N, r2, ls, scale, hint):
+    import analytic as A
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(B + N + r2 + 2)
+    q = scale * torch.randn(B, r2, generator=g) / r2 ** 0.5
+    O = torch.randn(N, r2, generator=g)
+    if hint is not None:
+        O = O.clamp(-hint, hint)
+    off, idx = make_csr(B, N, g, max_per_row=min(6, N), dense_row=min(1, B - 1))
+    z = (q.double() @ O.double().T).float()
+    t = A.dense_targets(B, N, off.long(), idx, ls, torch.float32)
+    _, loss_el, gsum = A.bce_sigmoid_terms(z, t)
+    loss_ref = loss_el.double().sum()
+    G = gsum.double() / (B * N)
+    H_ref, dO_ref = G @ O.double(), G.T @ q.double()
+    args = (q.to(dev), None, O.to(dev), off.to(dev), idx.to(dev), ls)
+    loss, H, dO = ops.score_bce_fwd_bwd(*args, variant=2, o_absmax=hint)
+    torch.cuda.synchronize()
+    assert abs(float(loss.cpu()) - float(loss_ref)) / abs(float(loss_ref)) < 1e-4
+    assert relerr(H, H_ref) < TC_REL, relerr(H, H_ref)
+    assert relerr(dO, dO_ref) < TC_REL, relerr(dO, dO_ref)
+    loss2, H2, dO2 = ops.score_bce_fwd_bwd(*args, variant=2, o_absmax=hint)
+    assert torch.equal(H, H2) and torch.equal(dO, dO2) and torch.equal(loss, loss2)      # deterministic
+    # the generic entry point dispatches to the same kernel and rejects a right factor it cannot fold
+    loss3, H3, dO3 = ops.score_bce_fwd_bwd(*args, variant=2)
+    assert torch.equal(H, H3) or hint is not None
+
+
+def test_score_bce_v3_saturation_and_sharding(cuda_device):
+    """Huge logits take the reference's saturation branches (log clamp -100, vanishing gradient); an entity shard
+    with global target ids gives the shard's partial sums."""
+    import analytic as A
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    B, N, r2, ls = 200, 1500, 24, 0.1
+    q = 40.0 * torch.randn(B, r2, generator=g)
+    O = torch.randn(N, r2, generator=g)
+    off, idx = make_csr(B, N, g, max_per_row=4, dense_row=0)
+    z = (q.double() @ O.double().T).float()
+    t = A.dense_targets(B, N, off.long(), idx, ls, torch.float32)
+    _, loss_el, gsum = A.bce_sigmoid_terms(z, t)
+    G = gsum.double() / (B * N)
+    lo, hi = 400, 1100
+    loss_ref = loss_el[:, lo:hi].double().sum()
+    H_ref, dO_ref = G[:, lo:hi] @ O[lo:hi].double(), G[:, lo:hi].T @ q.double()
+    loss, H, dO = ops.score_bce_fwd_bwd(q.to(dev), None, O[lo:hi].contiguous().to(dev), off.to(dev), idx.to(dev), ls,
+                                        n_total=N, b_total=B, n_begin=lo, variant=2)
+    torch.cuda.synchronize()
+    # logits of +-1000: a 1e-3 relative perturbation of z flips saturation decisions, so only the loss is compared tightly
+    assert abs(float(loss.cpu()) - float(loss_ref)) / abs(float(loss_ref)) < 5e-3
+    assert relerr(H, H_ref) < 5e-2 and relerr(dO, dO_ref) < 5e-2
+    assert torch.isfinite(H).all() and torch.isfinite(dO).all()
+
+
+# ------------------------------------------------------------------------------------------------
 # tcgen05 (3xTF32) variants of the tall-skinny passes: fp32-level accuracy required
 @pytest.mark.parametrize("n,ra,rb", [(4097, 200, 200), (40943, 200, 200), (5000, 20, 20), (3000, 10, 40), (2048, 256, 64), (70001, 130, 200)])
 def test_gram_tcgen05(cuda_device, n, ra, rb):
