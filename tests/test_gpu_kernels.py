@@ -373,7 +373,7 @@ def test_score_bce_v3_saturation_and_sharding(cuda_device):
     dev = cuda_device
     g = torch.Generator().manual_seed(5)
     B, N, r2, ls = 200, 1500, 24, 0.1
-    q = 40.0 * torch.randn(B, r2, generator=g)
+    q = 6.0 * torch.randn(B, r2, generator=g)           # logits ~ N(0, 29^2): most elements saturate one way or the other
     O = torch.randn(N, r2, generator=g)
     off, idx = make_csr(B, N, g, max_per_row=4, dense_row=0)
     z = (q.double() @ O.double().T).float()
@@ -386,9 +386,11 @@ def test_score_bce_v3_saturation_and_sharding(cuda_device):
     loss, H, dO = ops.score_bce_fwd_bwd(q.to(dev), None, O[lo:hi].contiguous().to(dev), off.to(dev), idx.to(dev), ls,
                                         n_total=N, b_total=B, n_begin=lo, variant=2)
     torch.cuda.synchronize()
-    # logits of +-1000: a 1e-3 relative perturbation of z flips saturation decisions, so only the loss is compared tightly
-    assert abs(float(loss.cpu()) - float(loss_ref)) / abs(float(loss_ref)) < 5e-3
-    assert relerr(H, H_ref) < 5e-2 and relerr(dO, dO_ref) < 5e-2
+    # the 11-bit operands perturb z by ~1e-3 |z|, which flips the saturation decision (p == 1 at z > 16.6) of the few
+    # elements that sit on the threshold: bounds are those of that effect, not of the arithmetic
+    e_loss = abs(float(loss.cpu()) - float(loss_ref)) / abs(float(loss_ref))
+    assert e_loss < 5e-3, e_loss
+    assert relerr(H, H_ref) < 5e-2 and relerr(dO, dO_ref) < 5e-2, (relerr(H, H_ref), relerr(dO, dO_ref))
     assert torch.isfinite(H).all() and torch.isfinite(dO).all()
 
 
