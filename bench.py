@@ -176,6 +176,15 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ncu_traffic(workload, variant):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    --set full capture of the same workload (profiles/ncu_traffic.json); None if never captured."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(path):
+        return json.load(open(path)).get("%s:variant%d" % (workload, variant))
+    return None
+
+
 def config_dict(w, args, note):
     return {"workload": f"{args.workload}: synthetic graph of that shape, N={w['N']} entities, M={w['M']} relations, "
                         f"rank={w['rank']}, batch {BATCH}, {'SF-Tucker rgd' if w['sym'] else 'Tucker rsgd'} "
@@ -346,6 +355,39 @@ def main():
         barrier()
         eval_qps = BATCH * len(ebs) / (e0.elapsed_time(e1) * 1e-3)
 
+    # ---- the fused score kernel on its own, launched back to back on the step's inputs (CUDA events on the
+    #      launching stream; its working set -- O, packed images, dO, per-CTA H partials -- exceeds the L2) ----
+    score_timing = None
+    if rank == 0 or world > 1:
+        from rtucker_b200 import ops as _ops
+        fd, od, xd = dev_batches[0]
+        O_fac = model.E.weight.data if w["sym"] else model.O.weight.data
+        B_, r2_ = BATCH, w["rank"][2]
+        qq = torch.randn(B_, r2_, device=dev) * 4.0 * (N / r2_) ** 0.5      # logits ~ N(0, 4^2) on orthonormal rows
+        outs = (torch.empty(1, dtype=torch.float64, device=dev), torch.empty(B_, r2_, device=dev),
+                torch.empty_like(O_fac))
+        v = args.variant
+        if v == 2 and not _ops.score_v3_supported(r2_):
+            v = 1
+        ws_s = torch.empty(int(lib().rt_score_bce_ws_bytes(B_, O_fac.shape[0], r2_, v)) + 16, dtype=torch.uint8, device=dev)
+        def run_score(phases=7):
+            _ops.score_bce_fwd_bwd(qq, None if v == 2 else qq, O_fac, od, xd, LABEL_SMOOTHING, n_total=N, b_total=B_,
+                                   n_begin=n_begin, variant=v, out=outs, ws=ws_s, o_absmax=1.0 if v == 2 else None,
+                                   phases=phases)
+        reps = max(10, args.steps)
+        def timed(phases):
+            for _ in range(3):
+                run_score(phases)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                run_score(phases)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        run_score(7)
+        score_timing = {"op_ms": timed(7), "kernel_ms": timed(2) if v == 2 else None, "launches_timed": reps}
+
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -361,13 +403,19 @@ def main():
     r2 = w["rank"][2]
     flops = 6.0 * BATCH * (n_end - n_begin) * r2
     score_ms = stage_ms.get("score_bce_fwd_bwd")
+    if score_timing is not None:
+        score_ms = score_timing["kernel_ms"] if score_timing.get("kernel_ms") else score_timing["op_ms"]
     achieved = flops / (score_ms * 1e-3) / 1e12 if score_ms else None
     roofline = {"kernel": "fused 1-N score + BCE + backward, variant %d (%s)" % (
                     args.variant, {0: "score_kernel, fp32 FFMA", 1: "score_tc_kernel, tcgen05 TF32",
                                    2: "score_v3_kernel, warp-specialised tcgen05 kind::f16 + its pack / reduce launches"}[args.variant]),
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf if achieved else None, "traffic": None, "peak_source": peak_src,
-                "algorithmic_flops_per_launch": flops, "ms_per_launch": score_ms}
+                "frac": achieved / peak_tf if achieved else None, "traffic": ncu_traffic(args.workload, args.variant),
+                "peak_source": peak_src, "algorithmic_flops_per_launch": flops, "ms_per_launch": score_ms,
+                "timing": score_timing,
+                "timing_note": "ms_per_launch = the fused kernel alone (kernel_ms: %d back-to-back launches between CUDA "
+                               "events); op_ms adds its operand packing and H-reduction launches; in-step stage time "
+                               "is stage_ms.score_bce_fwd_bwd" % (score_timing["launches_timed"] if score_timing else 0)}
 
     cpu = None
     if args.cpu_steps > 0 and world == 1:

@@ -135,6 +135,13 @@ size_t rt_score_bce_v3_ws_bytes(int B, int n_local, int r2);
 int rt_score_bce_v3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
                     int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
                     float o_absmax_hint, double* loss_sum, float* H, float* dO, void* ws, void* stream);
+/* Same call restricted to some of its phases (bit 0: operand scaling + packing, bit 1: the fused kernel,
+ * bit 2: H / loss reduction); a single phase needs a workspace prepared by the earlier ones on the same inputs.
+ * bench.py times the fused kernel alone this way. */
+int rt_score_bce_v3_phases(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
+                           int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
+                           float o_absmax_hint, double* loss_sum, float* H, float* dO, void* ws, void* stream,
+                           int phases);
 /* Debug: per-CTA, per-role (producer, MMA issuer, epilogue, flush) cycle counters [grid][4][10] int64; NULL = off. */
 int rt_score_v3_set_profile(long long* dev_buf);
 

@@ -679,9 +679,25 @@ extern "C" int rt_score_bce_v3_supported(int r2) { return r2 >= 1 && r2 <= R2P_M
 
 extern "C" size_t rt_score_bce_v3_ws_bytes(int B, int n_local, int r2) { return v3_layout(B, n_local, r2).total; }
 
+// phases: bit 0 = operand scaling + packing, bit 1 = the fused kernel, bit 2 = H / loss reduction.  Running a
+// single phase needs a workspace already prepared by the earlier phases on the same inputs (bench.py times the
+// fused kernel alone this way).
+extern "C" int rt_score_bce_v3_phases(const float* q, const float* O, int B, int r2, int n_begin, int n_local,
+                                      int n_total, int b_total, const int32_t* tgt_off, const int32_t* tgt_idx,
+                                      float label_smoothing, float o_absmax_hint, double* loss_sum, float* H, float* dO,
+                                      void* ws, void* stream, int phases);
+
 extern "C" int rt_score_bce_v3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
                                int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
                                float o_absmax_hint, double* loss_sum, float* H, float* dO, void* ws, void* stream) {
+  return rt_score_bce_v3_phases(q, O, B, r2, n_begin, n_local, n_total, b_total, tgt_off, tgt_idx, label_smoothing,
+                                o_absmax_hint, loss_sum, H, dO, ws, stream, 7);
+}
+
+extern "C" int rt_score_bce_v3_phases(const float* q, const float* O, int B, int r2, int n_begin, int n_local,
+                                      int n_total, int b_total, const int32_t* tgt_off, const int32_t* tgt_idx,
+                                      float label_smoothing, float o_absmax_hint, double* loss_sum, float* H, float* dO,
+                                      void* ws, void* stream, int phases) {
   RT_REQUIRE(rt_score_bce_v3_supported(r2), "rt_score_bce_v3: r2=%d out of range (1..%d)", r2, R2P_MAX);
   RT_REQUIRE(B >= 1 && n_local >= 0, "rt_score_bce_v3: bad sizes B=%d n_local=%d", B, n_local);
   cudaStream_t s = (cudaStream_t)stream;
@@ -709,6 +725,7 @@ extern "C" int rt_score_bce_v3(const float* q, const float* O, int B, int r2, in
   a.OB = L.OB; a.QB = L.QB;
   a.prof = g_v3_prof;
 
+  if (phases & 1) {
   if (!(o_absmax_hint > 0.0f)) {
     RT_CHECK_CUDA(cudaMemsetAsync(absbits, 0, sizeof(unsigned), s));
     absmax_kernel<<<4 * rt::sm_count(), 256, 0, s>>>(O, (size_t)n_local * r2, absbits);
@@ -719,6 +736,8 @@ extern "C" int rt_score_bce_v3(const float* q, const float* O, int B, int r2, in
   RT_LAUNCH_CHECK();
   pack16_kernel<<<L.n_tiles, 256, 0, s>>>(O, n_local, r2, L.TN, L.ncb, a.scal, 1, (unsigned char*)a.Opk, L.OB);
   RT_LAUNCH_CHECK();
+  }
+  if (phases & 2) {
 #define RT_V3_LAUNCH(TN_, PROF_)                                                                                   \
   do {                                                                                                            \
     RT_CHECK_CUDA(cudaFuncSetAttribute(score_v3_kernel<TN_, PROF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -729,9 +748,12 @@ extern "C" int rt_score_bce_v3(const float* q, const float* O, int B, int r2, in
   else            { if (a.prof) RT_V3_LAUNCH(128, true); else RT_V3_LAUNCH(128, false); }
 #undef RT_V3_LAUNCH
   RT_LAUNCH_CHECK();
+  }
+  if (phases & 4) {
   const int cnt = L.n_chunks * (L.r2p / 4) * TB;
   reduce_H_v3_kernel<<<(cnt + 31) / 32, 256, 0, s>>>(a.H_ws, L.grid, L.n_chunks, L.r2p, B, r2, H, a.loss_partial, loss_sum);
   RT_LAUNCH_CHECK();
+  }
   return 0;
 }
 

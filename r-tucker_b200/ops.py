@@ -2,6 +2,7 @@
 and the current CUDA stream only; all arithmetic happens in librtucker_b200.so.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -110,10 +111,11 @@ def score_v3_supported(r2):
     return bool(lib().rt_score_bce_v3_supported(int(r2)))
 
 def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None, b_total=None,
-                      n_begin=0, variant=0, out=None, ws=None, o_absmax=None):
+                      n_begin=0, variant=0, out=None, ws=None, o_absmax=None, phases=7):
     """Returns (loss_sum[1] f64 -- un-normalised, H [B,r2], dO [n_local,r2]).
     variant 2 (warp-specialised fp16 tcgen05 kernel) computes dO = G^T q: qp must be None; ``o_absmax`` is an
-    optional promise max|O| <= o_absmax (1.0 for orthonormal factors) that saves the measuring pass."""
+    optional promise max|O| <= o_absmax (1.0 for orthonormal factors) that saves the measuring pass;
+    ``phases`` (variant 2 only) selects packing (1), fused kernel (2), reduction (4) for timing."""
     require_cuda(q, qp, O, tgt_off, tgt_idx)
     if variant == 2:
         if qp is not None and qp is not q:
@@ -128,10 +130,10 @@ def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None,
                    torch.empty(n_local, r2, dtype=f32, device=dev))
         loss, H, dO = out
         ws = ws if ws is not None else _ws(lib().rt_score_bce_v3_ws_bytes(B, n_local, r2), dev)
-        check(lib().rt_score_bce_v3(ptr(_c(q, f32)), ptr(_c(O, f32)), B, r2, n_begin, n_local, n_total, b_total,
-                                    ptr(_c(tgt_off, i32)), ptr(_c(tgt_idx, i32)), float(label_smoothing),
-                                    float(o_absmax or 0.0), ptr(loss), ptr(H), ptr(dO), ptr(ws), stream_ptr()),
-              "rt_score_bce_v3")
+        check(lib().rt_score_bce_v3_phases(ptr(_c(q, f32)), ptr(_c(O, f32)), B, r2, n_begin, n_local, n_total,
+                                           b_total, ptr(_c(tgt_off, i32)), ptr(_c(tgt_idx, i32)),
+                                           float(label_smoothing), float(o_absmax or 0.0), ptr(loss), ptr(H),
+                                           ptr(dO), ptr(ws), stream_ptr(), int(phases)), "rt_score_bce_v3")
         return loss, H, dO
     B, r2 = q.shape
     n_local = O.shape[0]
@@ -153,7 +155,8 @@ def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None,
 
 
 # ---------------------------------------------------------------- (c) tall-skinny
-USE_TENSOR_CORES = False   # opt-in: tall-skinny passes on tcgen05 (3xTF32, ~3e-6 accuracy) instead of fp32 FFMA (~3e-7)
+# tall-skinny passes on tcgen05 (3xTF32, ~3e-6 accuracy) instead of fp32 FFMA (~3e-7): RT_TALLSKINNY_TC=1 opts in
+USE_TENSOR_CORES = os.environ.get("RT_TALLSKINNY_TC", "0") == "1"
 
 
 def gram(A, B, out=None, ws=None, precise=False, tc=None):
