@@ -263,6 +263,9 @@ int rt_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a
 int rt_tc_selftest16(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn, int flags,
                      void* stream);
 int rt_bulk_reduce_selftest(const float* a, const float* b, float* out, int n, void* stream);
+/* Debug: issue `reps` back-to-back kind::f16 MMAs (M = 128, N, K = 16) on shared-memory operands in the K-major
+ * (0) or MN-major (1) view; out_dev[0] = cycles to issue, out_dev[1] = cycles until all have completed. */
+int rt_mma_probe(int N, int ksteps, int a_mn, int b_mn, int reps, long long* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "rt_tc_selftest": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "rt_tc_selftest16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "rt_bulk_reduce_selftest": (i32, [vp, vp, vp, i32, vp]),
+    "rt_mma_probe": (i32, [i32, i32, i32, i32, i32, vp, vp]),
     "rt_score_bce_v3_supported": (i32, [i32]),
     "rt_score_bce_v3_ws_bytes": (sz, [i32, i32, i32]),
     "rt_score_v3_set_profile": (i32, [vp]),

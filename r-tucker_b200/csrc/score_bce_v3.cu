@@ -18,8 +18,11 @@
 //   warps 2-9  epilogue: Z -> registers (Z is released at once), sigmoid / BCE / gradient in fp32 with the
 //              reference's saturation semantics, G -> shared memory as fp16 in the interleaved core-matrix
 //              format that is simultaneously a K-major operand (GEMM2) and an MN-major operand (GEMM3)
-//   warps 10-13 flush: D2 -> per-CTA H partial (bulk store for the CTA's first tile, bulk fp32 add-reduction at
-//              the L2 afterwards: cp.reduce.async.bulk), D3 -> dO rows once per tile
+//   warps 10-13 flush: D2 -> per-CTA H partial straight from registers (st.global on the first visit of a chunk,
+//              red.global.add.v4.f32 afterwards; a staging + cp.reduce.async.bulk variant measured slower),
+//              D3 -> dO rows once per tile (32-byte stores)
+//   Query chunks are visited in boustrophedon order over the tiles, so the chunk at a tile boundary repeats: its Q
+//   image stays in shared memory and its H accumulator stays in TMEM (one flush and one reload less per tile).
 // Operands are fp16 scaled by powers of two (exact) chosen from the arrays' absolute maxima: 11 significant
 // bits like TF32 at twice the tensor rate and half the shared-memory footprint.  Stated tolerance: 2e-3 (same as
 // the TF32 kernel of score_bce_tc.cu); the fp32-FFMA kernel of score_bce.cu is the 1e-5 path.
@@ -39,7 +42,6 @@ constexpr int kWarps = 2 + kEpiWarps + kFlushWarps;
 constexpr int kThreads = kWarps * 32;   // 448
 constexpr int kMaxCachedChunks = 4;     // query chunks whose target lists an epilogue thread keeps in registers
 constexpr uint32_t QCS = TB * 16;       // byte stride between 8-column blocks of a Q chunk image (and of G)
-constexpr uint32_t STG_BYTES = 4096;    // per flush warp: one [32 rows][32 cols] fp32 block of the dO tile (transposition)
 constexpr float G_SCALE = 1024.0f;      // G is stored as (p - t) * 2^10 in fp16; 1/(B N) is applied at the flush
 constexpr int R2P_MAX = 208;
 
@@ -94,6 +96,10 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 __device__ __forceinline__ void red_add_v4(float* p, float x, float y, float z, float w) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" :: "l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
+__device__ __forceinline__ void st_v8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+               :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -123,7 +129,6 @@ score_v3_kernel(V3Args a) {
   unsigned char* sO[2] = {smem, smem + a.OB};
   unsigned char* sQ[2] = {smem + 2 * a.OB, smem + 2 * a.OB + a.QB};
   unsigned char* sG = smem + 2 * a.OB + 2 * a.QB;
-  unsigned char* sStg = sG + C::GB;
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(&ofull[s], 1); mbar_init(&oempty[s], 1); mbar_init(&qfull[s], 1); mbar_init(&qempty[s], 1); }
@@ -154,16 +159,20 @@ score_v3_kernel(V3Args a) {
         bulk_g2s_split(sO[s], a.Opk + (size_t)tile * a.OB, a.OB, &ofull[s]);
       };
       if (first_tile < a.n_tiles) load_O(0, first_tile);
-      int pair = 0, lt = 0;
+      int lt = 0, rho = -1;
       for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++lt) {
-        for (int c = 0; c < n_chunks; ++c, ++pair) {
-          const int s = pair & 1;
-          pf.lap(2);
-          if (pair >= 2) mbar_wait(&qempty[s], ((pair >> 1) + 1) & 1);
-          pf.lap(1);
-          mbar_expect_tx(&qfull[s], a.QB);
-          bulk_g2s_split(sQ[s], a.Qpk + (size_t)c * a.QB, a.QB, &qfull[s]);
-          if (c == 0 && tile + tile_step < a.n_tiles) load_O(lt + 1, tile + tile_step);
+        for (int i = 0; i < n_chunks; ++i) {
+          const int c = (lt & 1) ? n_chunks - 1 - i : i;     // boustrophedon: the chunk at a tile boundary repeats
+          if (i > 0 || lt == 0) {                             // a new run of pairs sharing one query chunk
+            ++rho;
+            const int s = rho & 1;
+            pf.lap(2);
+            if (rho >= 2) mbar_wait(&qempty[s], ((rho >> 1) + 1) & 1);
+            pf.lap(1);
+            mbar_expect_tx(&qfull[s], a.QB);
+            bulk_g2s_split(sQ[s], a.Qpk + (size_t)c * a.QB, a.QB, &qfull[s]);
+          }
+          if (i == 0 && tile + tile_step < a.n_tiles) load_O(lt + 1, tile + tile_step);
         }
       }
       pf.lap(2);
@@ -177,55 +186,71 @@ score_v3_kernel(V3Args a) {
       const uint32_t idesc3 = make_idesc_f16(128, r2p, true, true);
       const uint32_t aG = smem_u32(sG);
       const int ks1 = r2p / 16;
+      const uint64_t dQk0 = make_desc(smem_u32(sQ[0]), QCS, 128), dQk1 = make_desc(smem_u32(sQ[1]), QCS, 128);      // K-major
+      const uint64_t dQm0 = make_desc(smem_u32(sQ[0]), 128, QCS), dQm1 = make_desc(smem_u32(sQ[1]), 128, QCS);      // MN-major
+      const uint64_t dOk0 = make_desc(smem_u32(sO[0]), C::OCS, 128), dOk1 = make_desc(smem_u32(sO[1]), C::OCS, 128);
+      const uint64_t dOm0 = make_desc(smem_u32(sO[0]), 128, C::OCS), dOm1 = make_desc(smem_u32(sO[1]), 128, C::OCS);
+      const uint64_t dGk = make_desc(aG, QCS, 128), dGm = make_desc(aG, 128, QCS);
       Prof pf; pf.start(a.prof != nullptr);
       // GEMM2 + GEMM3 of pair pp = (tile lt, chunk c) whose operands sit in stages (os, qs)
-      auto g23 = [&](int pp, int lt, int c, int os, int qs) {
+      // GEMM3 + GEMM2 of pair pp = (tile lt, position i) whose operands sit in stages (os, qs); run = maximal
+      // sequence of consecutive pairs with the same query chunk (D2 keeps accumulating inside a run)
+      auto g23 = [&](int pp, int lt, int i, int os, int qs, int rho, bool new_run, bool end_run) {
         mbar_wait(&gfull, pp & 1);
         pf.lap(4);
-        if (c == 0 && lt > 0) mbar_wait(&d3free, (lt - 1) & 1);
+        if (i == 0 && lt > 0) mbar_wait(&d3free, (lt - 1) & 1);
         pf.lap(7);
         fence_after_sync();
-        const uint32_t aO = smem_u32(sO[os]), aQ = smem_u32(sQ[qs]);
+        // descriptors are built once per stage; a k-step only adds to the 14-bit address field (the uniform datapath
+        // that feeds tcgen05.mma has a long latency per dependent operation: rebuilding descriptors per MMA made the
+        // issue loop the bottleneck)
+        const uint64_t dQm = qs ? dQm1 : dQm0, dOm = os ? dOm1 : dOm0;
+#pragma unroll
         for (int ks = 0; ks < TB / 16; ++ks)        // D3[n, c] += sum_b G[b, n] Q[b, c]
-          mma_f16(tmem + C::D3_COL, make_desc(aG + ks * 256, 128, QCS), make_desc(aQ + ks * 256, 128, QCS),
-                  idesc3, (c | ks) != 0);
-        mma_commit(&qempty[qs]);                     // the Q stage is free as early as possible: its refill is the
-        if (c == n_chunks - 1) mma_commit(&d3full);  // longest latency of the pipeline
+          mma_f16(tmem + C::D3_COL, dGm + (uint64_t)(ks * 16), dQm + (uint64_t)(ks * 16), idesc3, (i | ks) != 0);
+        if (end_run) mma_commit(&qempty[qs]);        // the Q stage is free as early as possible: its refill is the
+        if (i == n_chunks - 1) mma_commit(&d3full);  // longest latency of the pipeline
         pf.lap(8);
-        if (pp > 0) { mbar_wait(&d2free, (pp - 1) & 1); fence_after_sync(); }
+        if (new_run && rho > 0) { mbar_wait(&d2free, (rho - 1) & 1); fence_after_sync(); }
         pf.lap(5);
-        for (int ks = 0; ks < TN / 16; ++ks)        // D2[b, c] = sum_n G[b, n] O[n, c]
-          mma_f16(tmem + C::D2_COL, make_desc(aG + ks * 2 * QCS, QCS, 128), make_desc(aO + ks * 256, 128, C::OCS),
-                  idesc2, ks != 0);
-        mma_commit(&d2full);
+#pragma unroll
+        for (int ks = 0; ks < TN / 16; ++ks)        // D2[b, c] (+)= sum_n G[b, n] O[n, c]
+          mma_f16(tmem + C::D2_COL, dGk + (uint64_t)(ks * (2 * QCS >> 4)), dOm + (uint64_t)(ks * 16), idesc2,
+                  !new_run || ks != 0);
+        if (end_run) mma_commit(&d2full);
         mma_commit(&gfree);
-        if (c == n_chunks - 1) mma_commit(&oempty[os]);
+        if (i == n_chunks - 1) mma_commit(&oempty[os]);
         pf.lap(6);
       };
-      int pair = 0, lt = 0;
-      int pv = 0, pv_lt = 0, pv_c = 0, pv_os = 0, pv_qs = 0;
+      int pair = 0, lt = 0, rho = -1;
+      int pv = 0, pv_lt = 0, pv_i = 0, pv_os = 0, pv_qs = 0, pv_rho = 0;
+      bool pv_new = false, pv_end = false;
       for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++lt) {
         const int os = lt & 1;
+        const bool last_tile = tile + tile_step >= a.n_tiles;
         mbar_wait(&ofull[os], (lt >> 1) & 1);
         pf.lap(0);
-        for (int c = 0; c < n_chunks; ++c, ++pair) {
-          const int qs = pair & 1;
-          mbar_wait(&qfull[qs], (pair >> 1) & 1);
+        for (int i = 0; i < n_chunks; ++i, ++pair) {
+          const bool new_run = (i > 0 || lt == 0), end_run = (i < n_chunks - 1 || last_tile);
+          if (new_run) { ++rho; mbar_wait(&qfull[rho & 1], (rho >> 1) & 1); }
+          const int qs = rho & 1;
           pf.lap(1);
           if (pair > 0) mbar_wait(&zfree, (pair - 1) & 1);
           pf.lap(2);
           fence_after_sync();
-          const uint32_t aO = smem_u32(sO[os]), aQ = smem_u32(sQ[qs]);
-          for (int ks = 0; ks < ks1; ++ks)          // Z[b, n] = sum_k Q[b, k] O[n, k]
-            mma_f16(tmem + C::Z_COL, make_desc(aQ + ks * 2 * QCS, QCS, 128), make_desc(aO + ks * 2 * C::OCS, C::OCS, 128),
-                    idesc1, ks != 0);
+          const uint64_t dQk = qs ? dQk1 : dQk0, dOk = os ? dOk1 : dOk0;
+#pragma unroll
+          for (int ks = 0; ks < R2P_MAX / 16; ++ks)  // Z[b, n] = sum_k Q[b, k] O[n, k]
+            if (ks < ks1)
+              mma_f16(tmem + C::Z_COL, dQk + (uint64_t)(ks * (2 * QCS >> 4)), dOk + (uint64_t)(ks * (2 * C::OCS >> 4)),
+                      idesc1, ks != 0);
           mma_commit(&zfull);
           pf.lap(3);
-          if (pv) g23(pair - 1, pv_lt, pv_c, pv_os, pv_qs);
-          pv = 1; pv_lt = lt; pv_c = c; pv_os = os; pv_qs = qs;
+          if (pv) g23(pair - 1, pv_lt, pv_i, pv_os, pv_qs, pv_rho, pv_new, pv_end);
+          pv = 1; pv_lt = lt; pv_i = i; pv_os = os; pv_qs = qs; pv_rho = rho; pv_new = new_run; pv_end = end_run;
         }
       }
-      if (pv) g23(pair - 1, pv_lt, pv_c, pv_os, pv_qs);
+      if (pv) g23(pair - 1, pv_lt, pv_i, pv_os, pv_qs, pv_rho, pv_new, pv_end);
       if (PROF && a.prof) pf.dump(a.prof + ((size_t)blockIdx.x * 4 + 1) * 10);
     }
   } else if (warp < 2 + kEpiWarps) {
@@ -254,12 +279,14 @@ score_v3_kernel(V3Args a) {
     double loss_acc = 0.0;
     int pair = 0;
     Prof pf; pf.start(PROF && a.prof != nullptr && warp == 2 && lane == 0);
-    for (int tile = first_tile; tile < a.n_tiles; tile += tile_step) {
+    int lt_e = 0;
+    for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++lt_e) {
       const int n0 = tile * TN;
       const int cols_valid = min(CH, a.n_local - n0 - half * CH);     // may be <= 0 on the last tile
       const int nbase = a.n_begin + n0 + half * CH;
 #pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c, ++pair) {
+      for (int i = 0; i < n_chunks; ++i, ++pair) {
+        const int c = (lt_e & 1) ? n_chunks - 1 - i : i;
         const int b = c * TB + r;
         const bool row_ok = b < a.B;
         // sparse positives of (row, this warp's columns) as a bit mask
@@ -314,6 +341,9 @@ score_v3_kernel(V3Args a) {
           const bool fast = row_ok && mg == 0u && ym < 32.0f && (16 * g + 16 <= cols_valid);
           if (fast) {
             nfast += 16;
+            // sum of log2(1 + e^{-z}) as log2 of products of three (each factor < 2^40 + 1 inside the window): one
+            // MUFU.LG2 per three logits instead of one each -- the epilogue is bound by the MUFU / MIO pipe
+            float prod = 1.0f;
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
               float gq[2];
@@ -321,7 +351,8 @@ score_v3_kernel(V3Args a) {
               for (int u = 0; u < 2; ++u) {
                 const float s = fmaf(ex2_approx(y[j + u]), 256.0f, 1.0f);    // 1 + e^{-z}
                 const float p = rcp_approx(s);
-                A1 += lg2_approx(s);
+                prod *= s;
+                if ((j + u) % 3 == 2 || j + u == 15) { A1 += lg2_approx(prod); prod = 1.0f; }
                 Y2 += y[j + u];
                 gq[u] = fmaf(p, G_SCALE, gneg);
               }
@@ -380,7 +411,7 @@ score_v3_kernel(V3Args a) {
     if (lane == 0) red[warp - 2] = wsum;
   } else {
     // ============================== flush: D2 -> H partial of this CTA, D3 -> dO ==============================
-    // H partial: thread (row r) owns H_ws[cta][chunk][quad][r][0..3]; the CTA's first tile stores, later tiles add
+    // H partial: thread (row r) owns H_ws[cta][chunk][quad][r][0..3]; the first visit of a chunk stores, later ones add
     // with red.global.add.v4.f32 (same thread, same address, program order: deterministic).  TMEM loads of the
     // next 32 columns are in flight while the current ones are written.
     const int quarter = warp & 3;
@@ -391,8 +422,9 @@ score_v3_kernel(V3Args a) {
     const uint32_t lanebits = (uint32_t)(quarter * 32) << 16;
     const int np = (r2p + 31) / 32;               // 32-column pieces (the last one may hold 16 columns)
     const bool vec_ok = (a.r2 % 4 == 0);
-    unsigned char* stg = sStg + (warp - (2 + kEpiWarps)) * STG_BYTES;
-    int pair = 0, lt = 0;
+    const bool vec8_ok = (a.r2 % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.dO) & 31) == 0);
+    int lt = 0, rho = -1;
+    unsigned long long touched = 0ull;            // chunks whose H slice this CTA has already written once
     Prof pf; pf.start(PROF && a.prof != nullptr && warp == 2 + kEpiWarps && lane == 0);
     auto ld_piece = [&](uint32_t col0, int h, uint32_t (&v)[32]) {
       if (32 * h + 32 <= r2p) tmem_ld32(tmem + lanebits + col0 + 32u * h, v);
@@ -401,22 +433,30 @@ score_v3_kernel(V3Args a) {
     for (int tile = first_tile; tile < a.n_tiles; tile += tile_step, ++lt) {
       const int n0 = tile * TN;
       const int n_valid = min(TN, a.n_local - n0);
-      for (int c = 0; c < n_chunks; ++c, ++pair) {
+      const bool last_tile = tile + tile_step >= a.n_tiles;
+      for (int i = 0; i < n_chunks; ++i) {
+        const int c = (lt & 1) ? n_chunks - 1 - i : i;
+        if (i > 0 || lt == 0) ++rho;
+        if (!(i < n_chunks - 1 || last_tile)) continue;      // the run continues into the next tile: D2 keeps accumulating
+        const bool first_touch = !((touched >> c) & 1ull);
+        touched |= 1ull << c;
         float* hrow = a.H_ws + ((size_t)blockIdx.x * n_chunks + c) * ((size_t)r2p * TB) + (size_t)r * 4;
         auto st_piece = [&](int h, const uint32_t (&v)[32]) {
           const int nq = (32 * h + 32 <= r2p) ? 8 : 4;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (j < nq) {
+              // a warp instruction covers 32 rows x 16 B = 512 contiguous bytes: whole 32-byte sectors for the
+              // L2 atomic units (a 32-byte-per-thread layout halves their throughput: measured)
               float* dst = hrow + (size_t)(8 * h + j) * (TB * 4);
               const float x0 = __uint_as_float(v[4 * j]) * hscale, x1 = __uint_as_float(v[4 * j + 1]) * hscale;
               const float x2 = __uint_as_float(v[4 * j + 2]) * hscale, x3 = __uint_as_float(v[4 * j + 3]) * hscale;
-              if (lt == 0) *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+              if (first_touch) *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
               else red_add_v4(dst, x0, x1, x2, x3);
             }
           }
         };
-        mbar_wait(&d2full, pair & 1);
+        mbar_wait(&d2full, rho & 1);
         __syncwarp();
         pf.lap(0);
         fence_after_sync();
@@ -424,50 +464,60 @@ score_v3_kernel(V3Args a) {
         ld_piece(C::D2_COL, 0, va);
         for (int h = 0; h < np; h += 2) {
           tmem_ld_wait();
+          pf.lap(2);
           if (h + 1 < np) ld_piece(C::D2_COL, h + 1, vb);
           else { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(&d2free); }
           st_piece(h, va);
+          pf.lap(first_touch ? 3 : 1);
           if (h + 1 >= np) break;
           tmem_ld_wait();
+          pf.lap(2);
           if (h + 2 < np) ld_piece(C::D2_COL, h + 2, va);
           else { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(&d2free); }
           st_piece(h + 1, vb);
+          pf.lap(first_touch ? 3 : 1);
         }
-        pf.lap(1);
       }
       // ---- tile epilogue: D3 -> dO rows of this tile (transposed through shared memory: 128-byte row segments) ----
       mbar_wait(&d3full, lt & 1);
       __syncwarp();
       pf.lap(7);
       fence_after_sync();
-      for (int h = 0; h < np; ++h) {
+      {
+        // straight from registers: every memory instruction of these warps queues behind the epilogue's MUFU stream
+        // (same MIO path), so the fewest, widest instructions win: 32-byte stores where the row pitch allows
         uint32_t v[32];
-        ld_piece(C::D3_COL, h, v);
-        tmem_ld_wait();
-        if (h == np - 1) { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(&d3free); }
-        const int ncol = min(32, r2p - 32 * h);
-        if (vec_ok) {
+        ld_piece(C::D3_COL, 0, v);
+        for (int h = 0; h < np; ++h) {
+          const int ncol = min(min(32, r2p - 32 * h), a.r2 - 32 * h);
+          tmem_ld_wait();
+          pf.lap(9);
+          if (r < n_valid) {
+            float* drow = a.dO + (size_t)(n0 + r) * a.r2 + 32 * h;
+            if (vec8_ok) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_float4(__uint_as_float(v[4 * j]) * dscale, __uint_as_float(v[4 * j + 1]) * dscale,
-                            __uint_as_float(v[4 * j + 2]) * dscale, __uint_as_float(v[4 * j + 3]) * dscale);
-          __syncwarp();
-          const int ch = lane & 7;
+              for (int j = 0; j < 4; ++j)
+                if (8 * j < ncol)
+                  st_v8(drow + 8 * j, __uint_as_float(v[8 * j]) * dscale, __uint_as_float(v[8 * j + 1]) * dscale,
+                        __uint_as_float(v[8 * j + 2]) * dscale, __uint_as_float(v[8 * j + 3]) * dscale,
+                        __uint_as_float(v[8 * j + 4]) * dscale, __uint_as_float(v[8 * j + 5]) * dscale,
+                        __uint_as_float(v[8 * j + 6]) * dscale, __uint_as_float(v[8 * j + 7]) * dscale);
+            } else if (vec_ok) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = 4 * i + (lane >> 3);
-            const int col = 32 * h + 4 * ch;
-            const float4 x = *reinterpret_cast<const float4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
-            if (quarter * 32 + row < n_valid && 4 * ch < ncol && col < a.r2)
-              *reinterpret_cast<float4*>(a.dO + (size_t)(n0 + quarter * 32 + row) * a.r2 + col) = x;
+              for (int j = 0; j < 8; ++j)
+                if (4 * j < ncol)
+                  *reinterpret_cast<float4*>(drow + 4 * j) =
+                      make_float4(__uint_as_float(v[4 * j]) * dscale, __uint_as_float(v[4 * j + 1]) * dscale,
+                                  __uint_as_float(v[4 * j + 2]) * dscale, __uint_as_float(v[4 * j + 3]) * dscale);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) drow[j] = __uint_as_float(v[j]) * dscale;
+            }
           }
-          __syncwarp();
-        } else if (r < n_valid) {
-          float* drow = a.dO + (size_t)(n0 + r) * a.r2 + 32 * h;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol && 32 * h + j < a.r2) drow[j] = __uint_as_float(v[j]) * dscale;
+          if (h + 1 < np) ld_piece(C::D3_COL, h + 1, v);
+          else { fence_before_sync(); __syncwarp(); if (lane == 0) mbar_arrive(&d3free); }
+          pf.lap(8);
         }
       }
       pf.lap(8);
@@ -661,7 +711,7 @@ V3Layout v3_layout(int B, int n_local, int r2) {
   L.OB = (uint32_t)L.ncb * L.TN * 16u;
   L.QB = (uint32_t)L.ncb * QCS;
   // G3 reads 16 n-blocks of G whatever TN is: keep 32 KB addressable behind sG
-  const uint32_t tail = (uint32_t)(L.TN / 8) * QCS + kFlushWarps * STG_BYTES;
+  const uint32_t tail = (uint32_t)(L.TN / 8) * QCS;
   L.smem = 2 * L.OB + 2 * L.QB + (tail < 16 * QCS ? 16 * QCS : tail);
   size_t o = rt::align_up((size_t)L.grid * L.n_chunks * L.r2p * TB * sizeof(float), 256);
   L.off_loss = o; o += rt::align_up((size_t)L.grid * sizeof(double), 256);
@@ -699,7 +749,7 @@ extern "C" int rt_score_bce_v3_phases(const float* q, const float* O, int B, int
                                       float label_smoothing, float o_absmax_hint, double* loss_sum, float* H, float* dO,
                                       void* ws, void* stream, int phases) {
   RT_REQUIRE(rt_score_bce_v3_supported(r2), "rt_score_bce_v3: r2=%d out of range (1..%d)", r2, R2P_MAX);
-  RT_REQUIRE(B >= 1 && n_local >= 0, "rt_score_bce_v3: bad sizes B=%d n_local=%d", B, n_local);
+  RT_REQUIRE(B >= 1 && B <= 64 * TB && n_local >= 0, "rt_score_bce_v3: bad sizes B=%d (1..%d) n_local=%d", B, 64 * TB, n_local);
   cudaStream_t s = (cudaStream_t)stream;
   const V3Layout L = v3_layout(B, n_local, r2);
   char* base = (char*)ws;

@@ -107,3 +107,59 @@ extern "C" int rt_bulk_reduce_selftest(const float* a, const float* b, float* ou
   RT_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- MMA throughput probe: `reps` back-to-back kind::f16 MMAs (M = 128, N, K = 16 each, `ksteps` distinct
+//      k-steps cycled) on operands resident in shared memory; returns the elapsed SM cycles of the issue..commit
+//      window.  a_mn / b_mn choose the descriptor view; the contents are irrelevant (zeros). ----
+namespace {
+__global__ void __launch_bounds__(128, 1)
+mma_probe_kernel(int N, int ksteps, int a_mn, int b_mn, int reps, long long* out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int e = tid; e < 200 * 1024 / 4; e += 128) reinterpret_cast<uint32_t*>(smem)[e] = 0u;
+  if (tid == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<256>(&tmem_base_slot);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  if (tid == 0) {
+    const uint32_t a_CS = 128 * 16, b_CS = (uint32_t)N * 16u, RS = 128u;
+    const uint32_t sA = smem_u32(smem), sB = sA + 64 * 1024;
+    const uint32_t idesc = make_idesc_f16(128, N, a_mn != 0, b_mn != 0);
+    // descriptors are built once; a k-step only adds to the 14-bit address field (the uniform datapath that feeds
+    // tcgen05.mma has a long latency per dependent operation: rebuilding a descriptor per MMA costs ~200 cycles)
+    const uint64_t da0 = a_mn ? make_desc(sA, RS, a_CS) : make_desc(sA, a_CS, RS);
+    const uint64_t db0 = b_mn ? make_desc(sB, RS, b_CS) : make_desc(sB, b_CS, RS);
+    const uint32_t sa = (a_mn ? 2 * RS : 2 * a_CS) >> 4, sb = (b_mn ? 2 * RS : 2 * b_CS) >> 4;
+    (void)ksteps;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < reps; i += 8) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) mma_f16(tmem, da0 + (uint64_t)(ks * sa), db0 + (uint64_t)(ks * sb), idesc, (i | ks) > 0);
+    }
+    const long long t1 = clock64();
+    mma_commit(&mbar);
+    mbar_wait(&mbar, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+}  // namespace
+
+extern "C" int rt_mma_probe(int N, int ksteps, int a_mn, int b_mn, int reps, long long* out_dev, void* stream) {
+  RT_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && ksteps >= 1 && ksteps <= 8 && reps >= 1, "rt_mma_probe: bad arguments");
+  const size_t smem = 200 * 1024;
+  RT_CHECK_CUDA(cudaFuncSetAttribute(mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(N, ksteps, a_mn, b_mn, reps, out_dev);
+  RT_LAUNCH_CHECK();
+  return 0;
+}

@@ -31,7 +31,7 @@ p = prof.double().cpu()
 names = [["wait oempty", "wait qempty", "issue/other"] + [""] * 7,
          ["wait ofull", "wait qfull", "wait zfree", "issue G1", "wait gfull", "wait d2free", "issue G2", "wait d3free", "issue G3", ""],
          ["mask", "wait zfull", "tmem ld", "math", "wait gfree", "store G", "", "", "", ""],
-         ["wait d2full", "D2 flush", "", "", "", "", "", "wait d3full", "d3 flush", ""]]
+         ["wait d2full", "D2 red.add", "D2 tmem ld wait", "D2 first st", "", "", "", "wait d3full", "d3 stores", "d3 tmem ld wait"]]
 for r, role in enumerate(["producer", "mma", "epilogue(w2)", "flush leader"]):
     tot = p[:, r].sum(1).mean()
     print(f"{role}: total {tot:.0f} cycles")
