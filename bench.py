@@ -220,6 +220,8 @@ def main():
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keeps NCCL's version banner off stdout: rank 0 prints ONE JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
