@@ -117,20 +117,19 @@ gemm64_kernel(GemmT<T> g) {
   }
 }
 
-// one warp per output element: lanes stride over the splits, shuffle-tree sum (fixed order)
+// one thread per output element, splits summed in index order (fixed order: deterministic); consecutive threads
+// read consecutive elements of each partial slab
 template <typename T>
 __global__ void gemm64_reduce_kernel(GemmT<T> g) {
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (e >= g.m * g.n) return;
-  const int mm = e / g.n, nn = e - mm * g.n;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t mn = (int64_t)g.m * g.n;
+  if (e >= mn) return;
+  const int mm = (int)(e / g.n), nn = (int)(e - (int64_t)mm * g.n);
   T s = (T)0;
-  for (int k = lane; k < g.ksplit; k += 32) s += g.partial[(int64_t)k * g.m * g.n + e];
-  s = rt::warp_sum(s);
-  if (lane == 0) {
-    T* c = g.C + (int64_t)mm * g.c_m + (int64_t)nn * g.c_n;
-    *c = (T)g.alpha * s + (g.beta != 0.0 ? (T)g.beta * (*c) : (T)0);
-  }
+#pragma unroll 4
+  for (int k = 0; k < g.ksplit; ++k) s += g.partial[(int64_t)k * mn + e];
+  T* c = g.C + (int64_t)mm * g.c_m + (int64_t)nn * g.c_n;
+  *c = (T)g.alpha * s + (g.beta != 0.0 ? (T)g.beta * (*c) : (T)0);
 }
 
 // ---- elementwise helpers ----------------------------------------------------------------
