@@ -196,15 +196,16 @@ struct Ctx {
     dot_final_kernel<<<1, 32, 0, s>>>(p(L.dot_partial), blocks, scale, out, accumulate); rt::g_launches += 2;
   }
   int spd(const SpdBatch& b, int count, int nmax) {
-    const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + nmax) * sizeof(double);
-    if (smem > 227 * 1024) { rt::set_error("small stage: rank %d exceeds the in-shared-memory Cholesky limit (240)", nmax); return 2; }
+    const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + (size_t)SPD_NB * nmax) * sizeof(double);
+    if (smem > 227 * 1024 || nmax > 256) {
+      rt::set_error("small stage: rank %d exceeds the in-shared-memory Cholesky limit (232)", nmax); return 2; }
     static size_t configured = 0;
     if (smem > configured) {
-      if (cudaFuncSetAttribute(spd_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      if (cudaFuncSetAttribute(spd_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         rt::set_error("small stage: cannot raise shared memory to %zu", smem); return 1; }
       configured = smem;
     }
-    spd_factor_kernel<<<count, 1024, smem, s>>>(b); ++rt::g_launches;
+    spd_blocked_kernel<<<count, 1024, smem, s>>>(b); ++rt::g_launches;
     return 0;
   }
 };
