@@ -12,6 +12,7 @@
 // grid.sync() separates the phases.  N-independent, latency-bound: reported separately from the
 // HBM / tensor rooflines (SURVEY.md section 8d "N-independent serial part").
 #include "common.h"
+#include "tc.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
 
@@ -299,6 +300,13 @@ eig_block_jacobi_kernel(EigBatch batch) {
   double* Qk = T + EP * ELD;
   double* Ql = Qk + EP * ELD;
   __shared__ double red[kEigWarps], red2[kEigWarps];
+  __shared__ uint64_t jbar[kEigWarps];      // per warp: completion of the bulk copies of Q_l / Q_k in phase B
+  uint32_t jph = 0u;
+  if (threadIdx.x == 0) {
+    for (int wq = 0; wq < kEigWarps; ++wq) tc::mbar_init(&jbar[wq], 1);
+    tc::fence_mbar_init();
+  }
+  __syncthreads();
 
   // ---- phase 0: scale factor, padded copies, V = I, norms ----
   for (int pi = 0; pi < batch.count; ++pi) {
@@ -336,6 +344,9 @@ eig_block_jacobi_kernel(EigBatch batch) {
   for (int pi = 0; pi < kMaxProblems; ++pi) done[pi] = (pi >= batch.count);
 
   long long tA = 0, tS1 = 0, tB = 0, tS2 = 0, t0 = 0, t1 = 0;
+#ifdef RT_EIG_PROF
+  long long pLoad = 0, pVisit = 0, pStore = 0, pN = 0;
+#endif
   for (int sweep = 0; sweep < kMaxSweeps; ++sweep) {
     bool all_done = true;
     for (int pi = 0; pi < batch.count; ++pi) all_done = all_done && done[pi];
@@ -364,6 +375,9 @@ eig_block_jacobi_kernel(EigBatch batch) {
           int* pqi = reinterpret_cast<int*>(csf + 4 * EB);
           VisitSmem vm{{Sf0, Sf1}, Qm, csd, csf, pqi, pqi + 4 * EB};
           double dsum = 0.0;
+#ifdef RT_EIG_PROF
+          long long q0 = clock64(), q1;
+#endif
           for (int e = threadIdx.x; e < EP * EP; e += kEigThreads) {
             const int i = e / EP, j = e % EP;
             const double v = P.Ap[(int64_t)pair_index(bi, bj, i) * P.np + pair_index(bi, bj, j)];
@@ -386,9 +400,19 @@ eig_block_jacobi_kernel(EigBatch batch) {
               Sf0[i * ELDF + j] = (float)(i == j ? v - mu : v);
             }
             __syncthreads();
+#ifdef RT_EIG_PROF
+            q1 = clock64(); pLoad += q1 - q0; q0 = q1;
+#endif
             cta_visit(vm, intra);
-            for (int e = threadIdx.x; e < EP * EP; e += kEigThreads)
-              P.J[(int64_t)item * EP * EP + e] = Qm[(e / EP) * ELD + (e % EP)];
+#ifdef RT_EIG_PROF
+            q1 = clock64(); pVisit += q1 - q0; q0 = q1; ++pN;
+#endif
+            // J keeps the padded shared-memory layout [EP][ELD], so that phase B fetches it with ONE bulk copy
+            for (int e = threadIdx.x; e < EP * ELD; e += kEigThreads)
+              P.J[(int64_t)item * EP * ELD + e] = Qm[e];
+#ifdef RT_EIG_PROF
+            q1 = clock64(); pStore += q1 - q0; q0 = q1;
+#endif
           }
           if (threadIdx.x == 0) {
             P.skip[item] = skip ? 1 : 0;
@@ -422,18 +446,25 @@ eig_block_jacobi_kernel(EigBatch batch) {
           rr_pair(P.nb, round, l, bil, bjl);
           double* M = isV ? P.Vp : P.Ap;
           // ---- tiles -> shared memory: every 16-byte chunk is one cp.async (all in flight together) ----
+          // the rotation products Q_l, Q_k arrive by bulk copies (one instruction each: a warp's 16-byte cp.async
+          // stream was the slowest part of this phase), the gathered tile by cp.async
+          const bool need_l = !sl, need_k = !isV && !sk;
+          __syncwarp();                                   // earlier reads of T / Ql / Qk by this warp are done
+          if (lane == 0 && (need_l || need_k)) {
+            asm volatile("fence.proxy.async;\n" ::: "memory");     // generic accesses (smem reads, J written by other CTAs) before the async proxy
+            tc::mbar_expect_tx(&jbar[warp], (uint32_t)((need_l ? 1 : 0) + (need_k ? 1 : 0)) * (uint32_t)(EP * ELD * sizeof(double)));
+            if (need_l) tc::bulk_g2s(Ql, P.J + (int64_t)l * EP * ELD, (uint32_t)(EP * ELD * sizeof(double)), &jbar[warp]);
+            if (need_k) tc::bulk_g2s(Qk, P.J + (int64_t)k * EP * ELD, (uint32_t)(EP * ELD * sizeof(double)), &jbar[warp]);
+          }
           for (int cidx = lane; cidx < EP * (EP / 2); cidx += 32) {
             const int i = cidx >> 4, jc = (cidx & 15) * 2;            // row, first of two columns
             const int gi = isV ? k * EP + i : pair_index(bik, bjk, i);
             cp_async16_d(&T[i * ELD + jc], M + (int64_t)gi * P.np + pair_index(bil, bjl, jc));
-            if (!sl) cp_async16_d(&Ql[i * ELD + jc], P.J + (int64_t)l * EP * EP + i * EP + jc);
-            else { Ql[i * ELD + jc] = (i == jc) ? 1.0 : 0.0; Ql[i * ELD + jc + 1] = (i == jc + 1) ? 1.0 : 0.0; }
-            if (!isV) {
-              if (!sk) cp_async16_d(&Qk[i * ELD + jc], P.J + (int64_t)k * EP * EP + i * EP + jc);
-              else { Qk[i * ELD + jc] = (i == jc) ? 1.0 : 0.0; Qk[i * ELD + jc + 1] = (i == jc + 1) ? 1.0 : 0.0; }
-            }
+            if (sl) { Ql[i * ELD + jc] = (i == jc) ? 1.0 : 0.0; Ql[i * ELD + jc + 1] = (i == jc + 1) ? 1.0 : 0.0; }
+            if (!isV && sk) { Qk[i * ELD + jc] = (i == jc) ? 1.0 : 0.0; Qk[i * ELD + jc + 1] = (i == jc + 1) ? 1.0 : 0.0; }
           }
           cp_async_wait_all_d();
+          if (need_l || need_k) { tc::mbar_wait(&jbar[warp], jph); jph ^= 1u; }
           __syncwarp();
           // ---- X = T Ql ;  Y = Qk^T X  on the fp64 tensor cores ----
           const int g = lane >> 2, t = lane & 3;
@@ -476,6 +507,11 @@ eig_block_jacobi_kernel(EigBatch batch) {
     }
   }
 
+#ifdef RT_EIG_PROF
+  if (threadIdx.x == 0 && blockIdx.x == 5)
+    printf("eig cta %d: phaseA %lld = load %lld visit %lld store %lld (visits %lld) sync1 %lld phaseB %lld sync2 %lld\n",
+           blockIdx.x, tA, pLoad, pVisit, pStore, pN, tS1, tB, tS2);
+#endif
   if (batch.prof && threadIdx.x == 0) {
     batch.prof[blockIdx.x * 4 + 0] = tA; batch.prof[blockIdx.x * 4 + 1] = tS1;
     batch.prof[blockIdx.x * 4 + 2] = tB; batch.prof[blockIdx.x * 4 + 3] = tS2;
@@ -520,7 +556,7 @@ EigLayout eig_layout(int n) {
   size_t o = 0;
   L.off_Ap = o; o += align_up(sizeof(double) * L.np * L.np, 256);
   L.off_Vp = o; o += align_up(sizeof(double) * L.np * L.np, 256);
-  L.off_J = o; o += align_up(sizeof(double) * L.npairs * EP * EP, 256);
+  L.off_J = o; o += align_up(sizeof(double) * L.npairs * EP * ELD, 256);
   L.off_skip = o; o += align_up(sizeof(int) * L.npairs, 256);
   L.off_scal = o; o += align_up(sizeof(double) * (kPermSlot + L.np), 256);
   L.total = o;
