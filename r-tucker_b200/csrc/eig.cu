@@ -266,6 +266,9 @@ __device__ __forceinline__ void apply_round(const VisitSmem& m, int buf, int fir
 // cyclic Jacobi whose rotations are applied to the matrix tile-wise in phase B.
 // Pipeline, ONE barrier per inner round:  warp 0 derives the rotations of round r+1 from S_r and the
 // rotations of round r, while warps 1.. apply round r (S_r -> S_{r+1} in fp32, Q <- Q R_r in fp64).
+#ifdef RT_EIG_PROF
+__device__ long long g_vprof[8];
+#endif
 __device__ void cta_visit(const VisitSmem& m, bool intra) {
   const int tid = threadIdx.x;
   for (int e = tid; e < EP * EP; e += kEigThreads) m.Q[(e / EP) * ELD + (e % EP)] = (e / EP == e % EP) ? 1.0 : 0.0;
@@ -275,6 +278,9 @@ __device__ void cta_visit(const VisitSmem& m, bool intra) {
   __syncthreads();
   for (int r = 0; r < total; ++r) {
     const int buf = r & 1;
+#ifdef RT_EIG_PROF
+    const long long v0 = clock64();
+#endif
     if (tid < 32) {
       if (r + 1 < total) {
         const int rn = r + 1;
@@ -283,7 +289,15 @@ __device__ void cta_visit(const VisitSmem& m, bool intra) {
     } else {
       apply_round(m, buf, 32);
     }
+#ifdef RT_EIG_PROF
+    const long long v1 = clock64();
+#endif
     __syncthreads();
+#ifdef RT_EIG_PROF
+    const long long v2 = clock64();
+    if (tid == 0) { g_vprof[0] += v1 - v0; g_vprof[1] += v2 - v1; g_vprof[4] += 1; }
+    if (tid == 32) { g_vprof[2] += v1 - v0; g_vprof[3] += v2 - v1; }
+#endif
   }
 }
 
@@ -343,6 +357,8 @@ eig_block_jacobi_kernel(EigBatch batch) {
   bool done[kMaxProblems];
   for (int pi = 0; pi < kMaxProblems; ++pi) done[pi] = (pi >= batch.count);
 
+  double norm2[kMaxProblems];                 // ||A||_F^2 of every problem: fixed after the set-up phase
+  for (int pi = 0; pi < kMaxProblems; ++pi) norm2[pi] = (pi < batch.count) ? batch.p[pi].scal[0] : 0.0;
   long long tA = 0, tS1 = 0, tB = 0, tS2 = 0, t0 = 0, t1 = 0;
 #ifdef RT_EIG_PROF
   long long pLoad = 0, pVisit = 0, pStore = 0, pN = 0;
@@ -378,9 +394,22 @@ eig_block_jacobi_kernel(EigBatch batch) {
 #ifdef RT_EIG_PROF
           long long q0 = clock64(), q1;
 #endif
-          for (int e = threadIdx.x; e < EP * EP; e += kEigThreads) {
+          // the tile is read from global memory ONCE (all loads in flight together) and kept in registers for the
+          // steering copy below: the visit is on the critical path of the round, every L2 round trip counts
+          constexpr int kTileRegs = (EP * EP) / kEigThreads;
+          static_assert(kTileRegs * kEigThreads == EP * EP, "tile elements per thread");
+          double tv[kTileRegs];
+#pragma unroll
+          for (int u = 0; u < kTileRegs; ++u) {
+            const int e = threadIdx.x + u * kEigThreads;
             const int i = e / EP, j = e % EP;
-            const double v = P.Ap[(int64_t)pair_index(bi, bj, i) * P.np + pair_index(bi, bj, j)];
+            tv[u] = P.Ap[(int64_t)pair_index(bi, bj, i) * P.np + pair_index(bi, bj, j)];
+          }
+#pragma unroll
+          for (int u = 0; u < kTileRegs; ++u) {
+            const int e = threadIdx.x + u * kEigThreads;
+            const int i = e / EP, j = e % EP;
+            const double v = tv[u];
             const bool cross = (i < EB) != (j < EB);
             if (cross || (intra && i != j)) off += v * v;
             if (i == j) dsum += v;
@@ -391,13 +420,14 @@ eig_block_jacobi_kernel(EigBatch batch) {
           __syncthreads();
           off = 0.0; dsum = 0.0;
           for (int wq = 0; wq < kEigWarps; ++wq) { off += red[wq]; dsum += red2[wq]; }
-          const bool skip = (off <= 1e-30 * P.scal[0]);
+          const bool skip = (off <= 1e-30 * norm2[pi]);
           if (!skip) {
             const double mu = dsum / EP;       // the steering tile holds A - mu I (rotations do not see the shift)
-            for (int e = threadIdx.x; e < EP * EP; e += kEigThreads) {
+#pragma unroll
+            for (int u = 0; u < kTileRegs; ++u) {
+              const int e = threadIdx.x + u * kEigThreads;
               const int i = e / EP, j = e % EP;
-              const double v = P.Ap[(int64_t)pair_index(bi, bj, i) * P.np + pair_index(bi, bj, j)];
-              Sf0[i * ELDF + j] = (float)(i == j ? v - mu : v);
+              Sf0[i * ELDF + j] = (float)(i == j ? tv[u] - mu : tv[u]);
             }
             __syncthreads();
 #ifdef RT_EIG_PROF
@@ -438,30 +468,35 @@ eig_block_jacobi_kernel(EigBatch batch) {
           int k, l;
           if (isV) { k = (item - nA) / P.npairs; l = (item - nA) % P.npairs; }
           else { k = item / P.npairs; l = item % P.npairs; }
-          const bool sk = isV ? true : (P.skip[k] != 0);
-          const bool sl = P.skip[l] != 0;
-          if (sk && sl) continue;
           int bik = 0, bjk = 0, bil, bjl;
           if (!isV) rr_pair(P.nb, round, k, bik, bjk);
           rr_pair(P.nb, round, l, bil, bjl);
           double* M = isV ? P.Vp : P.Ap;
-          // ---- tiles -> shared memory: every 16-byte chunk is one cp.async (all in flight together) ----
-          // the rotation products Q_l, Q_k arrive by bulk copies (one instruction each: a warp's 16-byte cp.async
-          // stream was the slowest part of this phase), the gathered tile by cp.async
-          const bool need_l = !sl, need_k = !isV && !sk;
+          // ---- tiles -> shared memory.  The gathered tile goes first (16-byte cp.async, all in flight together, issued
+          //      before the skip flags are even read: their L2 round trip hides behind it); the rotation products
+          //      Q_l, Q_k arrive by bulk copies (one instruction each: a warp's cp.async stream was the slowest part) ----
           __syncwarp();                                   // earlier reads of T / Ql / Qk by this warp are done
+          for (int cidx = lane; cidx < EP * (EP / 2); cidx += 32) {
+            const int i = cidx >> 4, jc = (cidx & 15) * 2;            // row, first of two columns
+            const int gi = isV ? k * EP + i : pair_index(bik, bjk, i);
+            cp_async16_d(&T[i * ELD + jc], M + (int64_t)gi * P.np + pair_index(bil, bjl, jc));
+          }
+          const bool sk = isV ? true : (P.skip[k] != 0);
+          const bool sl = P.skip[l] != 0;
+          if (sk && sl) { cp_async_wait_all_d(); __syncwarp(); continue; }
+          const bool need_l = !sl, need_k = !isV && !sk;
           if (lane == 0 && (need_l || need_k)) {
             asm volatile("fence.proxy.async;\n" ::: "memory");     // generic accesses (smem reads, J written by other CTAs) before the async proxy
             tc::mbar_expect_tx(&jbar[warp], (uint32_t)((need_l ? 1 : 0) + (need_k ? 1 : 0)) * (uint32_t)(EP * ELD * sizeof(double)));
             if (need_l) tc::bulk_g2s(Ql, P.J + (int64_t)l * EP * ELD, (uint32_t)(EP * ELD * sizeof(double)), &jbar[warp]);
             if (need_k) tc::bulk_g2s(Qk, P.J + (int64_t)k * EP * ELD, (uint32_t)(EP * ELD * sizeof(double)), &jbar[warp]);
           }
-          for (int cidx = lane; cidx < EP * (EP / 2); cidx += 32) {
-            const int i = cidx >> 4, jc = (cidx & 15) * 2;            // row, first of two columns
-            const int gi = isV ? k * EP + i : pair_index(bik, bjk, i);
-            cp_async16_d(&T[i * ELD + jc], M + (int64_t)gi * P.np + pair_index(bil, bjl, jc));
-            if (sl) { Ql[i * ELD + jc] = (i == jc) ? 1.0 : 0.0; Ql[i * ELD + jc + 1] = (i == jc + 1) ? 1.0 : 0.0; }
-            if (!isV && sk) { Qk[i * ELD + jc] = (i == jc) ? 1.0 : 0.0; Qk[i * ELD + jc + 1] = (i == jc + 1) ? 1.0 : 0.0; }
+          if (sl || (!isV && sk)) {
+            for (int cidx = lane; cidx < EP * (EP / 2); cidx += 32) {
+              const int i = cidx >> 4, jc = (cidx & 15) * 2;
+              if (sl) { Ql[i * ELD + jc] = (i == jc) ? 1.0 : 0.0; Ql[i * ELD + jc + 1] = (i == jc + 1) ? 1.0 : 0.0; }
+              if (!isV && sk) { Qk[i * ELD + jc] = (i == jc) ? 1.0 : 0.0; Qk[i * ELD + jc + 1] = (i == jc + 1) ? 1.0 : 0.0; }
+            }
           }
           cp_async_wait_all_d();
           if (need_l || need_k) { tc::mbar_wait(&jbar[warp], jph); jph ^= 1u; }
@@ -508,6 +543,9 @@ eig_block_jacobi_kernel(EigBatch batch) {
   }
 
 #ifdef RT_EIG_PROF
+  if (threadIdx.x == 0 && blockIdx.x == 5)
+    printf("visit rounds %lld (all CTAs): warp0 next_pairs %lld wait %lld | warp1 apply %lld wait %lld (cycles per round)\n", g_vprof[4],
+           g_vprof[0] / max(1ll, g_vprof[4]), g_vprof[1] / max(1ll, g_vprof[4]), g_vprof[2] / max(1ll, g_vprof[4]), g_vprof[3] / max(1ll, g_vprof[4]));
   if (threadIdx.x == 0 && blockIdx.x == 5)
     printf("eig cta %d: phaseA %lld = load %lld visit %lld store %lld (visits %lld) sync1 %lld phaseB %lld sync2 %lld\n",
            blockIdx.x, tA, pLoad, pVisit, pStore, pN, tS1, tB, tS2);
