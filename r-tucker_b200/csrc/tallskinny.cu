@@ -125,6 +125,86 @@ gram_partial_kernel(const float* __restrict__ A, int64_t lda, const float* __res
     }
 }
 
+// ---- exact-fp64 Gram on the fp64 tensor cores (what rt_gram(precise = 1) launches) ----
+// Same tiling and the same two-stage, fixed-order reduction as gram_partial_kernel<true>; the products of two fp32
+// values are exact in fp64 and accumulated in fp64 by mma.sync m8n8k4 (DMMA).  A CTA owns a 64 x 64 output tile over
+// its row split; warp w owns the 8 x 64 strip of A-columns [8w, 8w + 8): eight 8 x 8 accumulator tiles.
+// Row chunks are staged in shared memory as doubles (pitch 72: the four k-rows of a fragment load fall into
+// different bank halves).
+__device__ __forceinline__ void dmma884_g(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+constexpr int DG_LD = GT + 8;
+__global__ void __launch_bounds__(256)
+gram_dmma_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+                 int n, int ra, int rb, int tiles_b, int rows_per_split, double* __restrict__ partial) {
+  __shared__ double As[GKC][DG_LD];
+  __shared__ double Bs[GKC][DG_LD];
+  const int tile = blockIdx.x, ta = tile / tiles_b, tb = tile - ta * tiles_b;
+  const int a0 = ta * GT, b0 = tb * GT;
+  const int split = blockIdx.y;
+  const int row_beg = split * rows_per_split;
+  const int row_end = min(n, row_beg + rows_per_split);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const bool warp_ok = a0 + 8 * warp < ra;
+  const int nbj = min(8, (rb - b0 + 7) / 8);
+  const bool vec_a = (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool vec_b = (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  double c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j][0] = 0.0; c[j][1] = 0.0; }
+  for (int r0 = row_beg; r0 < row_end; r0 += GKC) {
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int row = pass * 16 + (tid >> 4), c4 = (tid & 15) * 4;
+      const int gr = r0 + row;
+      float va[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gr < row_end) {
+        const float* pa = A + (int64_t)gr * lda + a0 + c4;
+        const float* pb = B + (int64_t)gr * ldb + b0 + c4;
+        if (vec_a && a0 + c4 + 4 <= ra) { const float4 x = __ldg(reinterpret_cast<const float4*>(pa)); va[0] = x.x; va[1] = x.y; va[2] = x.z; va[3] = x.w; }
+        else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) if (a0 + c4 + u < ra) va[u] = __ldg(pa + u);
+        }
+        if (vec_b && b0 + c4 + 4 <= rb) { const float4 x = __ldg(reinterpret_cast<const float4*>(pb)); vb[0] = x.x; vb[1] = x.y; vb[2] = x.z; vb[3] = x.w; }
+        else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) if (b0 + c4 + u < rb) vb[u] = __ldg(pb + u);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { As[row][c4 + u] = (double)va[u]; Bs[row][c4 + u] = (double)vb[u]; }
+    }
+    __syncthreads();
+    if (warp_ok) {
+#pragma unroll
+      for (int kk = 0; kk < GKC / 4; ++kk) {
+        const double a = As[4 * kk + t][8 * warp + g];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < nbj) dmma884_g(c[j][0], c[j][1], a, Bs[4 * kk + t][8 * j + g]);
+      }
+    }
+    __syncthreads();
+  }
+  if (warp_ok) {
+    const int i = a0 + 8 * warp + g;
+    if (i < ra) {
+      double* prow = partial + ((int64_t)split * ra + i) * rb;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = b0 + 8 * j + 2 * t;
+        if (j < nbj) {
+          if (col < rb) prow[col] = c[j][0];
+          if (col + 1 < rb) prow[col + 1] = c[j][1];
+        }
+      }
+    }
+  }
+}
+
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, int nsplit, int count,
                                    double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,8 +380,7 @@ extern "C" int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb,
   GramPlan p = gram_plan(n, ra, rb);
   dim3 grid(p.tiles_a * p.tiles_b, p.nsplit);
   if (precise)
-    gram_partial_kernel<true><<<grid, 256, 0, s>>>(A, lda, B, ldb, n, ra, rb, p.tiles_b,
-                                                   p.rows_per_split, (double*)ws);
+    gram_dmma_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, n, ra, rb, p.tiles_b, p.rows_per_split, (double*)ws);
   else
     gram_partial_kernel<false><<<grid, 256, 0, s>>>(A, lda, B, ldb, n, ra, rb, p.tiles_b,
                                                     p.rows_per_split, (double*)ws);

@@ -81,6 +81,21 @@ def test_gram(cuda_device, n, ra, rb):
     assert relerr(out, ref) < 1e-6
 
 
+@pytest.mark.parametrize("n,ra,rb", [(4097, 200, 200), (40943, 200, 200), (1001, 33, 17), (130, 10, 40), (5, 3, 3),
+                                     (2000, 7, 201)])
+def test_gram_precise_fp64_tensor_cores(cuda_device, n, ra, rb):
+    """precise=True (the Gram that feeds the retraction's Cholesky): exact fp32 x fp32 products accumulated in fp64 on
+    the fp64 tensor cores; equal to the fp64 reference to accumulation-order rounding; deterministic."""
+    from rtucker_b200 import ops
+    g = torch.Generator().manual_seed(n + ra + 11)
+    A = torch.randn(n, ra, generator=g)
+    Bm = torch.randn(n, rb, generator=g) + 0.5
+    ref = A.double().T @ Bm.double()
+    out = ops.gram(A.to(cuda_device), Bm.to(cuda_device), precise=True)
+    assert float((out.cpu() - ref).abs().max()) <= 1e-13 * float(ref.abs().max()) * max(1.0, n ** 0.5)
+    assert torch.equal(out, ops.gram(A.to(cuda_device), Bm.to(cuda_device), precise=True))
+
+
 @pytest.mark.parametrize("n,rc,rks", [(1000, 20, [20]), (4097, 200, [200, 200, 200]), (130, 10, [10, 10]), (22, 10, [])])
 def test_apply(cuda_device, n, rc, rks):
     from rtucker_b200 import ops
