@@ -465,6 +465,8 @@ def main():
         "metric": "train triples/s (1-N fwd+bwd+RSGD step), WN18RR shape", "value": value, "unit": "triples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "dtype_note": "fused score kernel: fp16 tensor-core operands scaled by powers of two (11 significant bits), fp32 "
+                      "accumulation; tall-skinny passes fp32; N-independent stage fp64",
         "config": config_dict(w, args, "entity-sharded over %d GPU(s)" % world),
         "queries_per_s": BATCH * args.steps / (ms * 1e-3),
         "eval_queries_per_s": eval_qps,

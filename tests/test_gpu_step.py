@@ -157,8 +157,8 @@ def test_step_parity_tcgen05_variant(cuda_device, variant, sym, beta):
         assert float((pr(x_dev) - pr(x_ref)).norm() / pr(x_ref).norm()) < 2e-3
 
 
-@pytest.mark.parametrize("sym,beta", [(False, 0.8), (True, None)])
-def test_cuda_graph_replay_is_bitwise_identical_to_eager(cuda_device, sym, beta):
+@pytest.mark.parametrize("sym,beta,variant", [(False, 0.8, 0), (True, None, 0), (False, 0.8, 2), (True, 0.8, 2)])
+def test_cuda_graph_replay_is_bitwise_identical_to_eager(cuda_device, sym, beta, variant):
     """The optimiser front end captures fit() and step() in CUDA graphs after the first eager step; the
     kernels are deterministic, so the graphed trajectory must equal the eager one bit for bit."""
     from rtucker_b200 import asymmetric, symmetric
@@ -177,8 +177,8 @@ def test_cuda_graph_replay_is_bitwise_identical_to_eager(cuda_device, sym, beta)
         model.to(dev)
         params = [model.core, model.E.weight, model.R.weight] if sym else \
             [model.core, model.S.weight, model.R.weight, model.O.weight]
-        opt = (mod.RSGDwithMomentum(params, rank, 50.0, beta, use_graphs=use_graphs) if beta is not None
-               else mod.RGD(params, rank, 50.0, use_graphs=use_graphs))
+        opt = (mod.RSGDwithMomentum(params, rank, 50.0, beta, use_graphs=use_graphs, score_variant=variant)
+               if beta is not None else mod.RGD(params, rank, 50.0, use_graphs=use_graphs, score_variant=variant))
         g = torch.Generator().manual_seed(9)
         out = []
         for it in range(6):
