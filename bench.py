@@ -366,7 +366,14 @@ def main():
         fd, od, xd = dev_batches[0]
         O_fac = model.E.weight.data if w["sym"] else model.O.weight.data
         B_, r2_ = BATCH, w["rank"][2]
-        qq = torch.randn(B_, r2_, device=dev) * 4.0 * (N / r2_) ** 0.5      # logits ~ N(0, 4^2) on orthonormal rows
+        # the query rows of a real batch at the current (trained-for-a-few-steps) point, exactly what the step feeds
+        # the kernel: q = core x1 R[rel] x2 S[sub]
+        S_fac = model.E.weight.data if w["sym"] else model.S.weight.data
+        r_rows = _ops.gather_rows(model.R.weight.data, fd[:, 1].contiguous())
+        s_rows = _ops.gather_rows(S_fac, fd[:, 0].contiguous(), n_begin)
+        if world > 1:
+            torch.distributed.all_reduce(s_rows)
+        qq = _ops.query_fwd(model.core.data, r_rows, s_rows)
         outs = (torch.empty(1, dtype=torch.float64, device=dev), torch.empty(B_, r2_, device=dev),
                 torch.empty_like(O_fac))
         v = args.variant
@@ -451,8 +458,11 @@ def main():
                     "frac": score_timing["large"]["flops"] / (score_timing["large"]["kernel_ms"] * 1e-3) / 1e12 / peak_tf,
                     "unit": "TFLOP/s", "algorithmic_flops_per_launch": score_timing["large"]["flops"]}),
                 "timing_note": "ms_per_launch = the fused kernel alone (kernel_ms: %d back-to-back launches between CUDA "
-                               "events); op_ms adds its operand packing and H-reduction launches; in-step stage time "
-                               "is stage_ms.score_bce_fwd_bwd" % (score_timing["launches_timed"] if score_timing else 0)}
+                               "events, on the query rows of a real batch at the current point); op_ms adds its operand "
+                               "packing and H-reduction launches; in-step stage time is stage_ms.score_bce_fwd_bwd. The "
+                               "epilogue has a warp-uniform short path for logits in (-27.7, 16.6): a launch on inputs with "
+                               "many saturated logits is up to 1.6x slower (tools/zdist.py)"
+                               % (score_timing["launches_timed"] if score_timing else 0)}
 
     cpu = None
     if args.cpu_steps > 0 and world == 1:
