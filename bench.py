@@ -162,7 +162,8 @@ def run_reference(args):
         return
     w = WORKLOADS[args.workload]
     graph = synth_graph(w)
-    tps, sps, cores = cpu_reference_steps(w, graph, args.steps, args.warmup)
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it can get
+    tps, sps, cores = cpu_reference_steps(w, graph, args.steps, args.warmup, threads=os.cpu_count())
     line = {
         "impl": "reference", "metric": "train triples/s (1-N fwd+bwd+RSGD step), WN18RR shape",
         "value": tps, "unit": "triples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -221,11 +222,21 @@ def main():
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keeps NCCL's version banner off stdout: rank 0 prints ONE JSON line
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
+        # NCCL prints its version banner on stdout when the communicator is created; rank 0 must print ONE JSON line,
+        # so stdout points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            group = dist.group.WORLD
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     from rtucker_b200 import asymmetric, lib, symmetric
     from rtucker_b200.engine import SparseTargets
@@ -466,7 +477,7 @@ def main():
 
     cpu = None
     if args.cpu_steps > 0 and world == 1:
-        tps, sps, cores = cpu_reference_steps(w, graph, args.cpu_steps, 1)
+        tps, sps, cores = cpu_reference_steps(w, graph, args.cpu_steps, 1, threads=os.cpu_count())
         cpu = {"value": tps, "unit": "triples/s", "cores": cores, "kind": "port",
                "sample": f"{args.cpu_steps} full train steps of B={BATCH} after 1 warm-up (oracle/reference_step.py: "
                          f"the reference's autodiff-through-rank-2r step), {sps:.3f} s/step; dense targets built outside the timed region"}
