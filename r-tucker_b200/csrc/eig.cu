@@ -63,25 +63,30 @@ __device__ __forceinline__ int pair_index(int bi, int bj, int i) {  // i in [0, 
 }
 
 // Rotation for the pivot with diagonal difference d = a_qq - a_pp and off-diagonal a = a_pq (fp32).  The ANGLE
-// is evaluated in fp32 (MUFU + FFMA, a short dependent chain); (c, s) is then re-normalised in fp64 so the
-// rotation is orthogonal to ~1e-15.  An fp32-accurate angle leaves a residual of ~1e-7 |a_pq| instead of an
-// exact zero, which only replaces the last quadratic step of the Jacobi iteration by one more sweep.
-__device__ __forceinline__ void rotation(float d, float a, double& c, double& s) {
-  c = 1.0;
-  s = 0.0;
+// is evaluated in fp32 (MUFU + FFMA, a short dependent chain) and steers the fp32 tile at once; a second warp
+// re-normalises (c, s) in fp64 one round later (a dependent fp64 operation costs ~80 cycles here), so the rotation
+// that is accumulated into Q is orthogonal to ~1e-15.  An fp32-accurate angle leaves a residual of ~1e-7 |a_pq|
+// instead of an exact zero, which only replaces the last quadratic step of the Jacobi iteration by one more sweep.
+__device__ __forceinline__ void rotation(float d, float a, float& c, float& s) {
+  c = 1.0f;
+  s = 0.0f;
   if (a * a > 1e-34f) {   // entries are scaled to <= 1: keeps the fp32 chain inside float range
     // tan(2 theta) = 2 a / d:  cos(2 theta) = |d| / h,  h = sqrt(d^2 + 4 a^2)
     const float x = fmaf(d, d, 4.0f * a * a);
     const float rh = rsqrtf(x);
     const float y = fmaf(0.5f * fabsf(d), rh, 0.5f);       // cos^2(theta) in [0.5, 1]
     const float ry = rsqrtf(y);
-    const double c0 = (double)(y * ry);
-    const double s0 = (double)((d >= 0.0f ? a : -a) * rh * ry);   // sin(theta) = sin(2 theta) / (2 cos(theta))
-    const double e = fma(c0, c0, fma(s0, s0, -1.0));       // c0^2 + s0^2 - 1 ~ 1e-7
-    const double f = fma(e, fma(e, 0.375, -0.5), 1.0);     // (1 + e)^(-1/2) to O(e^3)
-    c = c0 * f;
-    s = s0 * f;
+    c = y * ry;
+    s = (d >= 0.0f ? a : -a) * rh * ry;                     // sin(theta) = sin(2 theta) / (2 cos(theta))
   }
+}
+// (c0, s0) in fp32 -> the same rotation with c^2 + s^2 = 1 to ~1e-15 (fp64), off the critical path of the visit
+__device__ __forceinline__ void renormalise(float c0f, float s0f, double& c, double& s) {
+  const double c0 = (double)c0f, s0 = (double)s0f;
+  const double e = fma(c0, c0, fma(s0, s0, -1.0));       // c0^2 + s0^2 - 1 ~ 1e-7
+  const double f = fma(e, fma(e, 0.375, -0.5), 1.0);     // (1 + e)^(-1/2) to O(e^3)
+  c = c0 * f;
+  s = s0 * f;
 }
 
 __device__ __forceinline__ void cp_async16_d(double* dst_smem, const double* src) {
@@ -124,128 +129,159 @@ __device__ __forceinline__ void warp_mm32(const double* As, const double* Bs, do
 // differences keep their accuracy); only the accumulated rotation Q and the (c, s) pairs are fp64.
 // Phase B re-derives every tile, including the pair's own, as Q_k^T A_kl Q_l in fp64, so the
 // transformation applied to the matrix is an exact orthogonal similarity whatever the angles are.
-constexpr int ELDF = EP + 1;
-struct VisitSmem {
-  float* S[2];    // [EP][ELDF] steering tile, double buffered: round r reads S[r&1], writes S[(r+1)&1]
-  double* Q;      // [EP][ELD] accumulated rotations (fp64)
-  double* cs;     // [2][EB][2]  (c, s) of the rotations, double buffered over inner rounds
-  float* csf;     // [2][EB][2]  fp32 copies
-  int* pq;        // [2][EB][2]  (p, q)
-  int* pid;       // [2][EP]     pair id of every tile index in that round
-};
+constexpr int ELDF = 48;   // row stride = 16 banks: the 2 x 16 blocks a warp touches per access are conflict free
+// Rotation tables live in THREE slots (round r uses slot r % 3): round r + 1 is being written by warp 0 while
+// round r steers the tile and round r - 1 is still being accumulated into Q.  WHICH indices pair k of a round
+// rotates is never stored: pair_of / slot_of derive it from the round number with a few integer operations
+// (a table in shared memory costs more load bandwidth than the rotations themselves).
+constexpr int kSlots = 3;
+// Shared-memory map of a visit (inside the phase-B tile regions, idle during phase A):
+//   Q fp64 [EP][ELD] | cs fp64 [3][EB][2] | S fp32 2 x [EP][ELDF] (round r reads S[r&1], writes S[(r+1)&1]) | csf fp32 [3][EB][2]
+// The accessors name the dynamic shared array directly: a pointer that travels through a struct or a call loses its
+// address space, and every access becomes a generic load with 64-bit address arithmetic.
+__device__ __forceinline__ double* vis_Q() { extern __shared__ __align__(16) double esm[]; return esm; }
+__device__ __forceinline__ double2* vis_cs() { return reinterpret_cast<double2*>(vis_Q() + EP * ELD); }
+__device__ __forceinline__ float* vis_S(int buf) { return reinterpret_cast<float*>(vis_cs() + kSlots * EB) + buf * (EP * ELDF); }
+__device__ __forceinline__ float2* vis_csf() { return reinterpret_cast<float2*>(vis_S(0) + 2 * EP * ELDF); }
 
-__device__ __forceinline__ void pair_of(int t, int tid, bool intra_pass, int& p, int& q) {
-  if (intra_pass) {
-    rr_pair(EB, t, tid % (EB / 2), p, q);
-    const int o = (tid < EB / 2) ? 0 : EB;
+// Pairing of an inner round t.  INTRA: round-robin tournament inside each of the two blocks (EB - 1 rounds, pairs
+// 0..EB/2-1 in the first block, the rest in the second); otherwise round t pairs index k with EB + (k + t) % EB.
+// The kind of round is a template parameter: 24 of 25 visits only have the second kind, whose index arithmetic is two
+// integer instructions, and the visit is bound by the instruction count of its slowest warp.
+template <bool INTRA>
+__device__ __forceinline__ void pair_of(int t, int k, int& p, int& q) {
+  if (INTRA) {
+    rr_pair(EB, t, k % (EB / 2), p, q);
+    const int o = (k < EB / 2) ? 0 : EB;
     p += o; q += o;
   } else {
-    p = tid;
-    q = EB + (tid + t) % EB;
+    p = k;
+    q = EB + ((k + t) & (EB - 1));
   }
 }
-
-__device__ __forceinline__ void publish(const VisitSmem& m, int nb, int tid, int p, int q, double c, double s) {
-  m.pq[(nb * EB + tid) * 2 + 0] = p; m.pq[(nb * EB + tid) * 2 + 1] = q;
-  m.pid[nb * EP + p] = tid; m.pid[nb * EP + q] = tid;
-  m.cs[(nb * EB + tid) * 2 + 0] = c; m.cs[(nb * EB + tid) * 2 + 1] = s;
-  m.csf[(nb * EB + tid) * 2 + 0] = (float)c; m.csf[(nb * EB + tid) * 2 + 1] = (float)s;
+// the pair of round t that contains tile index x (inverse of pair_of)
+template <bool INTRA>
+__device__ __forceinline__ int slot_of(int t, int x) {
+  if (INTRA) {
+    constexpr int m = EB - 1;
+    const int y = x & (EB - 1), o = (x >= EB) ? EB / 2 : 0;
+    if (y == m) return o;
+    const int d = (y - t % m + m) % m;     // y = (t + k) % m  ->  k = d;   y = (t - k) % m  ->  k = m - d
+    return o + (d <= EB / 2 - 1 ? d : m - d);
+  }
+  return x < EB ? x : ((x - t) & (EB - 1));
 }
 
 // rotations of the FIRST inner round, from the tile itself
-__device__ __forceinline__ void first_pairs(const VisitSmem& m, bool intra_pass) {
+template <bool INTRA>
+__device__ __forceinline__ void first_pairs() {
   const int tid = threadIdx.x;
   if (tid < EB) {
     int p, q;
-    pair_of(0, tid, intra_pass, p, q);
-    const float* S = m.S[0];
-    double c, s;
+    pair_of<INTRA>(0, tid, p, q);
+    const float* S = vis_S(0);
+    float c, s;
     rotation(S[q * ELDF + q] - S[p * ELDF + p], S[p * ELDF + q], c, s);
-    publish(m, 0, tid, p, q, c, s);
+    vis_csf()[tid] = make_float2(c, s);
   }
 }
 
-// Rotations of round r+1, computed by lanes 0..EB-1 of warp 0 WHILE the other warps apply round r:
-// the pivot entries of S_{r+1} = J_r^T S_r J_r are closed-form in S_r (read-only this round) and the
-// rotations of round r:  S'[i,j] = sum_{a in pair(i)} sum_{b in pair(j)} J[a,i] J[b,j] S[a,b].
-__device__ __forceinline__ void next_pairs(const VisitSmem& m, int buf, int t_next, bool intra_next) {
+// Rotations of round r+1 (round tn of kind INTRA_N), computed by lanes 0..EB-1 of warp 0 WHILE the other warps apply
+// round r (round t of kind INTRA): the pivot entries of S_{r+1} = J_r^T S_r J_r are closed-form in S_r (read-only this
+// round) and the rotations of round r:  S'[i,j] = sum_{a in pair(i)} sum_{b in pair(j)} J[a,i] J[b,j] S[a,b].
+template <bool INTRA, bool INTRA_N>
+__device__ __forceinline__ void next_pairs(int buf, int slot, int slot_next, int t, int tn) {
   const int tid = threadIdx.x;
   if (tid < EB) {
-    int p, q;
-    pair_of(t_next, tid, intra_next, p, q);
-    const float* S = m.S[buf];
-    const float* cs = m.csf + buf * EB * 2;
-    const int* pq = m.pq + buf * EB * 2;
-    const int* pid = m.pid + buf * EP;
-    const int kp = pid[p], kq = pid[q];
-    const int a1 = pq[kp * 2], a2 = pq[kp * 2 + 1], b1 = pq[kq * 2], b2 = pq[kq * 2 + 1];
-    const float cp = cs[kp * 2], sp = cs[kp * 2 + 1], cq = cs[kq * 2], sq = cs[kq * 2 + 1];
+    int p, q, a1, a2, b1, b2;
+    pair_of<INTRA_N>(tn, tid, p, q);
+    const int kp = slot_of<INTRA>(t, p), kq = slot_of<INTRA>(t, q);
+    pair_of<INTRA>(t, kp, a1, a2);
+    pair_of<INTRA>(t, kq, b1, b2);
+    const float* S = vis_S(buf);
+    const float2 rp = vis_csf()[slot * EB + kp], rq = vis_csf()[slot * EB + kq];
+    const float saa1 = S[a1 * ELDF + a1], saa2 = S[a1 * ELDF + a2], saa3 = S[a2 * ELDF + a1], saa4 = S[a2 * ELDF + a2];
+    const float sbb1 = S[b1 * ELDF + b1], sbb2 = S[b1 * ELDF + b2], sbb3 = S[b2 * ELDF + b1], sbb4 = S[b2 * ELDF + b2];
+    const float sab1 = S[a1 * ELDF + b1], sab2 = S[a1 * ELDF + b2], sab3 = S[a2 * ELDF + b1], sab4 = S[a2 * ELDF + b2];
     // column p of J_r is wa1 e_a1 + wa2 e_a2, column q is wb1 e_b1 + wb2 e_b2
-    const float wa1 = (p == a1) ? cp : sp, wa2 = (p == a1) ? -sp : cp;
-    const float wb1 = (q == b1) ? cq : sq, wb2 = (q == b1) ? -sq : cq;
-    const float saa = wa1 * (wa1 * S[a1 * ELDF + a1] + wa2 * S[a1 * ELDF + a2]) +
-                      wa2 * (wa1 * S[a2 * ELDF + a1] + wa2 * S[a2 * ELDF + a2]);
-    const float sbb = wb1 * (wb1 * S[b1 * ELDF + b1] + wb2 * S[b1 * ELDF + b2]) +
-                      wb2 * (wb1 * S[b2 * ELDF + b1] + wb2 * S[b2 * ELDF + b2]);
-    const float sab = wa1 * (wb1 * S[a1 * ELDF + b1] + wb2 * S[a1 * ELDF + b2]) +
-                      wa2 * (wb1 * S[a2 * ELDF + b1] + wb2 * S[a2 * ELDF + b2]);
-    double c, s;
+    const float wa1 = (p == a1) ? rp.x : rp.y, wa2 = (p == a1) ? -rp.y : rp.x;
+    const float wb1 = (q == b1) ? rq.x : rq.y, wb2 = (q == b1) ? -rq.y : rq.x;
+    const float saa = wa1 * (wa1 * saa1 + wa2 * saa2) + wa2 * (wa1 * saa3 + wa2 * saa4);
+    const float sbb = wb1 * (wb1 * sbb1 + wb2 * sbb2) + wb2 * (wb1 * sbb3 + wb2 * sbb4);
+    const float sab = wa1 * (wb1 * sab1 + wb2 * sab2) + wa2 * (wb1 * sab3 + wb2 * sab4);
+    float c, s;
     rotation(sbb - saa, sab, c, s);
-    publish(m, buf ^ 1, tid, p, q, c, s);
+    vis_csf()[slot_next * EB + tid] = make_float2(c, s);
   }
 }
 
-// S[buf^1] <- R^T S[buf] R (fp32) and Q <- Q R (fp64) for the EB disjoint rotations of `buf`; executed by the
-// threads first_thread .. kEigThreads-1 (warp 0 is busy with the next rotations).  Every thread first LOADS
-// all of its work, then computes, then stores, so the independent chains overlap.
-__device__ __forceinline__ void apply_round(const VisitSmem& m, int buf, int first_thread) {
-  const double* __restrict__ cs = m.cs + buf * EB * 2;
-  const float* __restrict__ csf = m.csf + buf * EB * 2;
-  const int* __restrict__ pq = m.pq + buf * EB * 2;
-  const float* __restrict__ Si = m.S[buf];
-  float* __restrict__ So = m.S[buf ^ 1];
-  double* __restrict__ Q = m.Q;
-  const int nthr = kEigThreads - first_thread;
-  const int t0 = threadIdx.x - first_thread;
+// warp 1: fp64 re-normalisation of the rotations of `slot` (they steer the tile in fp32 meanwhile)
+__device__ __forceinline__ void renorm_round(int slot) {
+  const int l = threadIdx.x - 32;
+  if (l >= 0 && l < EB) {
+    const float2 r = vis_csf()[slot * EB + l];
+    double c, s;
+    renormalise(r.x, r.y, c, s);
+    vis_cs()[slot * EB + l] = make_double2(c, s);
+  }
+}
+
+// Threads kApplyFirst .. kEigThreads-1:  S[buf^1] <- R^T S[buf] R in fp32 for the EB disjoint rotations of round ts
+// (kind INTRA_S, tables in slot_s; DO_S = false: nothing), and Q <- Q R in fp64 for the rotations of round tq (kind
+// INTRA_Q, slot_q), which are one round older and already re-normalised (DO_Q = false: nothing).  Every thread first
+// LOADS all of its work, then computes, then stores, so the independent chains overlap.
+constexpr int kApplyFirst = 64;
+template <bool DO_S, bool INTRA_S, bool DO_Q, bool INTRA_Q>
+__device__ __forceinline__ void apply_round(int buf, int slot_s, int ts, int slot_q, int tq) {
+  const float* __restrict__ Si = vis_S(buf);
+  float* __restrict__ So = vis_S(buf ^ 1);
+  double* __restrict__ Q = vis_Q();
+  constexpr int nthr = kEigThreads - kApplyFirst;
+  const int t0 = threadIdx.x - kApplyFirst;
   if (t0 < 0) return;
-  constexpr int NB = 2, NQ = 3;
-  static_assert(EB * EB <= NB * (kEigThreads - 32) && EP * EB <= NQ * (kEigThreads - 32), "work split");
-  int p[NB], q[NB], u[NB], v[NB];
-  float ck[NB], sk[NB], cl[NB], sl[NB], m00[NB], m01[NB], m10[NB], m11[NB];
-  bool okb[NB];
+  constexpr int NB = DO_S ? (EB * EB + nthr - 1) / nthr : 0, NQ = DO_Q ? (EP * EB + nthr - 1) / nthr : 0;
+  const float2* __restrict__ csf = vis_csf() + slot_s * EB;
+  const double2* __restrict__ cs = vis_cs() + slot_q * EB;
+  int p[NB + 1], q[NB + 1], u[NB + 1], v[NB + 1];
+  float2 rk[NB + 1], rl[NB + 1];
+  float m00[NB + 1], m01[NB + 1], m10[NB + 1], m11[NB + 1];
+  bool okb[NB + 1];
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     const int blk = t0 + i * nthr;
     okb[i] = blk < EB * EB;
     const int k = okb[i] ? blk / EB : 0, l = okb[i] ? blk % EB : 0;
-    ck[i] = csf[k * 2]; sk[i] = csf[k * 2 + 1]; cl[i] = csf[l * 2]; sl[i] = csf[l * 2 + 1];
-    p[i] = pq[k * 2]; q[i] = pq[k * 2 + 1]; u[i] = pq[l * 2]; v[i] = pq[l * 2 + 1];
+    pair_of<INTRA_S>(ts, k, p[i], q[i]);
+    pair_of<INTRA_S>(ts, l, u[i], v[i]);
+    rk[i] = csf[k]; rl[i] = csf[l];
     m00[i] = Si[p[i] * ELDF + u[i]]; m01[i] = Si[p[i] * ELDF + v[i]];
     m10[i] = Si[q[i] * ELDF + u[i]]; m11[i] = Si[q[i] * ELDF + v[i]];
   }
-  int qr[NQ], qu_i[NQ], qv_i[NQ];
-  double qc[NQ], qs[NQ], qu[NQ], qv[NQ];
-  bool okq[NQ];
+  int qr[NQ + 1], qu_i[NQ + 1], qv_i[NQ + 1];
+  double2 qcs[NQ + 1];
+  double qu[NQ + 1], qv[NQ + 1];
+  bool okq[NQ + 1];
 #pragma unroll
   for (int i = 0; i < NQ; ++i) {
     const int it = t0 + i * nthr;
     okq[i] = it < EP * EB;
     qr[i] = okq[i] ? it / EB : 0;
     const int l = okq[i] ? it % EB : 0;
-    qc[i] = cs[l * 2]; qs[i] = cs[l * 2 + 1];
-    qu_i[i] = pq[l * 2]; qv_i[i] = pq[l * 2 + 1];
+    pair_of<INTRA_Q>(tq, l, qu_i[i], qv_i[i]);
+    qcs[i] = cs[l];
     qu[i] = Q[qr[i] * ELD + qu_i[i]]; qv[i] = Q[qr[i] * ELD + qv_i[i]];
   }
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
-    const float t00 = ck[i] * m00[i] - sk[i] * m10[i], t01 = ck[i] * m01[i] - sk[i] * m11[i];
-    const float t10 = sk[i] * m00[i] + ck[i] * m10[i], t11 = sk[i] * m01[i] + ck[i] * m11[i];
-    m00[i] = cl[i] * t00 - sl[i] * t01; m01[i] = sl[i] * t00 + cl[i] * t01;
-    m10[i] = cl[i] * t10 - sl[i] * t11; m11[i] = sl[i] * t10 + cl[i] * t11;
+    const float ck = rk[i].x, sk = rk[i].y, cl = rl[i].x, sl = rl[i].y;
+    const float t00 = ck * m00[i] - sk * m10[i], t01 = ck * m01[i] - sk * m11[i];
+    const float t10 = sk * m00[i] + ck * m10[i], t11 = sk * m01[i] + ck * m11[i];
+    m00[i] = cl * t00 - sl * t01; m01[i] = sl * t00 + cl * t01;
+    m10[i] = cl * t10 - sl * t11; m11[i] = sl * t10 + cl * t11;
   }
 #pragma unroll
   for (int i = 0; i < NQ; ++i) {
-    const double a = qc[i] * qu[i] - qs[i] * qv[i], bb = qs[i] * qu[i] + qc[i] * qv[i];
+    const double a = qcs[i].x * qu[i] - qcs[i].y * qv[i], bb = qcs[i].y * qu[i] + qcs[i].x * qv[i];
     qu[i] = a; qv[i] = bb;
   }
 #pragma unroll
@@ -265,41 +301,69 @@ __device__ __forceinline__ void apply_round(const VisitSmem& m, int buf, int fir
 // pairs INSIDE each of the two blocks, then one pass over the EB*EB cross pairs, as rounds of EB
 // disjoint rotations.  Over a sweep every index pair of the matrix is rotated exactly once: this is
 // cyclic Jacobi whose rotations are applied to the matrix tile-wise in phase B.
-// Pipeline, ONE barrier per inner round:  warp 0 derives the rotations of round r+1 from S_r and the
-// rotations of round r, while warps 1.. apply round r (S_r -> S_{r+1} in fp32, Q <- Q R_r in fp64).
 #ifdef RT_EIG_PROF
 __device__ long long g_vprof[8];
 #endif
-__device__ void cta_visit(const VisitSmem& m, bool intra) {
+// Pipeline, ONE barrier per inner round r:
+//   warp 0  derives the fp32 rotations of round r+1 from S_r and the rotations of round r (slot (r+1) % 3),
+//   warp 1  re-normalises the rotations of round r in fp64 (slot r % 3),
+//   warps 2.. apply round r to the steering tile (S_r -> S_{r+1}, fp32) and round r-1 to Q (fp64).
+// One more Q-only step after the last round.
+// one inner round: the three roles, then the barrier
+template <bool INTRA, bool INTRA_N, bool HAS_NEXT, bool DO_Q, bool INTRA_Q>
+__device__ __forceinline__ void visit_round(int r, int& slot, int t, int tn, int tq) {
   const int tid = threadIdx.x;
-  for (int e = tid; e < EP * EP; e += kEigThreads) m.Q[(e / EP) * ELD + (e % EP)] = (e / EP == e % EP) ? 1.0 : 0.0;
-  const int n_intra = intra ? EB - 1 : 0;
-  const int total = n_intra + EB;
-  first_pairs(m, n_intra > 0);
-  __syncthreads();
-  for (int r = 0; r < total; ++r) {
-    const int buf = r & 1;
+  const int slot_next = slot == kSlots - 1 ? 0 : slot + 1;
+  const int slot_prev = slot == 0 ? kSlots - 1 : slot - 1;
 #ifdef RT_EIG_PROF
-    const long long v0 = clock64();
+  const long long c0 = clock64();
 #endif
-    if (tid < 32) {
-      if (r + 1 < total) {
-        const int rn = r + 1;
-        next_pairs(m, buf, rn < n_intra ? rn : rn - n_intra, rn < n_intra);
-      }
-    } else {
-      apply_round(m, buf, 32);
-    }
-#ifdef RT_EIG_PROF
-    const long long v1 = clock64();
-#endif
-    __syncthreads();
-#ifdef RT_EIG_PROF
-    const long long v2 = clock64();
-    if (tid == 0) { g_vprof[0] += v1 - v0; g_vprof[1] += v2 - v1; g_vprof[4] += 1; }
-    if (tid == 32) { g_vprof[2] += v1 - v0; g_vprof[3] += v2 - v1; }
-#endif
+  if (tid < 32) {
+    if (HAS_NEXT) next_pairs<INTRA, INTRA_N>(r & 1, slot, slot_next, t, tn);
+  } else if (tid < kApplyFirst) {
+    renorm_round(slot);
+  } else {
+    apply_round<true, INTRA, DO_Q, INTRA_Q>(r & 1, slot, t, slot_prev, tq);
   }
+#ifdef RT_EIG_PROF
+  const long long c1 = clock64();
+#endif
+  __syncthreads();
+#ifdef RT_EIG_PROF
+  if (blockIdx.x == 5 && (tid == 0 || tid == 32 || tid == 64)) {
+    const long long c2 = clock64();
+    atomicAdd((unsigned long long*)&g_vprof[(tid >> 5) * 2], (unsigned long long)(c1 - c0));
+    atomicAdd((unsigned long long*)&g_vprof[(tid >> 5) * 2 + 1], (unsigned long long)(c2 - c1));
+    if (tid == 0) atomicAdd((unsigned long long*)&g_vprof[6], 1ull);
+  }
+#endif
+  slot = slot_next;
+}
+
+__device__ __forceinline__ void cta_visit(bool intra) {
+  const int tid = threadIdx.x;
+  for (int e = tid; e < EP * EP; e += kEigThreads) vis_Q()[(e / EP) * ELD + (e % EP)] = (e / EP == e % EP) ? 1.0 : 0.0;
+  int slot = 0;                                      // r % 3
+  int r = 0;
+  if (intra) {
+    // EB - 1 tournament rounds inside the two blocks, then the EB cross rounds
+    first_pairs<true>();
+    __syncthreads();
+    visit_round<true, true, true, false, true>(r, slot, 0, 1, 0); ++r;
+    for (; r < EB - 2; ++r) visit_round<true, true, true, true, true>(r, slot, r, r + 1, r - 1);
+    visit_round<true, false, true, true, true>(r, slot, r, 0, r - 1); ++r;          // r = EB - 2: next is cross round 0
+    visit_round<false, false, true, true, true>(r, slot, 0, 1, r - 1); ++r;         // cross round 0, Q still has an intra round
+    for (int t = 1; t < EB - 1; ++t, ++r) visit_round<false, false, true, true, false>(r, slot, t, t + 1, t - 1);
+  } else {
+    first_pairs<false>();
+    __syncthreads();
+    visit_round<false, false, true, false, false>(r, slot, 0, 1, 0); ++r;
+    for (int t = 1; t < EB - 1; ++t, ++r) visit_round<false, false, true, true, false>(r, slot, t, t + 1, t - 1);
+  }
+  visit_round<false, false, false, true, false>(r, slot, EB - 1, 0, EB - 2);
+  // the rotations of the last round are re-normalised by now: accumulate them
+  apply_round<false, false, true, false>(0, 0, 0, slot == 0 ? kSlots - 1 : slot - 1, EB - 1);
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(kEigThreads, 1)
@@ -382,15 +446,8 @@ eig_block_jacobi_kernel(EigBatch batch) {
           rr_pair(P.nb, round, item, bi, bj);
           double off = 0.0;
           const bool intra = (round == 0);
-          // shared-memory map of a visit (inside the phase-B tile regions, idle now):
-          //   Q fp64 [EP][ELD] | cs fp64 [2][EB][2] | S fp32 2 x [EP][ELDF] | csf fp32 [2][EB][2] | pq, pid int
-          double* Qm = esm;
-          double* csd = esm + EP * ELD;
-          float* Sf0 = reinterpret_cast<float*>(csd + 4 * EB);
-          float* Sf1 = Sf0 + EP * ELDF;
-          float* csf = Sf1 + EP * ELDF;
-          int* pqi = reinterpret_cast<int*>(csf + 4 * EB);
-          VisitSmem vm{{Sf0, Sf1}, Qm, csd, csf, pqi, pqi + 4 * EB};
+          float* Sf0 = vis_S(0);
+          double* Qm = vis_Q();
           double dsum = 0.0;
 #ifdef RT_EIG_PROF
           long long q0 = clock64(), q1;
@@ -434,7 +491,7 @@ eig_block_jacobi_kernel(EigBatch batch) {
 #ifdef RT_EIG_PROF
             q1 = clock64(); pLoad += q1 - q0; q0 = q1;
 #endif
-            cta_visit(vm, intra);
+            cta_visit(intra);
 #ifdef RT_EIG_PROF
             q1 = clock64(); pVisit += q1 - q0; q0 = q1; ++pN;
 #endif
@@ -548,8 +605,9 @@ eig_block_jacobi_kernel(EigBatch batch) {
 
 #ifdef RT_EIG_PROF
   if (threadIdx.x == 0 && blockIdx.x == 5)
-    printf("visit rounds %lld (all CTAs): warp0 next_pairs %lld wait %lld | warp1 apply %lld wait %lld (cycles per round)\n", g_vprof[4],
-           g_vprof[0] / max(1ll, g_vprof[4]), g_vprof[1] / max(1ll, g_vprof[4]), g_vprof[2] / max(1ll, g_vprof[4]), g_vprof[3] / max(1ll, g_vprof[4]));
+    printf("visit rounds %lld: warp0 next_pairs %lld wait %lld | warp1 renorm %lld wait %lld | apply %lld wait %lld (cycles per round)\n",
+           g_vprof[6], g_vprof[0] / max(1ll, g_vprof[6]), g_vprof[1] / max(1ll, g_vprof[6]), g_vprof[2] / max(1ll, g_vprof[6]),
+           g_vprof[3] / max(1ll, g_vprof[6]), g_vprof[4] / max(1ll, g_vprof[6]), g_vprof[5] / max(1ll, g_vprof[6]));
   if (threadIdx.x == 0 && blockIdx.x == 5)
     printf("eig cta %d: phaseA %lld = load %lld visit %lld store %lld (visits %lld) sync1 %lld phaseB %lld sync2 %lld\n",
            blockIdx.x, tA, pLoad, pVisit, pStore, pN, tS1, tB, tS2);
