@@ -599,6 +599,9 @@ eig_block_jacobi_kernel(EigBatch batch) {
       // The HOSVD passes 1e-10: the convergence is quadratic, what is left is ~1e-9 ||A|| -- far below the fp32
       // rounding of the factors the eigenvectors are multiplied into (V stays orthogonal to 1e-15 regardless: it
       // is a product of renormalised rotations).
+#ifdef RT_EIG_PROF
+      if (gtid == 0) printf("eig problem %d (n=%d) sweep %d: off-diagonal mass seen / ||A||^2 = %.3e\n", pi, P.n, sweep, off2 / n2);
+#endif
       if (off2 <= batch.stop * n2) done[pi] = true;
     }
   }

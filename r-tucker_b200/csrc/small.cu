@@ -11,6 +11,14 @@
 // Everything here costs O(poly(r)) and is replicated on every GPU of an entity-sharded run.
 #include "small_kernels.cuh"
 
+#include <cstdlib>
+// Stop criterion of the HOSVD eigenproblems (off-diagonal mass SEEN in a sweep, relative to ||A||_F^2).
+// RT_HOSVD_STOP overrides it for experiments.
+static double hosvd_stop() {
+  static const double v = [] { const char* e = std::getenv("RT_HOSVD_STOP"); return e ? std::atof(e) : 1e-10; }();
+  return v;
+}
+
 namespace rt {
 int eig_batch(int count, const double* const* A, const int* n, double* const* w, double* const* V,
               void* const* ws, cudaStream_t s, double stop);
@@ -483,7 +491,7 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
       Ain[i] = Nn[i]; nn[i] = 2 * d[i]; wv[i] = c.p(c.L.Wv[i]); Vv[i] = c.p(c.L.Vf[i]);
       ews[i] = c.base + c.L.eig[i];
     }
-    if ((rc = rt::eig_batch(nm, Ain, nn, wv, Vv, ews, s, 1e-10))) return rc;   // subspace accuracy ~1e-9: see eig.cu
+    if ((rc = rt::eig_batch(nm, Ain, nn, wv, Vv, ews, s, hosvd_stop()))) return rc;   // see eig.cu
   }
   // Y_i = V_i[:, :r_i]  (2r_i x r_i, row stride 2r_i);  W_i = Y_i^T = [Y_ia^T | Y_ib^T]
   const double* Y[3] = {c.p(c.L.Vf[0]), c.p(c.L.Vf[1]), c.p(c.L.Vf[sym ? 1 : 2])};
