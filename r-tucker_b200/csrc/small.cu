@@ -213,7 +213,7 @@ struct Ctx {
         rt::set_error("small stage: cannot raise shared memory to %zu", smem); return 1; }
       configured = smem;
     }
-    spd_blocked_kernel<<<count, 1024, smem, s>>>(b); ++rt::g_launches;
+    spd_blocked_kernel<<<count, SPD_THREADS, smem, s>>>(b); ++rt::g_launches;
     return 0;
   }
 };

@@ -284,14 +284,17 @@ struct SpdBatch { SpdProblem p[3]; };
 __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }
 
 // Blocked variant (what the small stage launches): same contract and the same zero-pivot semantics as
-// spd_factor_kernel below, but ~10x fewer block barriers.  Four threads per matrix row.
+// spd_factor_kernel below, but ~10x fewer block barriers.  Two threads per matrix row.
 //   Cholesky, left looking in blocks of 8 columns: (1) every row subtracts the contribution of all earlier
 //   columns from its 8 block entries (the 8 "pivot rows" are broadcast reads), (2) one thread factors the 8x8
 //   diagonal block, (3) every row below solves its 8 entries against that block.
 //   Inverse, in blocks of 8 rows: the rows of L are staged, then thread group j produces column j of the 8 new rows
 //   of L^-1 from its own (already inverted) column above.
 constexpr int SPD_NB = 8;
-__global__ void __launch_bounds__(1024, 1)
+// 512 threads, two per matrix row (n <= 256): 128 registers per thread, so that the 8 x 8 diagonal block really stays
+// in the registers of the thread that factors it (at 1024 threads x 64 registers it spilled to local memory)
+constexpr int SPD_THREADS = 512, SPD_TPR = 2;
+__global__ void __launch_bounds__(SPD_THREADS, 1)
 spd_blocked_kernel(SpdBatch batch) {
   extern __shared__ double sm[];
   const SpdProblem P = batch.p[blockIdx.x];
@@ -301,9 +304,9 @@ spd_blocked_kernel(SpdBatch batch) {
   double* stage = sm + n * (n + 1) / 2;         // [SPD_NB][n] staged rows of L
   __shared__ double D[SPD_NB][SPD_NB + 1], invd[SPD_NB];
   __shared__ double dinv_all[256];              // 1 / L[i][i] (0 for a zero pivot): the inverse never divides
-  __shared__ double s_maxd, s_inv_maxd, s_rsqrt_maxd;
+  __shared__ double s_maxd, s_scale[4];
   const int tid = threadIdx.x, nt = blockDim.x;
-  const int row = tid >> 2, sub = tid & 3;
+  const int row = tid / SPD_TPR, sub = tid % SPD_TPR;
   for (int e = tid; e < n * (n + 1) / 2; e += nt) {
     int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
     while (i * (i + 1) / 2 > e) --i;
@@ -318,10 +321,22 @@ spd_blocked_kernel(SpdBatch batch) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (tid == 0) {
-      s_maxd = m;
-      s_inv_maxd = m > 0.0 ? 1.0 / m : 1.0;
-      s_rsqrt_maxd = m > 0.0 ? 1.0 / sqrt(m) : 1.0;
+      // the factorisation runs on G / 4^k with the largest diagonal entry in [0.25, 1): exact scaling (powers of two
+      // in L, L^-1 and G^-1 as well), pivots inside the fp32 range for the reciprocal / rsqrt seeds, and no scaling
+      // operations on the serial pivot chain
+      int ex = 0;
+      if (m > 0.0) { frexp(m, &ex); ex += ex & 1; }
+      s_maxd = ldexp(m, -ex);
+      s_scale[0] = ldexp(1.0, -ex);        // G      -> scaled
+      s_scale[1] = ldexp(1.0, ex / 2);     // L      <- scaled
+      s_scale[2] = ldexp(1.0, -(ex / 2));  // L^-1   <- scaled
+      s_scale[3] = ldexp(1.0, -ex);        // G^-1   <- scaled
     }
+  }
+  __syncthreads();
+  {
+    const double sc = s_scale[0];
+    for (int e = tid; e < n * (n + 1) / 2; e += nt) Lp[e] *= sc;
   }
   __syncthreads();
   const double tol = 1e-12 * s_maxd;
@@ -343,7 +358,7 @@ spd_blocked_kernel(SpdBatch batch) {
         const double* Lc[SPD_NB];
 #pragma unroll
         for (int c = 0; c < SPD_NB; ++c) Lc[c] = Lp + pk(kb + (c < nbk ? c : 0), 0);
-        for (int k = sub; k < kb; k += 4) {
+        for (int k = sub; k < kb; k += SPD_TPR) {
           const double li = Li[k];
 #pragma unroll
           for (int c = 0; c < SPD_NB; ++c) acc[c] = fma(li, Lc[c][k], acc[c]);
@@ -351,8 +366,8 @@ spd_blocked_kernel(SpdBatch batch) {
       }
 #pragma unroll
       for (int c = 0; c < SPD_NB; ++c) {
-        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
-        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+#pragma unroll
+        for (int o = 1; o < SPD_TPR; o <<= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
       }
       if (row < n && row >= kb && sub == 0) {
 #pragma unroll
@@ -371,30 +386,44 @@ spd_blocked_kernel(SpdBatch batch) {
 #pragma unroll
         for (int c = 0; c < SPD_NB; ++c)
           if (c <= r) d[r][c] = (r < nbk) ? Lp[pk(kb + r, kb + c)] : (r == c ? 1.0 : 0.0);
+      // A dependent fp64 operation costs 50-85 cycles here and this thread is the serial part of the whole kernel, so
+      // the chain from one pivot to the next is kept minimal: the block is eliminated in L D L^T form -- next pivots
+      // only need 1 / d_cc (fp32 seed + two Newton steps) and ONE fma per entry, the products a_rc a_c2c do not wait
+      // for it -- and the square roots that turn it into the Cholesky factor are eight independent chains afterwards.
+      double rinv[SPD_NB];
 #pragma unroll
       for (int c = 0; c < SPD_NB; ++c) {
-        // 1/sqrt and sqrt of the pivot without the (slow, serial) fp64 sqrt and division routines: fp32 seed on the
-        // pivot scaled into (1e-12, 1], three Newton steps (22 -> 44 -> 88 -> full bits), one Heron correction
-        double piv = 0.0, inv = 0.0;
+        double ri = 0.0;
         if (d[c][c] > tol) {
-          const double t = d[c][c] * s_inv_maxd;
-          double y = (double)rsqrtf((float)t);
+          const double dc = d[c][c];
+          double y = (double)__frcp_rn((float)dc);
+          y = fma(y, fma(-dc, y, 1.0), y);
+          ri = fma(y, fma(-dc, y, 1.0), y);
+        }
+        rinv[c] = ri;                                     // 0 for a zero pivot: its column drops out of the updates
 #pragma unroll
-          for (int it = 0; it < 3; ++it) y = y * fma(-0.5 * t, y * y, 1.5);
-          inv = y * s_rsqrt_maxd;
-          piv = d[c][c] * inv;
-          piv = fma(0.5 * inv, fma(-piv, piv, d[c][c]), piv);
-          inv = fma(inv, fma(-piv, inv, 1.0), inv);          // 1 / piv to the last bits
+        for (int r = c + 1; r < SPD_NB; ++r)
+#pragma unroll
+          for (int c2 = c + 1; c2 <= r; ++c2) d[r][c2] = fma(-(d[r][c] * d[c2][c]), ri, d[r][c2]);
+      }
+#pragma unroll
+      for (int c = 0; c < SPD_NB; ++c) {
+        // sqrt(d_cc) and its inverse: fp32 seed, Newton steps (22 -> 44 -> 88 bits), one Heron correction
+        double piv = 0.0, inv = 0.0;
+        if (rinv[c] != 0.0) {
+          const double dc = d[c][c];
+          double y = (double)rsqrtf((float)dc);
+#pragma unroll
+          for (int it = 0; it < 2; ++it) y = y * fma(-0.5 * dc, y * y, 1.5);
+          piv = dc * y;
+          piv = fma(0.5 * y, fma(-piv, piv, dc), piv);
+          inv = fma(y, fma(-piv, y, 1.0), y);             // 1 / piv to the last bits
         }
         d[c][c] = piv;
         invd[c] = inv;
         if (c < nbk) dinv_all[kb + c] = inv;
 #pragma unroll
         for (int r = c + 1; r < SPD_NB; ++r) d[r][c] *= inv;
-#pragma unroll
-        for (int r = c + 1; r < SPD_NB; ++r)
-#pragma unroll
-          for (int c2 = c + 1; c2 <= r; ++c2) d[r][c2] = fma(-d[r][c], d[c2][c], d[r][c2]);
       }
 #pragma unroll
       for (int r = 0; r < SPD_NB; ++r)
@@ -432,7 +461,7 @@ spd_blocked_kernel(SpdBatch batch) {
   if (P.L) {
     for (int e = tid; e < n * n; e += nt) {
       const int i = e / n, j = e - i * n;
-      P.L[e] = (j <= i) ? Lp[pk(i, j)] : 0.0;
+      P.L[e] = (j <= i) ? Lp[pk(i, j)] * s_scale[1] : 0.0;
     }
   }
   if (!P.Linv && !P.Ginv) return;
@@ -445,12 +474,12 @@ spd_blocked_kernel(SpdBatch batch) {
       stage[e] = (k <= ib + r) ? Lp[pk(ib + r, k)] : 0.0;
     }
     __syncthreads();
-    const int j = row;                                   // column owned by this group of four threads
+    const int j = row;                                   // column owned by this pair of threads
     double acc[SPD_NB];
 #pragma unroll
     for (int r = 0; r < SPD_NB; ++r) acc[r] = 0.0;
     if (j < n && j < ib) {
-      for (int k = j + sub; k < ib; k += 4) {
+      for (int k = j + sub; k < ib; k += SPD_TPR) {
         const double xk = Lp[pk(k, j)];                  // X[k][j], rows above this block are already inverted
 #pragma unroll
         for (int r = 0; r < SPD_NB; ++r) acc[r] = fma(stage[r * n + k], xk, acc[r]);   // rows r >= nbi are stale: unused
@@ -458,8 +487,8 @@ spd_blocked_kernel(SpdBatch batch) {
     }
 #pragma unroll
     for (int r = 0; r < SPD_NB; ++r) {
-      acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 1);
-      acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 2);
+#pragma unroll
+      for (int o = 1; o < SPD_TPR; o <<= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
     }
     if (j < n && j < ib + nbi && sub == 0) {
       double xs[SPD_NB];
@@ -492,7 +521,7 @@ spd_blocked_kernel(SpdBatch batch) {
   if (P.Linv) {
     for (int e = tid; e < n * n; e += nt) {
       const int i = e / n, j = e - i * n;
-      P.Linv[e] = (j <= i) ? Lp[pk(i, j)] : 0.0;
+      P.Linv[e] = (j <= i) ? Lp[pk(i, j)] * s_scale[2] : 0.0;
     }
   }
   SPD_LAP(t_b);
@@ -512,7 +541,7 @@ spd_blocked_kernel(SpdBatch batch) {
         s3 = fma(Lp[pk(k + 3, i)], Lp[pk(k + 3, j)], s3);
       }
       for (; k < n; ++k) s0 = fma(Lp[pk(k, i)], Lp[pk(k, j)], s0);
-      const double v = (s0 + s1) + (s2 + s3);
+      const double v = ((s0 + s1) + (s2 + s3)) * s_scale[3];
       P.Ginv[(int64_t)i * n + j] = v;
       P.Ginv[(int64_t)j * n + i] = v;
     }
