@@ -377,41 +377,52 @@ spd_blocked_kernel(SpdBatch batch) {
     }
     __syncthreads();
     SPD_LAP(t_a);
-    if (tid == 0) {
-      // the 8 x 8 diagonal block lives in registers (fully unrolled): the serial part of the factorisation must not
-      // pay a shared-memory round trip per operation.  Rows past n are padded with the identity.
-      double d[SPD_NB][SPD_NB];
+    if (tid < 32) {
+      // The 8 x 8 diagonal block, by warp 0.  Every fp64 instruction occupies the fp64 pipe for a whole warp slot
+      // whether one lane or 32 use it, and one thread doing all ~320 operations of a block was the longest phase of the
+      // kernel: here each lane owns one (two for lanes 0-3) of the 36 entries, the block lives in shared memory, and
+      // ALL lanes evaluate the pivot reciprocal redundantly (nothing to broadcast).  Rows past n are padded with the
+      // identity.  Elimination in L D L^T form -- the next pivot needs 1 / d_cc (fp32 seed + two Newton steps) and one
+      // fma -- then the square roots that turn it into the Cholesky factor, one column per lane.
+      int er[2], ec[2];
 #pragma unroll
-      for (int r = 0; r < SPD_NB; ++r)
+      for (int u = 0; u < 2; ++u) {
+        const int e = tid + 32 * u;                       // entry index in the packed 8 x 8 lower triangle
+        int r = 0;
+        while ((r + 1) * (r + 2) / 2 <= e) ++r;
+        er[u] = r; ec[u] = e - r * (r + 1) / 2;
+      }
+      const bool has2 = tid + 32 < SPD_NB * (SPD_NB + 1) / 2;
+      if (!has2) { er[1] = 0; ec[1] = 0; }                // unused second slot: keep its (ignored) reads inside D
 #pragma unroll
-        for (int c = 0; c < SPD_NB; ++c)
-          if (c <= r) d[r][c] = (r < nbk) ? Lp[pk(kb + r, kb + c)] : (r == c ? 1.0 : 0.0);
-      // A dependent fp64 operation costs 50-85 cycles here and this thread is the serial part of the whole kernel, so
-      // the chain from one pivot to the next is kept minimal: the block is eliminated in L D L^T form -- next pivots
-      // only need 1 / d_cc (fp32 seed + two Newton steps) and ONE fma per entry, the products a_rc a_c2c do not wait
-      // for it -- and the square roots that turn it into the Cholesky factor are eight independent chains afterwards.
-      double rinv[SPD_NB];
+      for (int u = 0; u < 2; ++u)
+        if (u == 0 || has2)
+          D[er[u]][ec[u]] = (er[u] < nbk) ? Lp[pk(kb + er[u], kb + ec[u])] : (er[u] == ec[u] ? 1.0 : 0.0);
+      __syncwarp();
 #pragma unroll
-      for (int c = 0; c < SPD_NB; ++c) {
-        double ri = 0.0;
-        if (d[c][c] > tol) {
-          const double dc = d[c][c];
+      for (int c = 0; c < SPD_NB - 1; ++c) {
+        const double dc = D[c][c];
+        double a_rc[2], a_cc[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { a_rc[u] = D[er[u]][c]; a_cc[u] = D[ec[u]][c]; }
+        double ri = 0.0;                                  // 0 for a zero pivot: its column drops out of the updates
+        if (dc > tol) {
           double y = (double)__frcp_rn((float)dc);
           y = fma(y, fma(-dc, y, 1.0), y);
           ri = fma(y, fma(-dc, y, 1.0), y);
         }
-        rinv[c] = ri;                                     // 0 for a zero pivot: its column drops out of the updates
 #pragma unroll
-        for (int r = c + 1; r < SPD_NB; ++r)
-#pragma unroll
-          for (int c2 = c + 1; c2 <= r; ++c2) d[r][c2] = fma(-(d[r][c] * d[c2][c]), ri, d[r][c2]);
+        for (int u = 0; u < 2; ++u)
+          if ((u == 0 || has2) && ec[u] > c) D[er[u]][ec[u]] = fma(-(a_rc[u] * a_cc[u]), ri, D[er[u]][ec[u]]);
+        __syncwarp();
       }
-#pragma unroll
-      for (int c = 0; c < SPD_NB; ++c) {
-        // sqrt(d_cc) and its inverse: fp32 seed, Newton steps (22 -> 44 -> 88 bits), one Heron correction
+      {
+        // sqrt(d_cc) and its inverse for column c = lane & 7: fp32 seed, Newton steps (22 -> 44 -> 88 bits), one Heron
+        // correction
+        const int c = tid & (SPD_NB - 1);
+        const double dc = D[c][c];
         double piv = 0.0, inv = 0.0;
-        if (rinv[c] != 0.0) {
-          const double dc = d[c][c];
+        if (dc > tol) {
           double y = (double)rsqrtf((float)dc);
 #pragma unroll
           for (int it = 0; it < 2; ++it) y = y * fma(-0.5 * dc, y * y, 1.5);
@@ -419,20 +430,21 @@ spd_blocked_kernel(SpdBatch batch) {
           piv = fma(0.5 * y, fma(-piv, piv, dc), piv);
           inv = fma(y, fma(-piv, y, 1.0), y);             // 1 / piv to the last bits
         }
-        d[c][c] = piv;
-        invd[c] = inv;
-        if (c < nbk) dinv_all[kb + c] = inv;
+        __syncwarp();
+        if (tid < SPD_NB) {
+          invd[c] = inv;
+          if (c < nbk) dinv_all[kb + c] = inv;
+        }
+        __syncwarp();
 #pragma unroll
-        for (int r = c + 1; r < SPD_NB; ++r) d[r][c] *= inv;
+        for (int u = 0; u < 2; ++u)
+          if ((u == 0 || has2) && er[u] != ec[u]) D[er[u]][ec[u]] *= invd[ec[u]];
+        if (tid < SPD_NB) D[c][c] = piv;
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if ((u == 0 || has2) && er[u] < nbk) Lp[pk(kb + er[u], kb + ec[u])] = D[er[u]][ec[u]];
       }
-#pragma unroll
-      for (int r = 0; r < SPD_NB; ++r)
-#pragma unroll
-        for (int c = 0; c < SPD_NB; ++c)
-          if (c <= r) {
-            D[r][c] = d[r][c];
-            if (r < nbk) Lp[pk(kb + r, kb + c)] = d[r][c];
-          }
     }
     __syncthreads();
     SPD_LAP(t_b);
