@@ -497,7 +497,9 @@ def main():
         "cuda_graphs": bool(eng.use_graphs and eng._graphs),
         "roofline": roofline,
         "stage_ms": stage_ms,
-        "stage_ms_note": "mean ms per stage over %d eagerly launched steps (CUDA events on the launching stream)" % prof_steps,
+        "stage_ms_note": "mean ms per stage over %d EAGERLY launched steps (CUDA events on the launching stream): stages made "
+                         "of many short launches include host launch gaps, so the sum exceeds ms_per_step, which is "
+                         "measured on the CUDA-graph path" % prof_steps,
         "cpu_baseline": cpu,
         "clocks": clock_info,
     }
