@@ -105,7 +105,11 @@ struct Ctx {
     dim3 grid(cdiv(g.m, GT), cdiv(g.n, GT), g.ksplit > 1 ? g.ksplit : g.batch);
     gemm64_kernel<T><<<grid, 256, 0, s>>>(g);
     ++rt::g_launches;
-    if (g.ksplit > 1) { gemm64_reduce_kernel<T><<<cdiv(g.m * g.n, 256), 256, 0, s>>>(g); ++rt::g_launches; }
+    if (g.ksplit > 1) {
+      if (g.ksplit >= 64 && g.m * g.n <= 4096) gemm64_reduce_kernel<T, 32><<<cdiv(g.m * g.n * 32, 256), 256, 0, s>>>(g);
+      else gemm64_reduce_kernel<T, 1><<<cdiv(g.m * g.n, 256), 256, 0, s>>>(g);
+      ++rt::g_launches;
+    }
     if (cudaGetLastError() != cudaSuccess) err = 1;
   }
 

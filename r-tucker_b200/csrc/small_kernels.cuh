@@ -117,19 +117,30 @@ gemm64_kernel(GemmT<T> g) {
   }
 }
 
-// one thread per output element, splits summed in index order (fixed order: deterministic); consecutive threads
-// read consecutive elements of each partial slab
-template <typename T>
+// LANES threads per output element: lane l sums the splits l, l + LANES, ... in index order, then the lanes are
+// combined by a fixed xor tree -- a fixed order whatever the schedule, hence deterministic.  LANES = 1: consecutive
+// threads read consecutive elements of each partial slab.  LANES = 32 is for the tiny outputs of very long
+// contractions (e.g. 10 x 10 from K = 10^5, 278 splits): one thread per element walked the 278 slabs as one
+// dependent chain of L2 round trips and fp64 additions (60 us under ncu, six times per step).
+template <typename T, int LANES>
 __global__ void gemm64_reduce_kernel(GemmT<T> g) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e = t / LANES;
+  const int lane = (int)(t % LANES);
   const int64_t mn = (int64_t)g.m * g.n;
-  if (e >= mn) return;
-  const int mm = (int)(e / g.n), nn = (int)(e - (int64_t)mm * g.n);
+  const bool live = e < mn;                   // a whole group of LANES threads is live or not (blockDim % LANES == 0)
   T s = (T)0;
+  if (live) {
 #pragma unroll 4
-  for (int k = 0; k < g.ksplit; ++k) s += g.partial[(int64_t)k * mn + e];
-  T* c = g.C + (int64_t)mm * g.c_m + (int64_t)nn * g.c_n;
-  *c = (T)g.alpha * s + (g.beta != 0.0 ? (T)g.beta * (*c) : (T)0);
+    for (int k = lane; k < g.ksplit; k += LANES) s += g.partial[(int64_t)k * mn + e];
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (live && lane == 0) {
+    const int mm = (int)(e / g.n), nn = (int)(e - (int64_t)mm * g.n);
+    T* c = g.C + (int64_t)mm * g.c_m + (int64_t)nn * g.c_n;
+    *c = (T)g.alpha * s + (g.beta != 0.0 ? (T)g.beta * (*c) : (T)0);
+  }
 }
 
 // ---- elementwise helpers ----------------------------------------------------------------
