@@ -366,6 +366,25 @@ __device__ __forceinline__ void cta_visit(bool intra) {
   __syncthreads();
 }
 
+// Grid barrier of the round loop (two per round, ~230 rounds per problem: a fifth of the kernel's time went into
+// cooperative-groups grid.sync).  Arrival is a fire-and-forget reduction, the wait polls the same word in L2: one L2
+// round trip less than an atomic with a return value followed by the poll.  The launch is cooperative (all CTAs are
+// resident); the counter only grows during a launch and is reset by CTA 0 before the kernel's first grid.sync.
+__device__ unsigned int g_eig_barrier;
+__device__ __forceinline__ void round_barrier(unsigned int& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    // release: this CTA's writes (ordered before thread 0 by the barrier above) become visible with the arrival
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;\n" :: "l"(&g_eig_barrier) : "memory");
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(seen) : "l"(&g_eig_barrier) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kEigThreads, 1)
 eig_block_jacobi_kernel(EigBatch batch) {
   extern __shared__ __align__(16) double esm[];
@@ -387,6 +406,8 @@ eig_block_jacobi_kernel(EigBatch batch) {
   }
   __syncthreads();
 
+  unsigned int bar_target = 0u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_eig_barrier = 0u;      // visible to all after the grid.sync below
   // ---- phase 0: scale factor, padded copies, V = I, norms ----
   for (int pi = 0; pi < batch.count; ++pi) {
     const EigProblem& P = batch.p[pi];
@@ -511,7 +532,7 @@ eig_block_jacobi_kernel(EigBatch batch) {
         base = (base + P.npairs) % gridDim.x;
       }
       t1 = clock64(); tA += t1 - t0;
-      grid.sync();
+      round_barrier(bar_target);
       t0 = clock64(); tS1 += t0 - t1;
       // ---- phase B: A_kl <- Q_k^T A_kl Q_l (k != l),  V[:, l] <- V[:, l] Q_l ----
       base = 0;
@@ -587,7 +608,7 @@ eig_block_jacobi_kernel(EigBatch batch) {
         base = (base + nA + nV) % nwarps;
       }
       t1 = clock64(); tB += t1 - t0;
-      grid.sync();
+      round_barrier(bar_target);
       t0 = clock64(); tS2 += t0 - t1;
     }
     // convergence: off-diagonal mass seen during this sweep (uniform decision: same memory, after sync)
