@@ -253,6 +253,13 @@ int rt_small_retract(const float* core, const float* dS_dir,
  * A[n,n] (destroyed) -> eigenvalues w[n] descending, eigenvectors V[n,n] (columns). */
 size_t rt_eigh_ws_bytes(int n);
 int rt_eigh(double* A, int n, double* w, double* V, void* ws, void* stream);
+/* Orthonormal basis Y[n, r] (row-major, fp64) of the dominant r-dimensional invariant subspace of the symmetric
+ * positive semi-definite A[n, n] (not modified), by trace-correcting purification + Newton-Schulz polar iteration
+ * on the fp64 tensor cores (csrc/subspace.cu): what Tucker.round / SFTucker.round need from the SVD of an
+ * unfolding (asymmetric/optim.py:108, symmetric/optim.py:55,102).  info (device int[4], may be NULL) receives
+ * the purification and Newton-Schulz iteration counts.  Exposed for testing; rt_small_retract uses it in batch. */
+size_t rt_dominant_subspace_ws_bytes(int n, int r);
+int rt_dominant_subspace(const double* A, int n, int r, double* Y, int* info, void* ws, void* stream);
 
 /* Known-answer self test of the tcgen05 building blocks: D[128,N] = op(A) op(B)^T in TF32
  * (a_mn/b_mn select MN-major operands given as [K][M] / [K][N]); used by tests/test_gpu_tc.py. */

@@ -56,6 +56,8 @@ PROTOTYPES = {
     "rt_small_retract": (i32, [vp] * 6 + [i32, i32, i32, i32] + [vp] * 12),
     "rt_eigh_ws_bytes": (sz, [i32]),
     "rt_eigh": (i32, [vp, i32, vp, vp, vp, vp]),
+    "rt_dominant_subspace_ws_bytes": (sz, [i32, i32]),
+    "rt_dominant_subspace": (i32, [vp, i32, i32, vp, vp, vp, vp]),
     "rt_tc_selftest": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "rt_tc_selftest16": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "rt_bulk_reduce_selftest": (i32, [vp, vp, vp, i32, vp]),

@@ -23,7 +23,18 @@ namespace rt {
 int eig_batch(int count, const double* const* A, const int* n, double* const* w, double* const* V,
               void* const* ws, cudaStream_t s, double stop);
 size_t eig_ws_bytes(int n);
+int subspace_batch(int count, const double* const* N, const int* n, const int* r, double* const* Y, const int* ldy,
+                   void* const* ws, void* shared_ws, int* const* info, cudaStream_t s);
+size_t subspace_ws_bytes(int n, int r);
+size_t subspace_shared_ws_bytes();
 }  // namespace rt
+
+// HOSVD route: 1 (default) = dominant subspaces by purification + Newton-Schulz on the fp64 tensor cores
+// (subspace.cu); 0 = full eigen-decomposition by block Jacobi (eig.cu, round 1).  RT_HOSVD=jacobi selects 0.
+static int hosvd_route() {
+  static const int v = [] { const char* e = std::getenv("RT_HOSVD"); return (e && e[0] == 'j') ? 0 : 1; }();
+  return v;
+}
 
 extern "C" size_t rt_gram_ws_bytes(int n, int ra, int rb);
 
@@ -41,7 +52,7 @@ struct Layout {
   int B;
   int64_t c;  // r0*r1*r2
   size_t C64, Gm[3], Ainv[3], coresq, Tn[kNumT], KC[3], Nn[3], Vf[3], Wv[3], GL[3], GLinv[3], Gs[3],
-      tmpM[3], tmpK[3], eig[3], gemm_partial, gram_ws, dot_partial, scal, total;
+      tmpM[3], tmpK[3], eig[3], sub[3], sub_shared, gemm_partial, gram_ws, dot_partial, scal, total;
 };
 
 Layout make_layout(int r0, int r1, int r2, int B) {
@@ -66,7 +77,9 @@ Layout make_layout(int r0, int r1, int r2, int B) {
     L.tmpM[i] = take(2 * r * r);
     L.tmpK[i] = take(2 * r * r);
     size_t at = o; o += align_up(rt::eig_ws_bytes(2 * (int)r), 256); L.eig[i] = at;
+    at = o; o += align_up(rt::subspace_ws_bytes(2 * (int)r, (int)r), 256); L.sub[i] = at;
   }
+  { size_t at = o; o += align_up(rt::subspace_shared_ws_bytes(), 256); L.sub_shared = at; }
   L.gemm_partial = take((size_t)kMaxSplitCtas * GT * GT);
   int rmax = r0 > r1 ? r0 : r1; rmax = rmax > r2 ? rmax : r2;
   { size_t at = o; o += align_up(rt_gram_ws_bytes(B > 0 ? B : 1, rmax, rmax), 256); L.gram_ws = at; }
@@ -489,7 +502,14 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
   }
   if (sym) c.axpby(Nn[1], Nn[2], Nn[1], 4 * (int64_t)d[1] * d[1], 1.0, nullptr, 1.0, nullptr);
   if (c.err) return finish(c, "rt_small_retract");
-  {
+  if (hosvd_route() == 1) {
+    const double* Ain[3]; int nn[3]; int rr[3]; int ldy[3]; double* Yv[3]; void* sws[3];
+    for (int i = 0; i < nm; ++i) {
+      Ain[i] = Nn[i]; nn[i] = 2 * d[i]; rr[i] = d[i]; ldy[i] = 2 * d[i]; Yv[i] = c.p(c.L.Vf[i]);
+      sws[i] = c.base + c.L.sub[i];
+    }
+    if ((rc = rt::subspace_batch(nm, Ain, nn, rr, Yv, ldy, sws, c.base + c.L.sub_shared, nullptr, s))) return rc;
+  } else {
     const double* Ain[3]; int nn[3]; double* wv[3]; double* Vv[3]; void* ews[3];
     for (int i = 0; i < nm; ++i) {
       Ain[i] = Nn[i]; nn[i] = 2 * d[i]; wv[i] = c.p(c.L.Wv[i]); Vv[i] = c.p(c.L.Vf[i]);

@@ -300,6 +300,19 @@ def eigh(A):
     return w, V
 
 
+def dominant_subspace(A, r):
+    """Orthonormal basis Y [n, r] (fp64) of the dominant r-dimensional invariant subspace of the symmetric PSD
+    matrix A (purification + Newton-Schulz, csrc/subspace.cu); returns (Y, info[4] int32: iterations)."""
+    require_cuda(A)
+    n = A.shape[0]
+    A = _c(A, f64)
+    Y = torch.empty(n, r, dtype=f64, device=A.device)
+    info = torch.zeros(4, dtype=i32, device=A.device)
+    ws = _ws(lib().rt_dominant_subspace_ws_bytes(n, r), A.device)
+    check(lib().rt_dominant_subspace(ptr(A), n, r, ptr(Y), ptr(info), ptr(ws), stream_ptr()), "rt_dominant_subspace")
+    return Y, info
+
+
 def score_dense(q, O, out=None):
     """Dense sigmoid scores P[B, n] (compat path of R_TuckER.py:47-48)."""
     require_cuda(q, O)

@@ -285,6 +285,59 @@ def test_eigh(cuda_device, n):
     assert float((A @ V - V * w).abs().max()) <= 1e-10 * float(w_ref.abs().max())
 
 
+def graded_psd(n, r, top, bottom, ratio, seed):
+    """Symmetric PSD matrix with a graded spectrum like the unfolding Grams of a training run: the r dominant
+    eigenvalues log-spaced in [bottom, top], the rest log-spaced below bottom / ratio."""
+    g = torch.Generator().manual_seed(seed)
+    Q, _ = torch.linalg.qr(torch.randn(n, n, generator=g, dtype=torch.float64))
+    lam = torch.cat([torch.logspace(np.log10(top), np.log10(bottom), r, dtype=torch.float64),
+                     torch.logspace(np.log10(bottom / ratio), np.log10(bottom / ratio) - 6, n - r, dtype=torch.float64)])
+    return (Q * lam) @ Q.T, Q[:, :r], lam
+
+
+@pytest.mark.parametrize("n,r,top,bottom,ratio", [
+    (20, 10, 1e3, 1.0, 10.0), (40, 20, 1.0, 0.5, 2.0), (400, 200, 1e6, 0.3, 1.3), (400, 200, 1e5, 1e-1, 50.0),
+    (130, 65, 1e4, 1.0, 1.5), (64, 20, 10.0, 1.0, 3.0), (7, 3, 5.0, 1.0, 4.0)])
+def test_dominant_subspace(cuda_device, n, r, top, bottom, ratio):
+    """Purification + Newton-Schulz (csrc/subspace.cu) against the eigenvectors of numpy's eigh: the basis is
+    orthonormal to 1e-12 and spans the dominant invariant subspace (projector error bounded by eps / relative gap)."""
+    from rtucker_b200 import ops
+    A, Qr, lam = graded_psd(n, r, top, bottom, ratio, seed=n + r)
+    A = 0.5 * (A + A.T)
+    Y, info = ops.dominant_subspace(A.to(cuda_device), r)
+    Y, info = Y.cpu(), info.cpu()
+    assert 0 < int(info[0]) < 120 and 0 < int(info[1]) < 60, info
+    assert float((Y.T @ Y - torch.eye(r, dtype=torch.float64)).abs().max()) < 1e-12
+    w, V = torch.linalg.eigh(A)
+    Vr = V[:, -r:]
+    relgap = float((lam[r - 1] - lam[r]) / lam[0])
+    perr = float((Y @ Y.T - Vr @ Vr.T).norm())
+    assert perr < max(1e-11, 2e-15 / relgap), (perr, relgap, info)
+
+
+def test_dominant_subspace_of_identity_like(cuda_device):
+    """Already a projector: P = diag(1..1, 0..0) scaled; and a matrix with NO gap at r (degenerate): the basis must
+    still be orthonormal."""
+    from rtucker_b200 import ops
+    n, r = 64, 32
+    A = torch.zeros(n, n, dtype=torch.float64)
+    A[:r, :r] = 3.0 * torch.eye(r, dtype=torch.float64)
+    Y, info = ops.dominant_subspace(A.to(cuda_device), r)
+    Y = Y.cpu()
+    assert float((Y.T @ Y - torch.eye(r, dtype=torch.float64)).abs().max()) < 1e-12
+    assert float(Y[r:].abs().max()) < 1e-12
+    g = torch.Generator().manual_seed(5)
+    Q, _ = torch.linalg.qr(torch.randn(n, n, generator=g, dtype=torch.float64))
+    lam = torch.ones(n, dtype=torch.float64)
+    lam[: r - 4] = 5.0            # eigenvalues r-3 .. n all equal: no gap at r
+    A = (Q * lam) @ Q.T
+    Y, info = ops.dominant_subspace((0.5 * (A + A.T)).to(cuda_device), r)
+    Y = Y.cpu()
+    # (with an exact tie at r the truncation is not unique and the purification cannot settle: the iteration cap
+    # ends it and the basis of whatever subspace it reached must still be orthonormal)
+    assert float((Y.T @ Y - torch.eye(r, dtype=torch.float64)).abs().max()) < 1e-10, info
+
+
 # ------------------------------------------------------------------------------------------------
 # tcgen05 / TMEM variant of the fused score kernel: TF32 inputs, fp32 accumulation.  Stated looser
 # bound (north_star): 2e-3 norm-wise on H / dO, 1e-4 on the loss (vs 1e-5 for the fp32 FFMA path).
