@@ -10,6 +10,10 @@
 //
 // Everything here costs O(poly(r)) and is replicated on every GPU of an entity-sharded run.
 #include "small_kernels.cuh"
+#include "small_exec.cuh"
+
+#include <algorithm>
+#include <vector>
 
 #include <cstdlib>
 // Stop criterion of the HOSVD eigenproblems (off-diagonal mass SEEN in a sweep, relative to ||A||_F^2).
@@ -52,7 +56,7 @@ struct Layout {
   int B;
   int64_t c;  // r0*r1*r2
   size_t C64, Gm[3], Ainv[3], coresq, Tn[kNumT], KC[3], Nn[3], Vf[3], Wv[3], GL[3], GLinv[3], Gs[3],
-      tmpM[3], tmpK[3], eig[3], sub[3], sub_shared, gemm_partial, gram_ws, dot_partial, scal, total;
+      tmpM[3], tmpK[3], eig[3], sub[3], sub_shared, exec_bar, gemm_partial, gram_ws, dot_partial, scal, total;
 };
 
 Layout make_layout(int r0, int r1, int r2, int B) {
@@ -80,50 +84,150 @@ Layout make_layout(int r0, int r1, int r2, int B) {
     at = o; o += align_up(rt::subspace_ws_bytes(2 * (int)r, (int)r), 256); L.sub[i] = at;
   }
   { size_t at = o; o += align_up(rt::subspace_shared_ws_bytes(), 256); L.sub_shared = at; }
+  L.exec_bar = take(32);
   L.gemm_partial = take((size_t)kMaxSplitCtas * GT * GT);
   int rmax = r0 > r1 ? r0 : r1; rmax = rmax > r2 ? rmax : r2;
   { size_t at = o; o += align_up(rt_gram_ws_bytes(B > 0 ? B : 1, rmax, rmax), 256); L.gram_ws = at; }
-  L.dot_partial = take(kDotBlocks);
+  L.dot_partial = take(2048);
   L.scal = take(16);
   L.total = o;
   return L;
 }
+
+// ---- recording context: operations are RECORDED with the byte ranges they touch, scheduled into dependency
+// levels and executed by one persistent launch per flush() (small_exec.cuh) ------------------------------------------
+struct Range { const char* lo; const char* hi; };
+struct Rec { Op op; Range rd[4]; int nrd; Range wr[2]; int nwr; };
+
+constexpr size_t kPartialArenaBytes = (size_t)kMaxSplitCtas * GT * GT * sizeof(double);
+constexpr int kDotSlots = 2048;
+
+template <typename T> struct DT;
+template <> struct DT<float> { static constexpr int v = DT_F32; };
+template <> struct DT<double> { static constexpr int v = DT_F64; };
+static inline size_t dsize(int t) { return t == DT_F64 ? 8 : 4; }
 
 struct Ctx {
   Layout L;
   char* base;
   cudaStream_t s;
   int err = 0;
+  std::vector<Rec> recs;
+  size_t partial_off = 0;
+  int dot_off = 0;
   double* p(size_t off) const { return (double*)(base + off); }
   double* T(int t) const { return p(L.Tn[t]); }
   int r(int i) const { return L.r[i]; }
 
-  template <typename T>
-  void gemm(GemmT<T> g) {
+  static Range range(const void* ptr, size_t bytes) { return Range{(const char*)ptr, (const char*)ptr + bytes}; }
+  static bool overlap(const Range& a, const Range& b) { return a.lo < b.hi && b.lo < a.hi; }
+
+  void push(Rec& rec) {
     if (err) return;
-    if (g.m <= 0 || g.n <= 0) return;
-    g.ksplit = 1; g.k_per_split = g.K1 * g.K2; g.partial = reinterpret_cast<T*>(p(L.gemm_partial));
-    const int tiles = cdiv(g.m, GT) * cdiv(g.n, GT);
-    const int K = g.K1 * g.K2;
-    if (g.batch == 1 && tiles < 148 && K >= 8 * GK) {
-      int ks = cdiv(296, tiles);
-      const int max_ks = cdiv(K, 4 * GK);
-      if (ks > max_ks) ks = max_ks;
-      if ((int64_t)ks * tiles > kMaxSplitCtas) ks = kMaxSplitCtas / tiles;
+    if ((int)recs.size() >= kMaxOps) flush();
+    // level = 1 + the deepest earlier operation this one conflicts with (RAW, WAW, WAR on byte ranges)
+    int level = 0;
+    for (const Rec& q : recs) {
+      bool c = false;
+      for (int i = 0; i < q.nwr && !c; ++i) {
+        for (int j = 0; j < rec.nrd && !c; ++j) c = overlap(q.wr[i], rec.rd[j]);
+        for (int j = 0; j < rec.nwr && !c; ++j) c = overlap(q.wr[i], rec.wr[j]);
+      }
+      for (int i = 0; i < q.nrd && !c; ++i)
+        for (int j = 0; j < rec.nwr && !c; ++j) c = overlap(q.rd[i], rec.wr[j]);
+      if (c && q.op.level + 1 > level) level = q.op.level + 1;
+    }
+    rec.op.level = level;
+    recs.push_back(rec);
+  }
+
+  // Execute what has been recorded (one cooperative launch); direct launches may follow on the stream.
+  void flush() {
+    if (err || recs.empty()) { recs.clear(); return; }
+    std::stable_sort(recs.begin(), recs.end(), [](const Rec& a, const Rec& b) { return a.op.level < b.op.level; });
+    static Program prog;     // host staging of the parameter block (copied by the launch)
+    prog.nops = (int)recs.size();
+    prog.bar = reinterpret_cast<unsigned int*>(base + L.exec_bar);
+    for (int i = 0; i < prog.nops; ++i) prog.ops[i] = recs[i].op;
+    recs.clear();
+    partial_off = 0;
+    dot_off = 0;
+    const size_t smem = sizeof(double) * kExecWarps * XT * XLD;
+    if (cudaMemsetAsync(prog.bar, 0, 256, s) != cudaSuccess ||
+        cudaFuncSetAttribute(small_exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      err = 1; return;
+    }
+    void* args[] = {(void*)&prog};
+    if (cudaLaunchCooperativeKernel((const void*)small_exec_kernel, dim3(rt::sm_count()), dim3(kExecThreads), args,
+                                    smem, s) != cudaSuccess) err = 1;
+    ++rt::g_launches;
+  }
+
+  // C (tc) [m, n] = alpha * (alpha_dev ? *alpha_dev : 1) * sum_{k1, k2} A (ta) B (tb) + beta * C, batched; element strides
+  void gemm_any(const void* A, int ta, const void* B, int tb, void* C, int tc, int m, int n, int K1, int K2,
+                int64_t a_m, int64_t a_k1, int64_t a_k2, int64_t b_k1, int64_t b_k2, int64_t b_n, int64_t c_m,
+                int64_t c_n, int batch, int64_t a_b, int64_t b_b, int64_t c_b, double alpha, double beta,
+                const double* alpha_dev = nullptr) {
+    if (err || m <= 0 || n <= 0) return;
+    Rec rec{};
+    GemmPart& g = rec.op.g;
+    rec.op.kind = OP_GEMM;
+    g.A = A; g.B = B; g.C = C; g.ta = ta; g.tb = tb; g.tc = tc;
+    g.m = m; g.n = n; g.K1 = K1; g.K2 = K2;
+    g.a_m = a_m; g.a_k1 = a_k1; g.a_k2 = a_k2; g.b_k1 = b_k1; g.b_k2 = b_k2; g.b_n = b_n; g.c_m = c_m; g.c_n = c_n;
+    g.batch = batch; g.a_b = a_b; g.b_b = b_b; g.c_b = c_b;
+    g.alpha = alpha; g.beta = beta; g.alpha_dev = alpha_dev;
+    g.tiles_m = cdiv(m, XT); g.tiles_n = cdiv(n, XT);
+    const int tiles = batch * g.tiles_m * g.tiles_n;
+    const int S = K1 * cdiv(K2, 4);
+    g.ksplit = 1; g.steps_per_split = S > 0 ? S : 1; g.partial = nullptr;
+    if (tiles < 120 && S >= 32) {
+      int ks = cdiv(160, tiles);
+      if (ks > S / 16) ks = S / 16;
+      if (ks > 64) ks = 64;
       if (ks > 1) {
-        g.k_per_split = cdiv(cdiv(K, ks), GK) * GK;
-        g.ksplit = cdiv(K, g.k_per_split);
+        const int sps = cdiv(cdiv(S, ks), kExecWarps) * kExecWarps;
+        ks = cdiv(S, sps);
+        const size_t bytes = align_up((size_t)ks * batch * m * n * sizeof(double), 256);
+        if (ks > 1 && bytes <= kPartialArenaBytes) {
+          if (partial_off + bytes > kPartialArenaBytes) partial_off = 0;   // wrap: the hazard tracking orders the reuse
+          g.partial = reinterpret_cast<double*>(base + L.gemm_partial + partial_off);
+          partial_off += bytes;
+          g.ksplit = ks; g.steps_per_split = sps;
+        }
       }
     }
-    dim3 grid(cdiv(g.m, GT), cdiv(g.n, GT), g.ksplit > 1 ? g.ksplit : g.batch);
-    gemm64_kernel<T><<<grid, 256, 0, s>>>(g);
-    ++rt::g_launches;
+    rec.op.units = tiles * g.ksplit;
+    auto ext = [](int64_t a, int64_t b, int64_t c, int64_t d) { return (size_t)(a + b + c + d + 1); };
+    const size_t ea = ext((int64_t)(m - 1) * a_m, (int64_t)(K1 - 1) * a_k1, (int64_t)(K2 - 1) * a_k2, (int64_t)(batch - 1) * a_b);
+    const size_t eb = ext((int64_t)(n - 1) * b_n, (int64_t)(K1 - 1) * b_k1, (int64_t)(K2 - 1) * b_k2, (int64_t)(batch - 1) * b_b);
+    const size_t ec = ext((int64_t)(m - 1) * c_m, (int64_t)(n - 1) * c_n, 0, (int64_t)(batch - 1) * c_b);
+    rec.rd[rec.nrd++] = range(A, ea * dsize(ta));
+    rec.rd[rec.nrd++] = range(B, eb * dsize(tb));
+    if (alpha_dev) rec.rd[rec.nrd++] = range(alpha_dev, 8);
     if (g.ksplit > 1) {
-      if (g.ksplit >= 64 && g.m * g.n <= 4096) gemm64_reduce_kernel<T, 32><<<cdiv(g.m * g.n * 32, 256), 256, 0, s>>>(g);
-      else gemm64_reduce_kernel<T, 1><<<cdiv(g.m * g.n, 256), 256, 0, s>>>(g);
-      ++rt::g_launches;
+      rec.wr[rec.nwr++] = range(g.partial, (size_t)g.ksplit * batch * m * n * sizeof(double));
+      push(rec);
+      Rec red{};
+      red.op.kind = OP_REDUCE;
+      red.op.g = g;
+      red.op.units = cdiv(batch * m * n, kReduceChunk);
+      red.rd[red.nrd++] = range(g.partial, (size_t)g.ksplit * batch * m * n * sizeof(double));
+      if (alpha_dev) red.rd[red.nrd++] = range(alpha_dev, 8);
+      if (beta != 0.0) red.rd[red.nrd++] = range(C, ec * dsize(tc));
+      red.wr[red.nwr++] = range(C, ec * dsize(tc));
+      push(red);
+    } else {
+      if (beta != 0.0) rec.rd[rec.nrd++] = range(C, ec * dsize(tc));
+      rec.wr[rec.nwr++] = range(C, ec * dsize(tc));
+      push(rec);
     }
-    if (cudaGetLastError() != cudaSuccess) err = 1;
+  }
+
+  template <typename T>
+  void gemm(const GemmT<T>& g) {
+    gemm_any(g.A, DT<T>::v, g.B, DT<T>::v, g.C, DT<T>::v, g.m, g.n, g.K1, g.K2, g.a_m, g.a_k1, g.a_k2, g.b_k1, g.b_k2,
+             g.b_n, g.c_m, g.c_n, g.batch, g.a_b, g.b_b, g.c_b, g.alpha, g.beta);
   }
 
   // Y = alpha * (X x_mode M) + beta * Y.  M is (mo x mi) with strides (sm_o, sm_i);
@@ -176,66 +280,113 @@ struct Ctx {
 
   // plain C[m,n] = alpha * A[m,k] B[k,n] + beta*C with row-major leading dims
   void matmul(const double* A, int64_t lda, bool ta, const double* B, int64_t ldb, bool tb, double* C,
-              int64_t ldc, int m, int n, int k, double alpha, double beta) {
-    Gemm g{};
-    g.alpha = alpha; g.beta = beta; g.batch = 1;
-    g.A = A; g.B = B; g.C = C; g.m = m; g.n = n; g.K1 = 1; g.K2 = k;
-    g.a_m = ta ? 1 : lda; g.a_k2 = ta ? lda : 1;
-    g.b_k2 = tb ? 1 : ldb; g.b_n = tb ? ldb : 1;
-    g.c_m = ldc; g.c_n = 1;
-    gemm(g);
+              int64_t ldc, int m, int n, int k, double alpha, double beta, const double* alpha_dev = nullptr) {
+    gemm_any(A, DT_F64, B, DT_F64, C, DT_F64, m, n, 1, k, ta ? 1 : lda, 0, ta ? lda : 1, 0, tb ? 1 : ldb, tb ? ldb : 1,
+             ldc, 1, 1, 0, 0, 0, alpha, beta, alpha_dev);
   }
 
   float* Tf(int t) const { return reinterpret_cast<float*>(T(t)); }   // the same temporaries viewed as fp32
-  void to32plain(const double* x, float* y, int64_t n) {
-    if (err) return;
-    int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
-    f64_to_f32_kernel<<<blocks, 256, 0, s>>>(x, y, n); ++rt::g_launches;
+
+  void ew(int kind, const void* x, int tx, size_t xbytes, const void* y, size_t ybytes, void* z, int tz, size_t zbytes,
+          int64_t count, double s0, const double* d0, double s1, const double* d1, int64_t p0 = 0, int64_t p1 = 0,
+          int64_t p2 = 0, int64_t p3 = 0, bool reads_z = false, size_t d0_bytes = 8) {
+    if (err || count <= 0) return;
+    Rec rec{};
+    rec.op.kind = OP_EW; rec.op.ew = kind;
+    EwPart& e = rec.op.e;
+    e.x = x; e.y = y; e.z = z; e.tx = tx; e.tz = tz; e.count = count; e.s0 = s0; e.s1 = s1; e.d0 = d0; e.d1 = d1;
+    e.p0 = p0; e.p1 = p1; e.p2 = p2; e.p3 = p3;
+    rec.op.units = kind == EW_NORM_FINISH ? 1 : (int)((count + kEwChunk - 1) / kEwChunk);
+    if (x) rec.rd[rec.nrd++] = range(x, xbytes);
+    if (y) rec.rd[rec.nrd++] = range(y, ybytes);
+    if (d0) rec.rd[rec.nrd++] = range(d0, d0_bytes);
+    if (d1) rec.rd[rec.nrd++] = range(d1, 8);
+    if (reads_z && rec.nrd < 4) rec.rd[rec.nrd++] = range(z, zbytes);
+    rec.wr[rec.nwr++] = range(z, zbytes);
+    push(rec);
   }
-  void scale32(const float* x, float* y, int64_t n, double a_host, const double* a_dev) {
-    if (err) return;
-    int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
-    scale_f32_kernel<<<blocks, 256, 0, s>>>(x, y, n, a_host, a_dev); ++rt::g_launches;
+  void cvt(const void* x, int tx, void* y, int ty, int64_t n, double a_host = 1.0, const double* a_dev = nullptr,
+           bool square_dev = false) {
+    ew(EW_CVT, x, tx, n * dsize(tx), nullptr, 0, y, ty, n * dsize(ty), n, a_host, a_dev, 0.0, nullptr, square_dev ? 1 : 0);
   }
-  void to64(const float* x, double* y, int64_t n) {
-    if (err) return;
-    int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
-    f32_to_f64_kernel<<<blocks, 256, 0, s>>>(x, y, n); ++rt::g_launches;
-  }
-  void to32(const double* x, float* y, int64_t n, double a_host, const double* a_dev) {
-    if (err) return;
-    int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
-    f64_to_f32_scaled_kernel<<<blocks, 256, 0, s>>>(x, y, n, a_host, a_dev); ++rt::g_launches;
-  }
+  void to32plain(const double* x, float* y, int64_t n) { cvt(x, DT_F64, y, DT_F32, n); }
+  void scale32(const float* x, float* y, int64_t n, double a_host, const double* a_dev) { cvt(x, DT_F32, y, DT_F32, n, a_host, a_dev); }
+  void to64(const float* x, double* y, int64_t n) { cvt(x, DT_F32, y, DT_F64, n); }
+  void to32(const double* x, float* y, int64_t n, double a_host, const double* a_dev) { cvt(x, DT_F64, y, DT_F32, n, a_host, a_dev); }
   void axpby(const double* x, const double* y, double* z, int64_t n, double a, const double* a_dev,
              double b, const double* b_dev) {
-    if (err) return;
-    int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
-    axpby64_kernel<<<blocks, 256, 0, s>>>(x, y, z, n, a, a_dev, b, b_dev); ++rt::g_launches;
+    ew(EW_AXPBY64, x, DT_F64, n * 8, y, n * 8, z, DT_F64, n * 8, n, a, a_dev, b, b_dev);
   }
-  template <typename TA, typename TB>
-  void dot(const TA* x, const TB* y, int64_t n, double scale, double* out, int accumulate) {
-    if (err) return;
-    int blocks = (int)((n + 255) / 256); if (blocks > kDotBlocks) blocks = kDotBlocks; if (blocks < 1) blocks = 1;
-    dot_partial_kernel<TA, TB><<<blocks, 256, 0, s>>>(x, y, n, p(L.dot_partial));
-    dot_final_kernel<<<1, 32, 0, s>>>(p(L.dot_partial), blocks, scale, out, accumulate); rt::g_launches += 2;
+  // dst[i, j] (ld ldd) = src[i, j] (ld lds), rows x cols, with conversion
+  void copy2d(const void* src, int ts, int64_t lds, void* dst, int td, int64_t ldd, int rows, int cols) {
+    ew(EW_CVT_2D, src, ts, ((size_t)(rows - 1) * lds + cols) * dsize(ts), nullptr, 0, dst, td,
+       ((size_t)(rows - 1) * ldd + cols) * dsize(td), (int64_t)rows * cols, 1.0, nullptr, 0.0, nullptr, lds, ldd, rows, cols);
   }
+  void transpose_into(const double* src, int n, double* dst, int64_t ldd) {
+    ew(EW_TRANSPOSE_INTO, src, DT_F64, (size_t)n * n * 8, nullptr, 0, dst, DT_F64, ((size_t)(n - 1) * ldd + n) * 8,
+       (int64_t)n * n, 1.0, nullptr, 0.0, nullptr, n, ldd, n, 0);
+  }
+  void symmetrize_lower(double* A, int n) {
+    ew(EW_SYMM_LOWER, nullptr, DT_F64, 0, nullptr, 0, A, DT_F64, (size_t)n * n * 8, (int64_t)n * n, 1.0, nullptr, 0.0,
+       nullptr, n, 0, n, 0, true);
+  }
+  // norm_out[0] = sqrt(max(sq[0], 0)); alpha_out[0] = hyper[3] != 0 ? hyper[3] / norm : 1
+  void norm_finish(const double* sq, const double* hyper, double* norm_out, double* alpha_out) {
+    if (err) return;
+    Rec rec{};
+    rec.op.kind = OP_EW; rec.op.ew = EW_NORM_FINISH; rec.op.units = 1;
+    EwPart& e = rec.op.e;
+    e.x = sq; e.y = alpha_out; e.z = norm_out; e.d0 = hyper; e.count = 1;
+    rec.rd[rec.nrd++] = range(sq, 8);
+    rec.rd[rec.nrd++] = range(hyper, 32);
+    rec.wr[rec.nwr++] = range(norm_out, 8);
+    rec.wr[rec.nwr++] = range(alpha_out, 8);
+    push(rec);
+  }
+  void zero64(double* z, int64_t n) { ew(EW_ZERO64, nullptr, DT_F64, 0, nullptr, 0, z, DT_F64, n * 8, n, 0.0, nullptr, 0.0, nullptr); }
+
+  // out[0] = (accumulate ? out[0] : 0) + scale * sum x[i] y[i]   (deterministic two-stage sum)
+  void dot(const void* x, int tx, const void* y, int ty, int64_t n, double scale, double* out, int accumulate) {
+    if (err || n <= 0) return;
+    const int units = (int)((n + kEwChunk - 1) / kEwChunk);
+    if (dot_off + units > kDotSlots) { flush(); }
+    double* part = p(L.dot_partial) + dot_off;
+    dot_off += units;
+    Rec rec{};
+    rec.op.kind = OP_DOT;
+    EwPart& e = rec.op.e;
+    e.x = x; e.y = y; e.z = part; e.tx = tx; e.tz = ty; e.count = n;
+    rec.op.units = units;
+    rec.rd[rec.nrd++] = range(x, n * dsize(tx));
+    rec.rd[rec.nrd++] = range(y, n * dsize(ty));
+    rec.wr[rec.nwr++] = range(part, (size_t)units * 8);
+    push(rec);
+    Rec fin{};
+    fin.op.kind = OP_DOTFIN;
+    EwPart& f = fin.op.e;
+    f.x = part; f.z = out; f.count = units; f.s0 = scale; f.p0 = accumulate;
+    fin.op.units = 1;
+    fin.rd[fin.nrd++] = range(part, (size_t)units * 8);
+    if (accumulate) fin.rd[fin.nrd++] = range(out, 8);
+    fin.wr[fin.nwr++] = range(out, 8);
+    push(fin);
+  }
+
   int spd(const SpdBatch& b, int count, int nmax) {
+    flush();
+    if (err) return 1;
     const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + (size_t)SPD_NB * nmax) * sizeof(double);
     if (smem > 227 * 1024 || nmax > 256) {
       rt::set_error("small stage: rank %d exceeds the in-shared-memory Cholesky limit (232)", nmax); return 2; }
-    static size_t configured = 0;
-    if (smem > configured) {
-      if (cudaFuncSetAttribute(spd_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-        rt::set_error("small stage: cannot raise shared memory to %zu", smem); return 1; }
-      configured = smem;
-    }
+    if (cudaFuncSetAttribute(spd_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      rt::set_error("small stage: cannot raise shared memory to %zu", smem); return 1; }
     spd_blocked_kernel<<<count, SPD_THREADS, smem, s>>>(b); ++rt::g_launches;
     return 0;
   }
 };
 
 int finish(Ctx& c, const char* what) {
+  c.flush();
   if (c.err) { rt::set_error("%s: kernel launch failed", what); return 1; }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { rt::set_error("%s: %s", what, cudaGetErrorString(e)); return 1; }
@@ -292,9 +443,9 @@ extern "C" int rt_small_prepare(const float* core, int r0, int r1, int r2, int s
     b.p[i].n = d[i];
     nmax = d[i] > nmax ? d[i] : nmax;
   }
+  c.dot(C64, DT_F64, C64, DT_F64, c.L.c, 1.0, c.p(c.L.coresq), 0);
   int rc = c.spd(b, 3, nmax);
   if (rc) return rc;
-  c.dot<double, double>(C64, C64, c.L.c, 1.0, c.p(c.L.coresq), 0);
   return finish(c, "rt_small_prepare");
 }
 
@@ -327,44 +478,33 @@ extern "C" int rt_small_grad(const float* core, const float* d_core, const float
                              double* P_O, void* small_ws, void* stream) {
   RT_REQUIRE(small_ws != nullptr && B > 0, "rt_small_grad: bad arguments");
   Ctx c{make_layout(r0, r1, r2, B), (char*)small_ws, (cudaStream_t)stream};
-  cudaStream_t s = c.s;
-  {
-    int blocks = (int)((c.L.c + 255) / 256); if (blocks > 1184) blocks = 1184;
-    grad_core_kernel<<<blocks, 256, 0, s>>>(d_core, core, hyper, dS_g, c.L.c); ++rt::g_launches;
-  }
+  // dS_g = d_core + 2 reg core
+  c.ew(EW_GRAD_CORE, d_core, DT_F32, c.L.c * 4, core, c.L.c * 4, dS_g, DT_F32, c.L.c * 4, c.L.c, 1.0, hyper, 0.0, nullptr,
+       0, 0, 0, 0, false, 32);
   // loss_total = bce_sum * inv_count + reg * ||core||^2
   c.axpby(bce_sum, c.p(c.L.coresq), loss_total, 1, inv_count, nullptr, 1.0, hyper + 1);
-  int rc;
-  if ((rc = rt_rows_times_ainv(dr_rows, B, 0, r0, r1, r2, drA, small_ws, stream))) return rc;
-  if ((rc = rt_rows_times_ainv(ds_rows, B, 1, r0, r1, r2, dsA, small_ws, stream))) return rc;
-  void* gws = c.base + c.L.gram_ws;
-  // P_i = -(U_i^T g_i A_i): the Gram of the gathered rows with the A-scaled gradient rows
-  if ((rc = rt_gram(r_rows, r0, drA, r0, B, r0, r0, P_R, 0, gws, stream))) return rc;
-  c.axpby(P_R, nullptr, P_R, (int64_t)r0 * r0, -1.0, nullptr, 0.0, nullptr);
-  if ((rc = rt_gram(s_rows, r1, dsA, r1, B, r1, r1, P_S, 0, gws, stream))) return rc;
-  double* tmp = c.p(c.L.tmpK[2]);
-  if ((rc = rt_gram(H, r2, qp, r2, B, r2, r2, sym ? tmp : P_O, 0, gws, stream))) return rc;
+  // drA = dr_rows A_R^-1, dsA = ds_rows A_S^-1   (fp32 rows times the fp64 inverses of rt_small_prepare)
+  auto rows_ainv = [&](const float* rows, int mode, float* out) {
+    const int r = c.r(mode);
+    c.gemm_any(rows, DT_F32, c.p(c.L.Ainv[mode]), DT_F64, out, DT_F32, B, r, 1, r, r, 0, 1, 0, r, 1, r, 1, 1, 0, 0, 0,
+               1.0, 0.0);
+  };
+  rows_ainv(dr_rows, 0, drA);
+  rows_ainv(ds_rows, 1, dsA);
+  // P_i = -(U_i^T g_i A_i): the Gram of the gathered rows with the A-scaled gradient rows (contraction over the batch)
+  auto gram_rows = [&](const float* X, const float* Y, int r, double* out, double alpha, double beta) {
+    c.gemm_any(X, DT_F32, Y, DT_F32, out, DT_F64, r, r, 1, B, 1, 0, r, 0, r, 1, r, 1, 1, 0, 0, 0, alpha, beta);
+  };
+  gram_rows(r_rows, drA, r0, P_R, -1.0, 0.0);
+  gram_rows(s_rows, dsA, r1, P_S, -1.0, 0.0);
   if (sym) {
-    c.axpby(P_S, tmp, P_S, (int64_t)r1 * r1, -1.0, nullptr, -1.0, nullptr);
+    gram_rows(H, qp, r2, P_S, -1.0, 1.0);
     if (P_O && P_O != P_S) c.axpby(P_S, nullptr, P_O, (int64_t)r1 * r1, 1.0, nullptr, 0.0, nullptr);
   } else {
-    c.axpby(P_S, nullptr, P_S, (int64_t)r1 * r1, -1.0, nullptr, 0.0, nullptr);
-    c.axpby(P_O, nullptr, P_O, (int64_t)r2 * r2, -1.0, nullptr, 0.0, nullptr);
+    gram_rows(H, qp, r2, P_O, -1.0, 0.0);
   }
   return finish(c, "rt_small_grad");
 }
-
-namespace {
-__global__ void norm_finish_kernel(const double* sq, const double* hyper, double* norm_out,
-                                   double* alpha_out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    const double nrm = sqrt(fmax(sq[0], 0.0));
-    norm_out[0] = nrm;
-    const double ng = hyper[3];
-    alpha_out[0] = (ng != 0.0) ? ng / nrm : 1.0;
-  }
-}
-}  // namespace
 
 extern "C" int rt_small_norm(const float* dS_g, const double* gram_R, const double* gram_S,
                              const double* gram_O, const double* hyper, int r0, int r1, int r2, int sym,
@@ -372,11 +512,11 @@ extern "C" int rt_small_norm(const float* dS_g, const double* gram_R, const doub
   RT_REQUIRE(small_ws != nullptr, "rt_small_norm: workspace is NULL");
   Ctx c{make_layout(r0, r1, r2, 0), (char*)small_ws, (cudaStream_t)stream};
   double* sq = c.p(c.L.scal);
-  c.dot<float, float>(dS_g, dS_g, c.L.c, 1.0, sq, 0);
-  c.dot<double, double>(gram_R, c.p(c.L.Gm[0]), (int64_t)r0 * r0, 1.0, sq, 1);
-  c.dot<double, double>(gram_S, c.p(c.L.Gm[1]), (int64_t)r1 * r1, 1.0, sq, 1);
-  if (!sym) c.dot<double, double>(gram_O, c.p(c.L.Gm[2]), (int64_t)r2 * r2, 1.0, sq, 1);
-  norm_finish_kernel<<<1, 32, 0, c.s>>>(sq, hyper, norm_out, alpha_out); ++rt::g_launches;
+  c.dot(dS_g, DT_F32, dS_g, DT_F32, c.L.c, 1.0, sq, 0);
+  c.dot(gram_R, DT_F64, c.p(c.L.Gm[0]), DT_F64, (int64_t)r0 * r0, 1.0, sq, 1);
+  c.dot(gram_S, DT_F64, c.p(c.L.Gm[1]), DT_F64, (int64_t)r1 * r1, 1.0, sq, 1);
+  if (!sym) c.dot(gram_O, DT_F64, c.p(c.L.Gm[2]), DT_F64, (int64_t)r2 * r2, 1.0, sq, 1);
+  c.norm_finish(sq, hyper, norm_out, alpha_out);
   return finish(c, "rt_small_norm");
 }
 
@@ -438,9 +578,7 @@ extern "C" int rt_small_project(const float* core, const float* core_old, const 
   const int nm = sym ? 2 : 3;
   for (int i = 0; i < nm; ++i) {
     // K_i = beta * KC_i Ainv_i ;  L_i = -M_i K_i
-    double* tk = c.p(c.L.tmpK[i]);
-    c.matmul(KC[i], d[i], false, c.p(c.L.Ainv[i]), d[i], false, tk, d[i], 2 * d[i], d[i], d[i], 1.0, 0.0);
-    c.axpby(tk, nullptr, Kout[i], 2 * (int64_t)d[i] * d[i], 1.0, hyper + 2, 0.0, nullptr);
+    c.matmul(KC[i], d[i], false, c.p(c.L.Ainv[i]), d[i], false, Kout[i], d[i], 2 * d[i], d[i], d[i], 1.0, 0.0, hyper + 2);
     c.matmul(M[i], 2 * d[i], false, Kout[i], d[i], false, Lout[i], d[i], d[i], d[i], 2 * d[i], -1.0, 0.0);
   }
   if (sym && K_O && K_O != K_S) {
@@ -466,17 +604,14 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
   double* C = c.p(c.L.C64);
   // C' = core - lr dS_dir
   double* Cp = c.T(0);
-  {
-    int blocks = (int)((c.L.c + 255) / 256); if (blocks > 1184) blocks = 1184;
-    core_minus_lr_kernel<<<blocks, 256, 0, s>>>(core, dS_dir, lr, Cp, c.L.c); ++rt::g_launches;
-  }
+  c.ew(EW_CORE_MINUS_LR, core, DT_F32, c.L.c * 4, dS_dir, c.L.c * 4, Cp, DT_F64, c.L.c * 8, c.L.c, 1.0, lr, 0.0, nullptr);
   // Gamma_i = lr^2 Gram_i = L_i L_i^T ; R_i = L_i^T
   SpdBatch b{};
   int nmax = 0;
   const int nm = sym ? 2 : 3;
   for (int i = 0; i < nm; ++i) {
     const int n2 = d[i] * d[i];
-    scale_mat_kernel<<<cdiv(n2, 256), 256, 0, s>>>(gram[i], c.p(c.L.Gs[i]), n2, 1.0, lr, 1); ++rt::g_launches;
+    c.cvt(gram[i], DT_F64, c.p(c.L.Gs[i]), DT_F64, n2, 1.0, lr, true);
     b.p[i].G = c.p(c.L.Gs[i]); b.p[i].L = c.p(c.L.GL[i]); b.p[i].Linv = c.p(c.L.GLinv[i]);
     b.p[i].Ginv = nullptr; b.p[i].n = d[i];
     nmax = d[i] > nmax ? d[i] : nmax;
@@ -492,15 +627,16 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
   double* Nn[3] = {c.p(c.L.Nn[0]), c.p(c.L.Nn[1]), c.p(c.L.Nn[2])};
   for (int i = 0; i < 3; ++i) {
     const int n = 2 * d[i];
-    RT_CHECK_CUDA(cudaMemsetAsync(Nn[i], 0, sizeof(double) * n * n, s));
+    c.zero64(Nn[i], (int64_t)n * n);
     c.unfold_gram(i, Cp, d, Cp, d[i], Nn[i], n, 1.0, 0.0);
     for (int j = 0; j < 3; ++j)
       if (j != i) c.unfold_gram(i, Bk[j], d, Bk[j], d[i], Nn[i], n, 1.0, 1.0);
     c.unfold_gram(i, Bk[i], d, Cp, d[i], Nn[i] + (int64_t)d[i] * n, n, 1.0, 0.0);
     c.unfold_gram(i, Bk[i], d, Bk[i], d[i], Nn[i] + (int64_t)d[i] * n + d[i], n, 1.0, 0.0);
-    symmetrize_lower_kernel<<<cdiv(n * n, 256), 256, 0, s>>>(Nn[i], n); ++rt::g_launches;
+    c.symmetrize_lower(Nn[i], n);
   }
   if (sym) c.axpby(Nn[1], Nn[2], Nn[1], 4 * (int64_t)d[1] * d[1], 1.0, nullptr, 1.0, nullptr);
+  c.flush();
   if (c.err) return finish(c, "rt_small_retract");
   if (hosvd_route() == 1) {
     const double* Ain[3]; int nn[3]; int rr[3]; int ldy[3]; double* Yv[3]; void* sws[3];
@@ -527,9 +663,7 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
   float* Yf[3];
   for (int i = 0; i < 3; ++i) Yf[i] = reinterpret_cast<float*>(c.p(c.L.tmpM[i]));
   for (int i = 0; i < nm; ++i) {
-    const int total = 2 * d[i] * d[i];
-    f64_to_f32_strided_kernel<<<cdiv(total, 256), 256, 0, s>>>(Y[i], 2 * d[i], Yf[i], d[i], 2 * d[i], d[i]);
-    ++rt::g_launches;
+    c.copy2d(Y[i], DT_F64, 2 * d[i], Yf[i], DT_F32, d[i], 2 * d[i], d[i]);
   }
   if (sym) Yf[2] = Yf[1];
   const float* Wa[3]; const float* Wb[3]; int64_t st_o[3], st_i[3];
@@ -542,14 +676,12 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
   float* Dn = c.Tf(6); float* E1 = c.Tf(6) + c.L.c; float* E2 = c.Tf(7); float* U1n = c.Tf(7) + c.L.c;
   // U2 reuses E1 (dead once U1 exists), the result reuses D
   grouped_contract<float>(c, CpF, Cb, Wa, Wb, st_o, st_i, Dn, E1, E2, U1n, E1, Dn);
-  RT_CHECK_CUDA(cudaMemcpyAsync(core_new, Dn, sizeof(float) * c.L.c, cudaMemcpyDeviceToDevice, s));
+  c.cvt(Dn, DT_F32, core_new, DT_F32, c.L.c);
   // Z1_i = Y_ia ; Z2_i = -lr * L_i^-T Y_ib
   for (int i = 0; i < nm; ++i) {
     const int64_t n = 2 * d[i];
-    c.matmul(Linv[i], d[i], true, Y[i] + (int64_t)d[i] * n, n, false, c.p(c.L.tmpK[i]), d[i], d[i], d[i], d[i], -1.0, 0.0);
-    c.axpby(c.p(c.L.tmpK[i]), nullptr, Z2[i], (int64_t)d[i] * d[i], 1.0, lr, 0.0, nullptr);
-    RT_CHECK_CUDA(cudaMemcpy2DAsync(Z1[i], sizeof(double) * d[i], Y[i], sizeof(double) * n,
-                                    sizeof(double) * d[i], d[i], cudaMemcpyDeviceToDevice, s));
+    c.matmul(Linv[i], d[i], true, Y[i] + (int64_t)d[i] * n, n, false, Z2[i], d[i], d[i], d[i], d[i], -1.0, 0.0, lr);
+    c.copy2d(Y[i], DT_F64, n, Z1[i], DT_F64, d[i], d[i], d[i]);
   }
   // Transport Grams of the NEXT fit() without touching N-sized data: with U^T U = I and
   // U^T dV = 0,  U_new^T [U | dV] = [Z1^T | Z2^T (dV^T dV)]   (r_i x 2 r_i)
@@ -557,8 +689,7 @@ extern "C" int rt_small_retract(const float* core, const float* dS_dir, const do
   for (int i = 0; i < nm; ++i) {
     if (!Mn[i]) continue;
     const int64_t n2 = 2 * d[i];
-    transpose_into_kernel<<<cdiv(d[i] * d[i], 256), 256, 0, s>>>(Z1[i], d[i], Mn[i], n2);
-    ++rt::g_launches;
+    c.transpose_into(Z1[i], d[i], Mn[i], n2);
     c.matmul(Z2[i], d[i], true, gram[i], d[i], false, Mn[i] + d[i], n2, d[i], d[i], d[i], 1.0, 0.0);
   }
   if (sym && Z1_O && Z1_O != Z1_S) {

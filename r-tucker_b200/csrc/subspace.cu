@@ -96,21 +96,31 @@ __device__ __forceinline__ void tile_nt(const double* __restrict__ A, int lda, i
   const double* pa = A + (int64_t)(i0 + g) * lda + k0 + t;
   const double* pb = B + (int64_t)(j0 + g) * ldb + k0 + t;
   const int64_t sa = (int64_t)8 * lda, sb = (int64_t)8 * ldb;
-  double a[4], b[4], an[4], bn[4];
-#pragma unroll
-  for (int x = 0; x < 4; ++x) { a[x] = __ldcg(pa + x * sa); b[x] = __ldcg(pb + x * sb); }
+  // three register buffers: the loads of step s + 2 are in flight while step s is multiplied (an L2 round trip is
+  // longer than the 16 DMMAs of one step)
+  double a0[4], b0[4], a1[4], b1[4], a2[4], b2[4];
   const int steps = kw / 4;
-  for (int s = 0; s < steps; ++s) {
-    if (s + 1 < steps) {
+  auto load = [&](int st, double (&ra)[4], double (&rb)[4]) {
 #pragma unroll
-      for (int x = 0; x < 4; ++x) { an[x] = __ldcg(pa + x * sa + 4 * (s + 1)); bn[x] = __ldcg(pb + x * sb + 4 * (s + 1)); }
-    }
+    for (int x = 0; x < 4; ++x) { ra[x] = __ldcg(pa + x * sa + 4 * st); rb[x] = __ldcg(pb + x * sb + 4 * st); }
+  };
+  auto mma = [&](const double (&ra)[4], const double (&rb)[4]) {
 #pragma unroll
     for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
-      for (int tj = 0; tj < 4; ++tj) sub_dmma(c[ti][tj][0], c[ti][tj][1], a[ti], b[tj]);
-#pragma unroll
-    for (int x = 0; x < 4; ++x) { a[x] = an[x]; b[x] = bn[x]; }
+      for (int tj = 0; tj < 4; ++tj) sub_dmma(c[ti][tj][0], c[ti][tj][1], ra[ti], rb[tj]);
+  };
+  load(0, a0, b0);
+  if (steps > 1) load(1, a1, b1);
+  for (int st = 0; st < steps; st += 3) {
+    if (st + 2 < steps) load(st + 2, a2, b2);
+    mma(a0, b0);
+    if (st + 1 >= steps) break;
+    if (st + 3 < steps) load(st + 3, a0, b0);
+    mma(a1, b1);
+    if (st + 2 >= steps) break;
+    if (st + 4 < steps) load(st + 4, a1, b1);
+    mma(a2, b2);
   }
   double* mine = red + warp * (ST * SLD);
 #pragma unroll
@@ -190,9 +200,10 @@ subspace_kernel(SubBatch batch) {
     }
   }
   sub_barrier(batch.bar, bar_target);
-  double trace[kSubMaxProblems];
-  int state[kSubMaxProblems], iters[kSubMaxProblems], ns_iters[kSubMaxProblems], cur[kSubMaxProblems], zcur[kSubMaxProblems];
-  bool ns_last[kSubMaxProblems];
+  // per-problem state: identical in every CTA (same inputs, same order of operations), kept in shared memory
+  __shared__ double trace[kSubMaxProblems];
+  __shared__ int state[kSubMaxProblems], iters[kSubMaxProblems], ns_iters[kSubMaxProblems], cur[kSubMaxProblems],
+      zcur[kSubMaxProblems], ns_last[kSubMaxProblems];
   for (int pi = 0; pi < count; ++pi) {
     const SubProblem& P = batch.p[pi];
     double f2 = 0.0, tr = 0.0;
@@ -207,8 +218,10 @@ subspace_kernel(SubBatch batch) {
     }
     const double fro = sqrt(f2);
     const double inv = fro > 0.0 ? 1.0 / fro : 0.0;
-    trace[pi] = tr * inv;
-    state[pi] = S_TC2; iters[pi] = 0; ns_iters[pi] = 0; cur[pi] = 0; zcur[pi] = 0; ns_last[pi] = false;
+    if (tid == 0) {
+      trace[pi] = tr * inv;
+      state[pi] = S_TC2; iters[pi] = 0; ns_iters[pi] = 0; cur[pi] = 0; zcur[pi] = 0; ns_last[pi] = 0;
+    }
     // X_0 = N / ||N||_F, zero padded
     const int np = P.np;
     for (int e = gtid; e < np * np; e += nthreads) {
@@ -253,6 +266,12 @@ subspace_kernel(SubBatch batch) {
         sym_tile(lu, T, ti, tj);
         const double* X = P.X[cur[pi]];
         double* Xn = P.X[cur[pi] ^ 1];
+        double xo[4];                      // this thread's entries of X_k (for 2 X - X^2), fetched behind the product
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int e = tid + kSubThreads * m;
+          xo[m] = __ldcg(&X[(int64_t)(ti * ST + (e >> 5)) * np + tj * ST + (e & 31)]);
+        }
         tile_nt(X, np, ti * ST, X, np, tj * ST, np, ssm, acc);
         const bool square = trace[pi] > (double)P.r;
         double trc = 0.0;
@@ -262,7 +281,7 @@ subspace_kernel(SubBatch batch) {
           const int i = ti * ST + (e >> 5), j = tj * ST + (e & 31);
           const double c = acc[m];
           if (ti == tj && i == j) trc += c;
-          const double v = square ? c : 2.0 * __ldcg(&X[(int64_t)i * np + j]) - c;
+          const double v = square ? c : 2.0 * xo[m] - c;
           Xn[(int64_t)i * np + j] = v;
           if (ti != tj) Xn[(int64_t)j * np + i] = v;
         }
@@ -305,13 +324,19 @@ subspace_kernel(SubBatch batch) {
       } else if (state[pi] == S_NSZ) {
         const int ti = lu / Tr, tj = lu - ti * Tr;
         const double* Z = P.Z[zcur[pi]];
+        double zo[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int e = tid + kSubThreads * m;
+          zo[m] = __ldcg(&Z[(int64_t)(ti * ST + (e >> 5)) * rp + tj * ST + (e & 31)]);
+        }
         tile_nt(Z, rp, ti * ST, P.G, rp, tj * ST, rp, ssm, acc);
-        const bool last = ns_last[pi];
+        const bool last = ns_last[pi] != 0;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           const int e = tid + kSubThreads * m;
           const int i = ti * ST + (e >> 5), j = tj * ST + (e & 31);
-          const double v = 1.5 * __ldcg(&Z[(int64_t)i * rp + j]) - 0.5 * acc[m];
+          const double v = 1.5 * zo[m] - 0.5 * acc[m];
           if (last) {
             if (i < P.n && j < P.r) P.Y_out[(int64_t)i * P.ldy + j] = v;
           } else {
@@ -322,38 +347,51 @@ subspace_kernel(SubBatch batch) {
       }
     }
     sub_barrier(batch.bar, bar_target);
-    // ---- state update: every CTA reads the same slots and takes the same decisions ----
-    for (int pi = 0; pi < count; ++pi) {
-      const SubProblem& P = batch.p[pi];
-      const int T = P.np / ST, Tr = P.rp / ST;
-      const double* slots = P.slots + par * kSlotsPerProblem;
-      if (state[pi] == S_TC2) {
-        const double trc = slot_sum(slots, T);
-        const double tr = trace[pi];
-        const double idem = tr - trc;                       // tr X_k - tr X_k^2 = sum lambda (1 - lambda) >= 0
-        trace[pi] = (tr > (double)P.r) ? trc : 2.0 * tr - trc;
-        cur[pi] ^= 1;
-        ++iters[pi];
-        const bool conv = idem < 1e-11 && fabs(tr - (double)P.r) < 0.25;
-        if (conv || iters[pi] >= kTc2MaxIter) state[pi] = S_COPY;
-      } else if (state[pi] == S_COPY) {
-        state[pi] = S_NSG;
-      } else if (state[pi] == S_NSG) {
-        const double err2 = slot_sum(slots, Tr * (Tr + 1) / 2);
-        ++ns_iters[pi];
-        // quadratic convergence: a defect below 1e-6 becomes ~1e-12 (rounding level) after one more update
-        ns_last[pi] = (err2 < 1e-12) || ns_iters[pi] >= kNsMaxIter;
-        state[pi] = S_NSZ;
-      } else if (state[pi] == S_NSZ) {
-        if (ns_last[pi]) {
-          state[pi] = S_DONE;
-          if (gtid == 0 && P.info) { P.info[0] = iters[pi]; P.info[1] = ns_iters[pi]; }
-        } else {
-          zcur[pi] ^= 1;
-          state[pi] = S_NSG;
+    // ---- state update: every CTA reads the same slots and takes the same decisions (warp 0, then broadcast
+    //      through shared memory) ----
+    if (tid < 32) {
+      for (int pi = 0; pi < count; ++pi) {
+        const SubProblem& P = batch.p[pi];
+        const int T = P.np / ST, Tr = P.rp / ST;
+        const double* slots = P.slots + par * kSlotsPerProblem;
+        const int st = state[pi];
+        if (st == S_TC2) {
+          const double trc = slot_sum(slots, T);
+          const double tr = trace[pi];
+          const double idem = tr - trc;                       // tr X_k - tr X_k^2 = sum lambda (1 - lambda) >= 0
+          const bool conv = idem < 1e-11 && fabs(tr - (double)P.r) < 0.25;
+          __syncwarp();
+          if (tid == 0) {
+            trace[pi] = (tr > (double)P.r) ? trc : 2.0 * tr - trc;
+            cur[pi] ^= 1;
+            ++iters[pi];
+            if (conv || iters[pi] >= kTc2MaxIter) state[pi] = S_COPY;
+          }
+        } else if (st == S_COPY) {
+          if (tid == 0) state[pi] = S_NSG;
+        } else if (st == S_NSG) {
+          const double err2 = slot_sum(slots, Tr * (Tr + 1) / 2);
+          if (tid == 0) {
+            ++ns_iters[pi];
+            // quadratic convergence: a defect below 1e-6 becomes ~1e-12 (rounding level) after one more update
+            ns_last[pi] = ((err2 < 1e-12) || ns_iters[pi] >= kNsMaxIter) ? 1 : 0;
+            state[pi] = S_NSZ;
+          }
+        } else if (st == S_NSZ) {
+          if (tid == 0) {
+            if (ns_last[pi]) {
+              state[pi] = S_DONE;
+              if (blockIdx.x == 0 && P.info) { P.info[0] = iters[pi]; P.info[1] = ns_iters[pi]; }
+            } else {
+              zcur[pi] ^= 1;
+              state[pi] = S_NSG;
+            }
+          }
         }
+        __syncwarp();
       }
     }
+    __syncthreads();
     ++round;
   }
 }
