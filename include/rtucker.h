@@ -219,6 +219,14 @@ int rt_small_grad(const float* core, const float* d_core, const float* qp, const
 int rt_small_norm(const float* dS_g, const double* gram_R, const double* gram_S, const double* gram_O,
                   const double* hyper, int r0, int r1, int r2, int sym,
                   double* norm_out, double* alpha_out, void* small_ws, void* stream);
+/* Same for SFTuckerAdam (src/model/symmetric/optim.py:110-167): adam = device state
+ * [v, ratio_prev, step_t, beta1, beta2, eps, step_velocity, -] (fp64, updated in place); alpha_out becomes
+ * (1 - beta1) / ratio and hyper[2] (the momentum coefficient rt_small_project reads) beta1 * ratio_prev / ratio,
+ * ratio = (1 - beta1^e) sqrt(v / (1 - beta2^e)) + eps, e = step_t // step_velocity + 1 (optim.py:139-144).
+ * The kept tangent is the step DIRECTION; the reference's momentum is ratio_prev times it (transport is linear). */
+int rt_small_norm_adam(const float* dS_g, const double* gram_R, const double* gram_S, const double* gram_O,
+                       double* hyper, double* adam, int r0, int r1, int r2, int sym,
+                       double* norm_out, double* alpha_out, void* small_ws, void* stream);
 /*
  * rt_small_project: projection of the previous direction (tangent at the OLD point) onto the
  * tangent space at the current point -- TuckerRiemannian.project at asymmetric/optim.py:86.
@@ -248,6 +256,16 @@ int rt_small_retract(const float* core, const float* dS_dir,
                      float* core_new, double* Z1_R, double* Z2_R, double* Z1_S, double* Z2_S,
                      double* Z1_O, double* Z2_O, double* Mn_R, double* Mn_S, double* Mn_O,
                      void* small_ws, void* stream);
+
+/*
+ * rt_epoch_batch: assemble batch [lo, lo + B) of a device-resident epoch (csrc/epoch.cu): the items are
+ * perm[lo + b] (int64, e.g. torch.randperm on the device: the shuffle of DataLoader(shuffle=True), train.py:227);
+ * feat_all [Q, feat_cols] int32 are the (s, r[, o]) rows, (off_all [Q+1], idx_all) the CSR of their target lists
+ * (what KG_dataset.__getitem__ builds densely, src/data/Dataset.py:42-53).  Outputs: feat_out [B, feat_cols],
+ * off_out [B+1], idx_out [cap] (cap >= the largest possible batch; lists are truncated at cap).  No host sync.
+ */
+int rt_epoch_batch(const int64_t* perm, int lo, int B, const int* feat_all, int feat_cols, const int* off_all,
+                   const int* idx_all, int* feat_out, int* off_out, int* idx_out, int cap, void* stream);
 
 /* Symmetric eigen-decomposition (block Jacobi, fp64), exposed for testing:
  * A[n,n] (destroyed) -> eigenvalues w[n] descending, eigenvectors V[n,n] (columns). */

@@ -16,6 +16,7 @@ Reference lines each stage follows:
   project             asymmetric/optim.py:86, symmetric/optim.py:80
   retract             asymmetric/optim.py:106-109 (construct().round(rank))
   RSGDState.fit/step  asymmetric/optim.py:74-114, symmetric/optim.py:23-107
+  AdamState.fit/step  symmetric/optim.py:110-167 (SFTuckerAdam)
 
 Conventions: modes are (relation, subject, object) (train.py:37-42); ``sym=True``
 means SF-Tucker with subject and object modes sharing the factor ``E``.
@@ -315,4 +316,56 @@ class RSGDState:
         new = retract(self.x, self.direction, lr)
         self.old = self.x
         self.x = new
+        return new
+
+
+class AdamState:
+    """Analytic twin of SFTuckerAdam (symmetric/optim.py:110-167); the same update on the Tucker manifold when
+    ``x.sym`` is False.  The gradient is NOT normalised (fit's normalize_grad argument is unused upstream).
+
+    ``live_point_quirk``.  In the reference the stored momentum is a TangentVector whose ``point`` wraps the LIVE
+    parameters (train.py:37-42 builds the point around ``param.data`` without copying) and ``momentum.construct()``
+    is only evaluated in the NEXT fit (optim.py:136), after step() has overwritten the parameters in place
+    (optim.py:163-165).  The ambient tensor that gets projected is then built from the OLD deltas (dS, dV) and the
+    NEW core / factors -- unlike RSGDwithMomentum, which constructs before the write-back (asymmetric/optim.py:109).
+    That tensor depends on the GAUGE of the new point (sign / rotation conventions of the SVD inside ``round``), so
+    the reference's Adam trajectory is not a function of the tensors alone and cannot be matched by any retraction
+    with another (equivalent) gauge.  ``live_point_quirk=True`` reproduces it exactly when the twin is re-seeded with
+    the reference's own (core, factors) before every step (tests/test_oracle_analytic.py::
+    test_live_reference_sftucker_adam); the default ``False`` transports the momentum as the ambient tensor at the
+    point where it was formed -- the gauge-invariant update the CUDA engine implements."""
+
+    def __init__(self, x: Point, betas=(0.9, 0.999), eps=1e-8, step_velocity=1, live_point_quirk=False):
+        self.x = x
+        self.betas, self.eps, self.step_velocity = betas, eps, step_velocity
+        self.live_point_quirk = live_point_quirk
+        self.momentum: Optional[Tangent] = None
+        self.momentum_point: Optional[Point] = None
+        self.second_momentum = 0.0
+        self.step_t = 1
+        self.loss = None
+
+    def fit(self, rel_idx, sub_idx, tgt_off, tgt_idx, label_smoothing, reg):
+        b1, b2 = self.betas
+        g, self.loss, self.inter = riemannian_grad(self.x, rel_idx, sub_idx, tgt_off, tgt_idx, label_smoothing, reg)
+        norm = tangent_norm(self.x, g)
+        if self.momentum is not None:                                   # optim.py:135-137
+            base = self.x if self.live_point_quirk else self.momentum_point
+            transported = project(self.x, base, self.momentum)
+            self.momentum = axpby(b1, transported, 1 - b1, g)
+        else:                                                           # optim.py:139
+            self.momentum = axpby(1 - b1, g, 0.0, None)
+        self.momentum_point = self.x
+        self.second_momentum = b2 * self.second_momentum + (1 - b2) * float(norm) ** 2          # optim.py:140
+        e = self.step_t // self.step_velocity + 1
+        corrected = self.second_momentum / (1 - b2 ** e)                                        # optim.py:141
+        ratio = (1 - b1 ** e) * corrected ** 0.5 + self.eps                                     # optim.py:142-144
+        self.ratio = ratio
+        self.direction = axpby(1.0 / ratio, self.momentum, 0.0, None)                           # optim.py:145
+        return norm
+
+    def step(self, lr):
+        new = retract(self.x, self.direction, lr)                                               # optim.py:157-161
+        self.x = new
+        self.step_t += 1                                                                        # optim.py:167
         return new

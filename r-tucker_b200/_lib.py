@@ -51,9 +51,11 @@ PROTOTYPES = {
     "rt_rows_times_ainv": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "rt_small_grad": (i32, [vp] * 9 + [f64, vp, i32, i32, i32, i32, i32] + [vp] * 9),
     "rt_small_norm": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "rt_small_norm_adam": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "rt_small_project": (i32, [vp] * 7 + [i32, i32, i32, i32] + [vp] * 9),
     "rt_core_axpby": (i32, [vp, vp, vp, i32, vp, vp]),
     "rt_small_retract": (i32, [vp] * 6 + [i32, i32, i32, i32] + [vp] * 12),
+    "rt_epoch_batch": (i32, [vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, i32, vp]),
     "rt_eigh_ws_bytes": (sz, [i32]),
     "rt_eigh": (i32, [vp, i32, vp, vp, vp, vp]),
     "rt_dominant_subspace_ws_bytes": (sz, [i32, i32]),

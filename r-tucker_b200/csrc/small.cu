@@ -343,6 +343,18 @@ struct Ctx {
     rec.wr[rec.nwr++] = range(alpha_out, 8);
     push(rec);
   }
+  void adam_finish(const double* sq, double* hyper, double* adam, double* norm_out, double* alpha_out) {
+    if (err) return;
+    Rec rec{};
+    rec.op.kind = OP_EW; rec.op.ew = EW_ADAM_FINISH; rec.op.units = 1;
+    EwPart& e = rec.op.e;
+    e.x = sq; e.y = alpha_out; e.z = norm_out; e.d0 = hyper; e.d1 = adam; e.count = 1;
+    rec.rd[rec.nrd++] = range(sq, 8);
+    rec.rd[rec.nrd++] = range(adam, 64);
+    rec.wr[rec.nwr++] = range(norm_out, 8);
+    rec.wr[rec.nwr++] = range(alpha_out, 8);
+    push(rec);
+  }
   void zero64(double* z, int64_t n) { ew(EW_ZERO64, nullptr, DT_F64, 0, nullptr, 0, z, DT_F64, n * 8, n, 0.0, nullptr, 0.0, nullptr); }
 
   // out[0] = (accumulate ? out[0] : 0) + scale * sum x[i] y[i]   (deterministic two-stage sum)
@@ -506,18 +518,34 @@ extern "C" int rt_small_grad(const float* core, const float* d_core, const float
   return finish(c, "rt_small_grad");
 }
 
-extern "C" int rt_small_norm(const float* dS_g, const double* gram_R, const double* gram_S,
-                             const double* gram_O, const double* hyper, int r0, int r1, int r2, int sym,
-                             double* norm_out, double* alpha_out, void* small_ws, void* stream) {
-  RT_REQUIRE(small_ws != nullptr, "rt_small_norm: workspace is NULL");
+static int small_norm_impl(const float* dS_g, const double* gram_R, const double* gram_S, const double* gram_O,
+                           double* hyper, double* adam, int r0, int r1, int r2, int sym, double* norm_out,
+                           double* alpha_out, void* small_ws, void* stream) {
   Ctx c{make_layout(r0, r1, r2, 0), (char*)small_ws, (cudaStream_t)stream};
   double* sq = c.p(c.L.scal);
   c.dot(dS_g, DT_F32, dS_g, DT_F32, c.L.c, 1.0, sq, 0);
   c.dot(gram_R, DT_F64, c.p(c.L.Gm[0]), DT_F64, (int64_t)r0 * r0, 1.0, sq, 1);
   c.dot(gram_S, DT_F64, c.p(c.L.Gm[1]), DT_F64, (int64_t)r1 * r1, 1.0, sq, 1);
   if (!sym) c.dot(gram_O, DT_F64, c.p(c.L.Gm[2]), DT_F64, (int64_t)r2 * r2, 1.0, sq, 1);
-  c.norm_finish(sq, hyper, norm_out, alpha_out);
+  if (adam) c.adam_finish(sq, hyper, adam, norm_out, alpha_out);
+  else c.norm_finish(sq, hyper, norm_out, alpha_out);
   return finish(c, "rt_small_norm");
+}
+
+extern "C" int rt_small_norm(const float* dS_g, const double* gram_R, const double* gram_S,
+                             const double* gram_O, const double* hyper, int r0, int r1, int r2, int sym,
+                             double* norm_out, double* alpha_out, void* small_ws, void* stream) {
+  RT_REQUIRE(small_ws != nullptr, "rt_small_norm: workspace is NULL");
+  return small_norm_impl(dS_g, gram_R, gram_S, gram_O, const_cast<double*>(hyper), nullptr, r0, r1, r2, sym, norm_out,
+                         alpha_out, small_ws, stream);
+}
+
+extern "C" int rt_small_norm_adam(const float* dS_g, const double* gram_R, const double* gram_S,
+                                  const double* gram_O, double* hyper, double* adam, int r0, int r1, int r2, int sym,
+                                  double* norm_out, double* alpha_out, void* small_ws, void* stream) {
+  RT_REQUIRE(small_ws != nullptr && adam != nullptr, "rt_small_norm_adam: NULL argument");
+  return small_norm_impl(dS_g, gram_R, gram_S, gram_O, hyper, adam, r0, r1, r2, sym, norm_out, alpha_out, small_ws,
+                         stream);
 }
 
 extern "C" int rt_small_project(const float* core, const float* core_old, const float* dS_old,

@@ -36,6 +36,8 @@ enum EwKind : int {
   EW_TRANSPOSE_INTO,   // z[a, b] (ld p1) = x[b, a] (ld p0) for an n x n fp64 matrix, n = p2
   EW_SYMM_LOWER,       // z[i, j] = z[j, i] for j > i (n = p2, ld = p0), fp64 in place
   EW_ZERO64,           // z[i] = 0 (fp64)
+  EW_ADAM_FINISH,      // SFTuckerAdam coefficients (symmetric/optim.py:133-145): x = ||g||^2, y = alpha out, z = norm out,
+                       // d0 = hyper (hyper[2] <- momentum coefficient), d1 = adam state (updated in place)
   EW_NORM_FINISH,      // z[0] = sqrt(max(x[0], 0)); y[0] = d0[3] != 0 ? d0[3] / z[0] : 1   (z = norm, y = alpha: both outputs)
 };
 
@@ -224,6 +226,25 @@ __device__ __forceinline__ void reduce_unit(const GemmPart& op, int unit) {
 
 __device__ __forceinline__ void ew_unit(const EwPart& op, int ew, int unit) {
   const int64_t base = (int64_t)unit * kEwChunk;
+  if (ew == EW_ADAM_FINISH) {
+    if (threadIdx.x == 0) {
+      double* st = const_cast<double*>(op.d1);          // [v, ratio_prev, t, beta1, beta2, eps, step_velocity, -]
+      double* hyper = const_cast<double*>(op.d0);
+      const double sq = fmax(__ldcg(reinterpret_cast<const double*>(op.x)), 0.0);
+      const double nrm = sqrt(sq);
+      const double v = __ldcg(st + 0), ratio_prev = __ldcg(st + 1), t = __ldcg(st + 2);
+      const double b1 = __ldcg(st + 3), b2 = __ldcg(st + 4), eps = __ldcg(st + 5), vel = __ldcg(st + 6);
+      const double vn = b2 * v + (1.0 - b2) * sq;
+      const double e = floor(t / vel) + 1.0;            // step_t // step_velocity + 1
+      const double vhat = vn / (1.0 - pow(b2, e));
+      const double ratio = (1.0 - pow(b1, e)) * sqrt(vhat) + eps;
+      reinterpret_cast<double*>(op.z)[0] = nrm;
+      reinterpret_cast<double*>(const_cast<void*>(op.y))[0] = (1.0 - b1) / ratio;   // direction = momentum / ratio
+      hyper[2] = b1 * ratio_prev / ratio;               // momentum_{k-1} = ratio_{k-1} * direction_{k-1}
+      st[0] = vn; st[1] = ratio; st[2] = t + 1.0;
+    }
+    return;
+  }
   if (ew == EW_NORM_FINISH) {
     if (threadIdx.x == 0) {
       const double nrm = sqrt(fmax(__ldcg(reinterpret_cast<const double*>(op.x)), 0.0));

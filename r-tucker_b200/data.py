@@ -11,6 +11,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
+from . import ops
 from .engine import SparseTargets
 
 
@@ -91,3 +92,99 @@ def from_reference_data(data, split, test_set=False, label_smoothing=0.0):
     rows = getattr(data, f"{split}_data")
     return SparseKGDataset(ids(rows), len(data.entities), all_triples=ids(data.data) if test_set else None,
                            test_set=test_set, label_smoothing=label_smoothing)
+
+
+class DeviceEpoch:
+    """A split resident in HBM, iterated without host work.
+
+    Stands where the reference builds ``DataLoader(KG_dataset(...), batch_size, shuffle, drop_last, num_workers=6,
+    pin_memory=True)`` (train.py:226-236): the (s, r[, o]) rows and the CSR of target lists are uploaded once
+    (WN18RR train: 2.2 MB instead of 84 MB per batch), every epoch draws a permutation and each batch is assembled on
+    the device by ``rt_epoch_batch``.  Iterating yields ``(features int32 [B, 2|3], SparseTargets)``.
+
+    ``shuffle``: "device" (torch.randperm on the device: no host work at all), "host" (the reference's own draw:
+    RandomSampler seeds a CPU generator from the global one and calls torch.randperm, so identical seeds give the
+    reference's batches; the permutation is uploaded once per epoch), or False.
+    """
+
+    def __init__(self, dataset: SparseKGDataset, batch_size, device, shuffle="device", drop_last=False, seed=None):
+        self.dataset = dataset
+        self.batch_size = int(batch_size)
+        self.device = torch.device(device)
+        self.shuffle = shuffle
+        self.drop_last = bool(drop_last)
+        self.label_smoothing = dataset.label_smoothing
+        self.n_entities = dataset.n_entities
+        self.feat = torch.from_numpy(np.ascontiguousarray(dataset.features)).to(self.device)
+        self.off = torch.from_numpy(dataset.off.astype(np.int32)).to(self.device)
+        self.idx = torch.from_numpy(np.ascontiguousarray(dataset.idx)).to(self.device)
+        self.counts_dev = torch.from_numpy(dataset.counts.astype(np.int64)).to(self.device)
+        top = np.sort(dataset.counts)[-self.batch_size:].sum() if len(dataset) else 0
+        self.cap = max(int(top), 16)            # no batch can hold more targets than the B longest lists
+        self.gen = None
+        if shuffle == "device":
+            self.gen = torch.Generator(device=self.device)
+            self.gen.manual_seed(int(seed) if seed is not None else int(torch.initial_seed()) & 0x7FFFFFFF)
+        self.last_perm = None
+
+    def __len__(self):
+        n = len(self.dataset)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def num_items(self):
+        n = len(self.dataset)
+        return n - n % self.batch_size if self.drop_last else n
+
+    def permutation(self):
+        n = len(self.dataset)
+        if self.shuffle == "device":
+            return torch.randperm(n, device=self.device, generator=self.gen)
+        if self.shuffle == "host":
+            # torch.utils.data.RandomSampler.__iter__: seed drawn from the global generator, then randperm
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())
+            g = torch.Generator()
+            g.manual_seed(seed)
+            return torch.randperm(n, generator=g).to(self.device, non_blocking=True)
+        return torch.arange(n, device=self.device)
+
+    def __iter__(self):
+        perm = self.permutation()
+        self.last_perm = perm
+        n, B = self.num_items(), self.batch_size
+        i32 = torch.int32
+        fc = self.feat.shape[1]
+        for lo in range(0, n, B):
+            b = min(B, n - lo)
+            out = (torch.empty(b, fc, dtype=i32, device=self.device), torch.empty(b + 1, dtype=i32, device=self.device),
+                   torch.empty(self.cap, dtype=i32, device=self.device))
+            ops.epoch_batch(perm, lo, b, self.feat, self.off, self.idx, out)
+            yield out[0], SparseTargets(out[1], out[2])
+
+    def triples_in_epoch(self):
+        """Number of (s, r, o) targets the last iterated epoch covered (device tensor, no sync)."""
+        perm = self.last_perm if self.last_perm is not None else torch.arange(len(self.dataset), device=self.device)
+        return self.counts_dev[perm[: self.num_items()]].sum()
+
+
+def wn18rr_fixture(path=None):
+    """The real WN18RR triples as ids in the reference's vocabulary order (tests/golden/wn18rr_ids.npz, written by
+    tests/golden/make_golden.py from the reference's Data(reverse=True)); None when the fixture is absent."""
+    import os
+    if path is None:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        path = os.path.join(root, "tests", "golden", "wn18rr_ids.npz")
+    if not os.path.isfile(path):
+        return None
+    d = np.load(path)
+    return dict(n_entities=int(d["n_entities"]), n_relations=int(d["n_relations"]),
+                train=d["train"], valid=d["valid"], test=d["test"])
+
+
+def datasets_from_ids(ids, label_smoothing=0.1):
+    """(train, valid, test) SparseKGDataset of an id-triple dictionary (wn18rr_fixture): what train.py:226-228 builds."""
+    allt = np.concatenate([ids["train"], ids["valid"], ids["test"]])
+    n = ids["n_entities"]
+    train = SparseKGDataset(ids["train"], n, label_smoothing=label_smoothing)
+    valid = SparseKGDataset(ids["valid"], n, all_triples=allt, test_set=True)
+    test = SparseKGDataset(ids["test"], n, all_triples=allt, test_set=True)
+    return train, valid, test

@@ -47,7 +47,7 @@ class Direction:
 class StepEngine:
     def __init__(self, core, factors: List[torch.Tensor], sym: bool, batch_size: int,
                  momentum_beta: Optional[float], group=None, n_total: Optional[int] = None,
-                 n_begin: int = 0, score_variant: int = 0, ops=None):
+                 n_begin: int = 0, score_variant: int = 0, ops=None, adam=None):
         """core: Parameter [r0,r1,r2]; factors: [R, S, O] Parameters (sym: [R, E]); entity factors
         hold rows [n_begin, n_begin + n_local) of the global n_total entities."""
         self.ops = ops if ops is not None else cuda_ops
@@ -70,6 +70,12 @@ class StepEngine:
         self.dev = dev
         self.small = self.ops.SmallStage(self.rank, self.B, self.sym, dev)
         self.hyper = torch.zeros(4, dtype=f64, device=dev)
+        # SFTuckerAdam (symmetric/optim.py:110-167): device-side scalar state [v, ratio_prev, t, beta1, beta2, eps,
+        # step_velocity, has_momentum]; the kept tangent is the step direction, the momentum is ratio_prev times it
+        self.adam = None
+        if adam is not None:
+            b1, b2, eps, vel = adam
+            self.adam = torch.tensor([0.0, 1.0, 1.0, b1, b2, eps, float(vel), 0.0], dtype=f64).to(dev)
         self._hyper_host = None
         self._hyper_vals = None
         # Every state buffer has a FIXED address for the life of the engine (the step is CUDA-graph
@@ -201,7 +207,8 @@ class StepEngine:
         # ---- norm of the Riemannian gradient ----
         grams = [ops.gram(v, v) for v in dV_g]
         self._allreduce(*[grams[k] for k in self._entity_factor_ids()])
-        norm, alpha = small.norm(dS_g, grams[0], grams[1], grams[2] if not sym else grams[1], self.hyper)
+        norm, alpha = small.norm(dS_g, grams[0], grams[1], grams[2] if not sym else grams[1], self.hyper,
+                                 adam=self.adam)
         # ---- momentum: transport the previous direction, then combine ----
         use_momentum = self.beta is not None and self.has_old
         dV_new = self.dV_new
@@ -266,6 +273,50 @@ class StepEngine:
             self.core.data.copy_(core_new)
         self.pending = None
         return self.core.data
+
+    # -------------------------------------------------------------------------------------------
+    # Checkpoint / resume (reference: StateDict.save / load, src/utils/storage.py:61-83, train.py:154-159 -- which drop
+    # the optimiser state; here the kept direction, its base point and the transport Grams are part of the state, so
+    # a resumed run continues the uninterrupted trajectory bit for bit).  Per rank: the rows this rank owns.
+    def state_dict(self):
+        keep = self.beta is not None
+
+        def c(t):
+            return None if t is None else t.detach().cpu().clone()
+        return {
+            "version": 1, "sym": self.sym, "rank": tuple(self.rank), "beta": self.beta,
+            "n_begin": self.n_begin, "n_local": self.n_local, "n_total": self.n_total,
+            "has_old": bool(self.has_old), "hyper_vals": self._hyper_vals,
+            "U_old": [c(t) for t in self.U_old] if keep else None,
+            "dV_dir": [c(t) for t in self.dV_dir] if keep else None,
+            "core_old": c(self.core_old), "dS_dir_old": c(self.dS_dir_old),
+            "M_next": [c(t) for t in self.M_next[: self.nf]] if keep else None,
+            "adam": c(self.adam),
+        }
+
+    def load_state_dict(self, sd):
+        if sd.get("version") != 1 or bool(sd["sym"]) != self.sym or tuple(sd["rank"]) != tuple(self.rank):
+            raise ValueError("engine state does not match this model (manifold / rank)")
+        if (sd["n_begin"], sd["n_local"], sd["n_total"]) != (self.n_begin, self.n_local, self.n_total):
+            raise ValueError("engine state belongs to a different entity shard")
+        if (sd["beta"] is None) != (self.beta is None):
+            raise ValueError("engine state belongs to a different optimiser (momentum / no momentum)")
+        if self.beta is not None and sd["has_old"]:
+            for k in range(self.nf):            # copies INTO the fixed buffers: captured graphs stay valid
+                self.U_old[k].copy_(sd["U_old"][k])
+                self.dV_dir[k].copy_(sd["dV_dir"][k])
+                self.M_next[k].copy_(sd["M_next"][k])
+            self.core_old.copy_(sd["core_old"])
+            self.dS_dir_old.copy_(sd["dS_dir_old"])
+        self.has_old = bool(sd["has_old"])
+        if self.adam is not None and sd.get("adam") is not None:
+            self.adam.copy_(sd["adam"])
+        if sd.get("hyper_vals") is not None:
+            self._hyper_vals = None
+            self._set_hyper(*sd["hyper_vals"])
+        self.pending = None
+        self._eager_steps = 0
+        self._graphs = {}
 
     # -------------------------------------------------------------------------------------------
     # CUDA-graph front end: same arithmetic, replayed from two captured graphs (fit, step).

@@ -252,8 +252,15 @@ class SmallStage:
                                   ptr(P_S), ptr(P_O), ptr(self.ws), stream_ptr()), "rt_small_grad")
         return dS_g, loss, drA, dsA, P_R, P_S, P_O
 
-    def norm(self, dS_g, gram_R, gram_S, gram_O, hyper):
+    def norm(self, dS_g, gram_R, gram_S, gram_O, hyper, adam=None):
+        """(||rgrad||, alpha): alpha = normalize / ||rgrad|| (RGD / RSGD, optim.py:92).  With ``adam`` (device state of
+        SFTuckerAdam) alpha and hyper[2] (the momentum coefficient rt_small_project reads) become the Adam ones."""
         out = torch.empty(2, dtype=f64, device=self.device)
+        if adam is not None:
+            check(lib().rt_small_norm_adam(ptr(dS_g), ptr(gram_R), ptr(gram_S), ptr(gram_O), ptr(hyper), ptr(adam),
+                                           *self._r(), self.sym, ptr(out[0:1]), ptr(out[1:2]), ptr(self.ws),
+                                           stream_ptr()), "rt_small_norm_adam")
+            return out[0:1], out[1:2]
         check(lib().rt_small_norm(ptr(dS_g), ptr(gram_R), ptr(gram_S), ptr(gram_O), ptr(hyper), *self._r(),
                                   self.sym, ptr(out[0:1]), ptr(out[1:2]), ptr(self.ws), stream_ptr()),
               "rt_small_norm")
@@ -298,6 +305,18 @@ def eigh(A):
     ws = _ws(lib().rt_eigh_ws_bytes(n), A.device)
     check(lib().rt_eigh(ptr(A), n, ptr(w), ptr(V), ptr(ws), stream_ptr()), "rt_eigh")
     return w, V
+
+
+def epoch_batch(perm, lo, B, feat_all, off_all, idx_all, out):
+    """Assemble batch [lo, lo+B) of the device-resident epoch into ``out`` = (feat [B,fc], off [B+1], idx [cap]),
+    all int32 device tensors; ``perm`` int64 device permutation.  No host synchronisation."""
+    require_cuda(perm, feat_all, off_all, idx_all, *out)
+    feat, off, idx = out
+    assert perm.dtype == torch.int64 and perm.is_contiguous()
+    check(lib().rt_epoch_batch(ptr(perm), int(lo), int(B), ptr(_c(feat_all, i32)), feat_all.shape[1],
+                               ptr(_c(off_all, i32)), ptr(_c(idx_all, i32)), ptr(_c(feat, i32)), ptr(_c(off, i32)),
+                               ptr(_c(idx, i32)), idx.shape[0], stream_ptr()), "rt_epoch_batch")
+    return out
 
 
 def dominant_subspace(A, r):

@@ -2,6 +2,8 @@
 
   asymmetric  RGD, RSGDwithMomentum   src/model/asymmetric/optim.py:10-57, 60-114   params [core, S, R, O]
   symmetric   RGD, RSGDwithMomentum   src/model/symmetric/optim.py:11-59, 62-107    params [core, E, R]
+              SFTuckerAdam            src/model/symmetric/optim.py:110-167 (also offered on the Tucker manifold as
+                                      ``asymmetric.TuckerAdam``; train.py:187,191 import both as ``RiemannianAdam``)
 
 Kept: torch.optim.Optimizer subclasses (OneCycleLR drives param_groups[0]["lr"], train.py:213-215),
 ``fit(loss_fn, x_k, normalize_grad=1.) -> ||rgrad||``, ``step(closure=None)``, attributes ``loss``,
@@ -34,6 +36,8 @@ class _RiemannianBase(Optimizer):
     symmetric = False
     uses_momentum = False
 
+    adam = None            # (beta1, beta2, eps, step_velocity) for the Adam subclasses
+
     def __init__(self, params, rank, max_lr, momentum_beta: Optional[float] = None, group=None,
                  n_total=None, n_begin=0, score_variant=0, ops=None, use_graphs=False):
         self.rank = rank
@@ -48,6 +52,7 @@ class _RiemannianBase(Optimizer):
         self.momentum = None
         self.loss = None
         self._engine = None
+        self._pending_engine_state = None
         self._use_graphs = bool(use_graphs)
         self._engine_kw = dict(group=group, n_total=n_total, n_begin=n_begin, score_variant=score_variant,
                                ops=ops)
@@ -64,12 +69,36 @@ class _RiemannianBase(Optimizer):
         if self._engine is None:
             core, factors = self._manifold_params()
             self._engine = StepEngine(core, factors, self.symmetric, max(B, 1),
-                                      self.momentum_beta if self.uses_momentum else None, **self._engine_kw)
+                                      self.momentum_beta if self.uses_momentum else None, adam=self.adam,
+                                      **self._engine_kw)
             self._engine.use_graphs = self._use_graphs
+            if self._pending_engine_state is not None:
+                self._engine.load_state_dict(self._pending_engine_state)
+                self._pending_engine_state = None
         elif B > self._engine.small.B:
+            # a larger batch needs a larger workspace: every captured graph holds the OLD workspace's address
+            # (fit and step alike), so all of them are dropped with it
             eng = self._engine
+            eng._graphs.clear()
             eng.small = eng.ops.SmallStage(eng.rank, B, eng.sym, eng.dev)
         return self._engine
+
+    # -- checkpoint / resume with the optimiser state (reference: train.py:154 collects optimizer.state_dict() and
+    #    storage.py:70-78 then drops it; RSGD's direction is not in it at all) --------------------------------------
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["rtucker_engine"] = self._engine.state_dict() if self._engine is not None else self._pending_engine_state
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        eng_state = state_dict.pop("rtucker_engine", None)
+        super().load_state_dict(state_dict)
+        if eng_state is not None:
+            if self._engine is not None:
+                self._engine.load_state_dict(eng_state)
+            else:
+                self._pending_engine_state = eng_state     # applied when the engine is built (first fit)
 
     def fit(self, loss_fn, x_k=None, normalize_grad=1.):
         """Riemannian gradient of ``loss_fn`` at the current parameters and the step direction
@@ -80,6 +109,8 @@ class _RiemannianBase(Optimizer):
                 "in place of the reference's loss lambda: there is no autodiff / dense-target path.")
         sf = loss_fn.score_fn
         eng = self._get_engine(sf.relation_idx.shape[0])
+        if self.adam is not None:
+            normalize_grad = 0.0       # SFTuckerAdam.fit never normalises (its normalize_grad argument is unused)
         norm = eng.fit_auto(sf.relation_idx, sf.subject_idx, loss_fn.targets, loss_fn.label_smoothing,
                             loss_fn.reg_coeff, lr_hint=self.param_groups[0]["lr"], normalize_grad=normalize_grad)
         self.loss = eng.loss.float().reshape(())
@@ -119,3 +150,27 @@ class SymRSGDwithMomentum(_RiemannianBase):
 
     def __init__(self, params, rank, max_lr, momentum_beta=0.9, **kw):
         super().__init__(params, rank, max_lr, momentum_beta, **kw)
+
+
+class _AdamMixin:
+    """SFTuckerAdam (src/model/symmetric/optim.py:110-167): momentum = beta1 * transport(momentum) + (1 - beta1) * rgrad,
+    scalar second moment of ||rgrad||^2, direction = momentum / ((1 - beta1^e) sqrt(v / (1 - beta2^e)) + eps) with
+    e = step_t // step_velocity + 1; the coefficients are evaluated on the device (rt_small_norm_adam)."""
+    uses_momentum = True
+
+    def __init__(self, params, rank, max_lr, betas=(0.9, 0.999), eps=1e-8, step_velocity=1, **kw):
+        self.betas, self.eps, self.step_velocity = betas, eps, step_velocity
+        self.adam = (float(betas[0]), float(betas[1]), float(eps), float(step_velocity))
+        super().__init__(params, rank, max_lr, float(betas[0]), **kw)
+
+    @property
+    def step_t(self):
+        return 1 if self._engine is None else int(self._engine.adam[2].item())
+
+
+class SFTuckerAdam(_AdamMixin, _RiemannianBase):
+    symmetric = True
+
+
+class TuckerAdam(_AdamMixin, _RiemannianBase):
+    symmetric = False

@@ -154,11 +154,19 @@ class SmallStage:
             P_O = P_S
         return dS_g, loss, drA, dsA, P_R, P_S, P_O
 
-    def norm(self, dS_g, gram_R, gram_S, gram_O, hyper):
+    def norm(self, dS_g, gram_R, gram_S, gram_O, hyper, adam=None):
         sq = (dS_g.double() ** 2).sum() + (gram_R * self.Gm[0]).sum() + (gram_S * self.Gm[1]).sum()
         if not self.sym:
             sq = sq + (gram_O * self.Gm[2]).sum()
         nrm = torch.sqrt(sq).reshape(1)
+        if adam is not None:      # rt_small_norm_adam: symmetric/optim.py:139-145, state updated in place
+            v, ratio_prev, t, b1, b2, eps, vel = (float(x) for x in adam[:7])
+            vn = b2 * v + (1 - b2) * float(sq)
+            e = t // vel + 1
+            ratio = (1 - b1 ** e) * (vn / (1 - b2 ** e)) ** 0.5 + eps
+            hyper[2] = b1 * ratio_prev / ratio
+            adam[0], adam[1], adam[2] = vn, ratio, t + 1
+            return nrm, torch.full((1,), (1 - b1) / ratio, dtype=f64)
         ng = float(hyper[3])
         alpha = (ng / nrm) if ng != 0.0 else torch.ones(1, dtype=f64)
         return nrm, alpha

@@ -12,6 +12,9 @@
                           a clean target): per-step loss, ||rgrad||, final dense tensor
   dataset_wn18rr.npz      reference Data + KG_dataset (src/data) on the real WN18RR files: first items of
                           the train / valid sets as (features, sorted target ids)
+  wn18rr_ids.npz          the real WN18RR triples as integer ids in the reference's vocabulary order
+                          (Data(reverse=True): sorted entities / relations, reverse triples appended per split)
+                          -- the data the GPU box trains and evaluates on (bench.py, tests, tools/train_wn18rr.py)
 Usage: python tests/golden/make_golden.py
 """
 import os
@@ -148,7 +151,22 @@ def dataset():
     np.savez_compressed(os.path.join(HERE, "dataset_wn18rr.npz"), **out)
 
 
+def wn18rr_ids():
+    ns = ref_harness.load("asymmetric", "rsgd")
+    data = ns.Data(os.path.join(ref_harness.REF_DIR, "data", "WN18RR"), reverse=True)
+    ent = {e: i for i, e in enumerate(data.entities)}
+    rel = {r: i for i, r in enumerate(data.relations)}
+    out = dict(n_entities=len(data.entities), n_relations=len(data.relations))
+    for split in ("train", "valid", "test"):
+        rows = getattr(data, f"{split}_data")
+        out[split] = np.asarray([(ent[a], rel[b], ent[c]) for a, b, c in rows], dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, "wn18rr_ids.npz"), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "wn18rr":
+        wn18rr_ids()
+        sys.exit(0)
     scores("asymmetric")
     scores("symmetric")
     ranking()
@@ -156,4 +174,5 @@ if __name__ == "__main__":
     steps("symmetric", "rsgd")
     steps("symmetric", "rgd")
     dataset()
+    wn18rr_ids()
     print("golden fixtures written to", HERE)

@@ -1,0 +1,302 @@
+"""GPU tests of the rows SURVEY.md section 8 marks "next": device-resident epochs (f1), the epoch driver (f2),
+SFTuckerAdam and asymmetric RGD (f3), checkpoint / resume with the optimiser state (f4), and the real-data
+trajectory against the reference-step fixture (north_star: reference quality on identical seeds)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util
+
+pytestmark = pytest.mark.gpu
+f64 = torch.float64
+
+
+def synthetic_ids(n_ent=600, n_rel=8, n_train=4000, seed=3):
+    g = np.random.default_rng(seed)
+    def tri(n):
+        return np.stack([g.integers(0, n_ent, n), g.integers(0, n_rel, n), g.integers(0, n_ent, n)], 1).astype(np.int32)
+    return dict(n_entities=n_ent, n_relations=n_rel, train=tri(n_train), valid=tri(300), test=tri(300))
+
+
+def make_model(mod, n_ent, n_rel, rank, dev, scale=400.0, seed=5):
+    torch.manual_seed(seed)
+    model = mod.R_TuckER((n_ent, n_rel), rank)
+    model.init(None)
+    with torch.no_grad():
+        model.core.mul_(scale)
+    return model.to(dev)
+
+
+def params_of(model):
+    return [model.core, model.E.weight, model.R.weight] if model.symmetric else \
+        [model.core, model.S.weight, model.R.weight, model.O.weight]
+
+
+def test_device_epoch_equals_host_batches(cuda_device):
+    """rt_epoch_batch against SparseKGDataset.host_batch (itself pinned on the reference KG_dataset): same
+    features, offsets and target ids for full and ragged batches, identity and shuffled order."""
+    from rtucker_b200.data import DeviceEpoch, datasets_from_ids
+    tr, va, _ = datasets_from_ids(synthetic_ids(), 0.1)
+    for ds, B in ((tr, 128), (va, 97)):
+        ep = DeviceEpoch(ds, B, cuda_device, shuffle=False, drop_last=False)
+        n = 0
+        for k, (feat, tg) in enumerate(ep):
+            items = np.arange(k * B, min((k + 1) * B, len(ds)))
+            f, off, idx = ds.host_batch(items)
+            assert np.array_equal(feat.cpu().numpy(), f)
+            assert np.array_equal(tg.off.cpu().numpy(), off)
+            assert np.array_equal(tg.idx.cpu().numpy()[: off[-1]], idx)
+            n += len(items)
+        assert n == len(ds) and k + 1 == len(ep)
+    ep = DeviceEpoch(tr, 128, cuda_device, shuffle="device", drop_last=True, seed=11)
+    seen = []
+    for feat, tg in ep:
+        perm = ep.last_perm.cpu().numpy()
+        items = perm[len(seen) * 128: (len(seen) + 1) * 128]
+        f, off, idx = tr.host_batch(items)
+        assert np.array_equal(feat.cpu().numpy(), f) and np.array_equal(tg.idx.cpu().numpy()[: off[-1]], idx)
+        seen.append(items)
+    assert len(seen) == len(tr) // 128 and len(np.unique(np.concatenate(seen))) == 128 * len(seen)
+    assert int(ep.triples_in_epoch()) == tr.num_triples(np.concatenate(seen))
+    # the reference's own shuffle: RandomSampler's draws from the global CPU generator
+    torch.manual_seed(77)
+    host = DeviceEpoch(tr, 128, cuda_device, shuffle="host", drop_last=True)
+    p1 = host.permutation().cpu()
+    torch.manual_seed(77)
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    g = torch.Generator()
+    g.manual_seed(seed)
+    assert torch.equal(p1, torch.randperm(len(tr), generator=g))
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_adam_step_parity(cuda_device, sym):
+    """SFTuckerAdam / TuckerAdam on the CUDA engine against the analytic twin (oracle/analytic.py::AdamState, pinned
+    on the reference's class): every step is taken from the device state, 1e-5."""
+    import analytic as A
+    from rtucker_b200 import asymmetric, symmetric
+    from rtucker_b200.engine import SparseTargets
+    from rtucker_b200.optim import FusedLoss
+    from test_gpu_step import make_batch, probes
+    A.ELEMENTWISE_FP32 = True
+    dev = cuda_device
+    N, M, rank, B = 1500, 12, (6, 40, 40), 64
+    mod = symmetric if sym else asymmetric
+    model = make_model(mod, N, M, rank, dev, scale=300.0)
+    betas, eps, lr = (0.9, 0.99), 1e-8, 30.0
+    opt = mod.RiemannianAdam(params_of(model), rank, lr, betas=betas, eps=eps)
+    g = torch.Generator().manual_seed(21)
+
+    def dev_point():
+        fs = [p.data.double().cpu() for p in model.factor_params()]
+        return A.Point(model.core.data.double().cpu(), [fs[0], fs[1], fs[1] if sym else fs[2]], sym)
+
+    st = A.AdamState(dev_point(), betas=betas, eps=eps)
+    for it in range(4):
+        rel, sub, off, idx = make_batch(N, M, B, g)
+        eng = opt._engine
+        st.x = dev_point()
+        if eng is not None and eng.has_old:     # the kept direction at its own point; momentum = ratio_prev * it
+            ofs = [u.double().cpu() for u in eng.U_old]
+            dvs = [v.double().cpu() for v in eng.dV_dir]
+            ratio_prev = float(eng.adam[1])
+            st.momentum_point = A.Point(eng.core_old.double().cpu(), [ofs[0], ofs[1], ofs[1] if sym else ofs[2]], sym)
+            st.momentum = A.axpby(ratio_prev, A.Tangent(eng.dS_dir_old.double().cpu(),
+                                                        [dvs[0], dvs[1], dvs[1] if sym else dvs[2]]), 0.0, None)
+            st.second_momentum, st.step_t = float(eng.adam[0]), int(eng.adam[2])
+        n_ref = st.fit(rel, sub, off, idx, 0.1, 1e-9)
+        x_ref = st.step(lr)
+        loss_fn = FusedLoss(model(sub.to(dev), rel.to(dev)), SparseTargets(off.int().to(dev), idx.int().to(dev)), 0.1, 1e-9)
+        n_dev = opt.fit(loss_fn, None)
+        opt.step()
+        torch.cuda.synchronize()
+        assert abs(float(n_dev.cpu()) - float(n_ref)) / float(n_ref) < 1e-5
+        assert abs(float(opt.loss.cpu()) - float(st.loss)) / float(st.loss) < 1e-5
+        pr = probes(x_ref, torch.Generator().manual_seed(it))
+        assert float((pr(dev_point()) - pr(x_ref)).norm() / pr(x_ref).norm()) < 1e-5, it
+    assert opt.step_t == 5
+
+
+def test_asymmetric_rgd_step_parity(cuda_device):
+    """asymmetric RGD (the reference's step is broken, asymmetric/optim.py:49-57; the documented update is
+    X <- round(X - lr * g / ||g||)): through the optimiser class against the analytic oracle with beta = None."""
+    import analytic as A
+    from rtucker_b200 import asymmetric
+    from rtucker_b200.engine import SparseTargets
+    from rtucker_b200.optim import FusedLoss
+    from test_gpu_step import make_batch, probes
+    A.ELEMENTWISE_FP32 = True
+    dev = cuda_device
+    N, M, rank, B = 2000, 22, (10, 48, 48), 96
+    model = make_model(asymmetric, N, M, rank, dev, scale=500.0)
+    opt = asymmetric.RGD(params_of(model), rank, 40.0)
+    g = torch.Generator().manual_seed(8)
+    for it in range(3):
+        rel, sub, off, idx = make_batch(N, M, B, g)
+        fs = [p.data.double().cpu() for p in model.factor_params()]
+        st = A.RSGDState(A.Point(model.core.data.double().cpu(), fs, False), None)
+        n_ref = st.fit(rel, sub, off, idx, 0.1, 1e-9)
+        x_ref = st.step(40.0)
+        n_dev = opt.fit(FusedLoss(model(sub.to(dev), rel.to(dev)), SparseTargets(off.int().to(dev), idx.int().to(dev)),
+                                  0.1, 1e-9), None)
+        opt.step()
+        assert abs(float(n_dev.cpu()) - float(n_ref)) / float(n_ref) < 1e-5
+        fs = [p.data.double().cpu() for p in model.factor_params()]
+        pr = probes(x_ref, torch.Generator().manual_seed(it))
+        assert float((pr(A.Point(model.core.data.double().cpu(), fs, False)) - pr(x_ref)).norm() / pr(x_ref).norm()) < 1e-5
+
+
+@pytest.mark.parametrize("kind,use_graphs", [("asym-rsgd", True), ("sym-rgd", False), ("sym-adam", True)])
+def test_checkpoint_resume_is_bitwise(cuda_device, tmp_path, kind, use_graphs):
+    """checkpoint.save / load (model + optimiser incl. kept direction, transport Grams, Adam moments + scheduler):
+    the resumed run reproduces the uninterrupted trajectory bit for bit, also through CUDA graphs
+    (reference: storage.py:61-83, train.py:154-159 lose the optimiser state)."""
+    from rtucker_b200 import asymmetric, checkpoint, symmetric
+    from rtucker_b200.engine import SparseTargets
+    from rtucker_b200.optim import FusedLoss
+    from test_gpu_step import make_batch
+    dev = cuda_device
+    N, M, rank, B = 2000, 12, (6, 40, 40), 128
+    sym = kind.startswith("sym")
+    mod = symmetric if sym else asymmetric
+
+    def build():
+        model = make_model(mod, N, M, rank, dev, scale=800.0)
+        p = params_of(model)
+        if kind.endswith("adam"):
+            opt = mod.RiemannianAdam(p, rank, 20.0, use_graphs=use_graphs, score_variant=2)
+        elif kind.endswith("rgd"):
+            opt = mod.RGD(p, rank, 50.0, use_graphs=use_graphs)
+        else:
+            opt = mod.RSGDwithMomentum(p, rank, 50.0, 0.8, use_graphs=use_graphs, score_variant=2)
+        sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=60.0, total_steps=20, pct_start=0.3, div_factor=5.5,
+                                                    cycle_momentum=False, anneal_strategy="linear")
+        return model, opt, sched
+
+    g = torch.Generator().manual_seed(9)
+    batches = [make_batch(N, M, B, g) for _ in range(8)]
+
+    def run(model, opt, sched, bs):
+        for rel, sub, off, idx in bs:
+            loss_fn = FusedLoss(model(sub.to(dev), rel.to(dev)), SparseTargets(off.int().to(dev), idx.int().to(dev)), 0.1, 1e-9)
+            opt.fit(loss_fn, None)
+            opt.step()
+            sched.step()
+        torch.cuda.synchronize()
+
+    m1, o1, s1 = build()
+    run(m1, o1, s1, batches)
+    m2, o2, s2 = build()
+    run(m2, o2, s2, batches[:4])
+    path = os.path.join(tmp_path, "snapshot.pth")
+    checkpoint.save(path, m2, o2, s2, last_epoch=4)
+    m3, o3, s3 = build()
+    state = checkpoint.load(path, m3, o3, s3, map_location=dev)
+    assert state["last_epoch"] == 4 and list(state["model"].keys()) == list(m1.state_dict().keys())
+    run(m3, o3, s3, batches[4:])
+    for a, b in zip(params_of(m1), params_of(m3)):
+        assert torch.equal(a.data, b.data)
+    assert o1.param_groups[0]["lr"] == o3.param_groups[0]["lr"]
+
+
+def test_graph_path_survives_a_growing_batch(cuda_device):
+    """A batch larger than the first one replaces the small-stage workspace: every captured graph (fit AND step)
+    must be dropped with it (advisor finding, round 1).  Graphed run == eager run, bit for bit."""
+    from rtucker_b200 import asymmetric
+    from rtucker_b200.engine import SparseTargets
+    from rtucker_b200.optim import FusedLoss
+    from test_gpu_step import make_batch
+    dev = cuda_device
+    N, M, rank = 1500, 12, (6, 40, 40)
+
+    def run(use_graphs):
+        model = make_model(asymmetric, N, M, rank, dev, scale=800.0)
+        opt = asymmetric.RSGDwithMomentum(params_of(model), rank, 50.0, 0.8, use_graphs=use_graphs)
+        g = torch.Generator().manual_seed(3)
+        for B in (64, 64, 64, 160, 160, 160, 64):
+            rel, sub, off, idx = make_batch(N, M, B, g)
+            opt.fit(FusedLoss(model(sub.to(dev), rel.to(dev)), SparseTargets(off.int().to(dev), idx.int().to(dev)),
+                              0.1, 1e-9), None)
+            opt.step()
+        torch.cuda.synchronize()
+        return [p.data.clone() for p in params_of(model)]
+
+    for a, b in zip(run(False), run(True)):
+        assert torch.equal(a, b)
+
+
+def test_epoch_driver_equals_per_batch_path(cuda_device):
+    """train.train_one_epoch / train.evaluate over DeviceEpoch loaders against the per-batch host path
+    (FusedLoss per batch from SparseKGDataset.batches; evaluation.evaluate): identical parameters and metrics."""
+    from rtucker_b200 import asymmetric, train
+    from rtucker_b200.data import DeviceEpoch, datasets_from_ids
+    from rtucker_b200.evaluation import evaluate as evaluate_host
+    from rtucker_b200.optim import FusedLoss
+    dev = cuda_device
+    ids = synthetic_ids()
+    tr, va, _ = datasets_from_ids(ids, 0.1)
+    rank, B = (4, 24, 24), 128
+
+    def build():
+        model = make_model(asymmetric, ids["n_entities"], ids["n_relations"], rank, dev, scale=200.0)
+        return model, asymmetric.RSGDwithMomentum(params_of(model), rank, 30.0, 0.8, use_graphs=True)
+
+    m1, o1 = build()
+    loader = DeviceEpoch(tr, B, dev, shuffle=False, drop_last=True)
+    crit = torch.nn.BCELoss(reduction="mean")
+    loss1, norm1 = train.train_one_epoch(m1, o1, crit, loader, regularization_coeff=1e-9)
+    met1, vloss1 = train.evaluate(m1, crit, DeviceEpoch(va, 100, dev, shuffle=False))
+    m2, o2 = build()
+    losses, norms = [], []
+    for feat, tg, _, _ in tr.batches(B, dev, shuffle=False, drop_last=True):
+        n = o2.fit(FusedLoss(m2(feat[:, 0], feat[:, 1]), tg, 0.1, 1e-9), None)
+        o2.step()
+        losses.append(float(o2.loss.cpu()))
+        norms.append(float(n.cpu()))
+    met2, vloss2 = evaluate_host(m2, va, 100, dev)
+    for a, b in zip(params_of(m1), params_of(m2)):
+        assert torch.equal(a.data, b.data)
+    assert abs(loss1 - np.mean(losses)) < 1e-6 and abs(norm1 - np.mean(norms)) / np.mean(norms) < 1e-5
+    assert met1 == met2 and abs(float(vloss1) - float(vloss2)) < 1e-7
+    with pytest.raises(TypeError):
+        train.train_one_epoch(m1, o1, torch.nn.MSELoss(), loader)
+
+
+def test_wn18rr_trajectory_matches_reference_step(cuda_device):
+    """The first steps of a REAL WN18RR run (seed 322, rank (10, 200, 200), batch 512, dataset order) against
+    tests/golden/wn18rr_trajectory.npz = oracle/reference_step.py (the reference's autodiff-through-rank-2r step) in
+    fp64.  Strict fp32 path (variant 0) and the fp16-operand tensor-core path (variant 2)."""
+    from rtucker_b200 import asymmetric, train
+    from rtucker_b200.data import DeviceEpoch, datasets_from_ids, wn18rr_fixture
+    from rtucker_b200.optim import FusedLoss
+    z = golden_util.load("wn18rr_trajectory.npz")
+    ids = wn18rr_fixture()
+    tr, _, _ = datasets_from_ids(ids, float(z["ls"]))
+    dev = cuda_device
+    steps = int(z["steps"])
+    for variant, tol_loss, tol_norm in ((0, 2e-6, 2e-3), (2, 2e-5, 2e-2)):
+        np.random.seed(int(z["seed"]))
+        torch.manual_seed(int(z["seed"]))
+        rank = tuple(int(x) for x in z["rank"])
+        model = asymmetric.R_TuckER((ids["n_entities"], ids["n_relations"]), rank)
+        model.init(None)
+        model.to(dev)
+        opt = asymmetric.RSGDwithMomentum(params_of(model), rank, float(z["lr"]), float(z["beta"]), use_graphs=True,
+                                          score_variant=variant)
+        loader = DeviceEpoch(tr, int(z["batch"]), dev, shuffle=False, drop_last=True)
+        loss, norm = [], []
+        for k, (feat, tg) in enumerate(loader):
+            if k == steps:
+                break
+            n = opt.fit(FusedLoss(model(feat[:, 0], feat[:, 1]), tg, float(z["ls"]), float(z["reg"])), train.extract_tensor(model))
+            opt.step()
+            loss.append(opt.loss)
+            norm.append(n)
+        loss = torch.stack(loss).double().cpu().numpy()
+        norm = torch.stack(norm).double().cpu().numpy()
+        e_loss = np.max(np.abs(loss - z["loss"]) / np.abs(z["loss"]))
+        e_norm = np.max(np.abs(norm - z["norm"]) / np.abs(z["norm"]))
+        print(f"variant {variant}: max rel err over {steps} steps: loss {e_loss:.2e}, ||rgrad|| {e_norm:.2e}")
+        assert e_loss < tol_loss and e_norm < tol_norm, (variant, e_loss, e_norm)

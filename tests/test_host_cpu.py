@@ -99,3 +99,109 @@ def test_fit_requires_fused_loss():
                                                 cycle_momentum=False, anneal_strategy="linear")
     assert abs(opt.param_groups[0]["lr"] - 600 / 5.5) < 1e-9      # train.py:213-215 drives param_groups[0]["lr"]
     assert "lr" in opt.state_dict()["param_groups"][0] and sched is not None
+
+
+def _small_problem(sym, seed=4):
+    g = torch.Generator().manual_seed(seed)
+    N, M, rank, B = 57, 6, (3, 5, 5), 16
+    q = lambda a, b: torch.linalg.qr(torch.randn(a, b, generator=g, dtype=f64))[0].contiguous()  # noqa: E731
+    core = 25 * torch.randn(rank, generator=g, dtype=f64)
+    R, S = q(M, rank[0]), q(N, rank[1])
+    O = S if sym else q(N, rank[2])
+    batches = []
+    for _ in range(6):
+        sub, rel = torch.randint(0, N, (B,), generator=g), torch.randint(0, M, (B,), generator=g)
+        cnt = torch.randint(1, 4, (B,), generator=g)
+        off = torch.zeros(B + 1, dtype=torch.long)
+        off[1:] = cnt.cumsum(0)
+        idx = torch.cat([torch.randperm(N, generator=g)[:c].sort().values for c in cnt.tolist()])
+        batches.append((rel, sub, off, idx))
+    return N, M, rank, B, core, R, S, O, batches
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_engine_adam_matches_analytic_twin(sym):
+    """SFTuckerAdam's state machine in the engine (device-side coefficients, kept DIRECTION + ratio instead of the
+    momentum) against the analytic twin of symmetric/optim.py:110-167 (gauge-invariant transport)."""
+    import analytic as A
+    A.ELEMENTWISE_FP32 = False
+    N, M, rank, B, core, R, S, O, batches = _small_problem(sym)
+    P = torch.nn.Parameter
+    pc = P(core.clone())
+    fs = [P(R.clone()), P(S.clone())] + ([] if sym else [P(O.clone())])
+    eng = StepEngine(pc, fs, sym, B, 0.9, ops=cpu_ops, adam=(0.9, 0.99, 1e-8, 1))
+    st = A.AdamState(A.Point(core.clone(), [R.clone(), S.clone(), S.clone() if sym else O.clone()], sym),
+                     betas=(0.9, 0.99), eps=1e-8)
+    if sym:
+        st.x.factors[2] = st.x.factors[1]
+    for rel, sub, off, idx in batches[:4]:
+        n_ref = st.fit(rel, sub, off, idx, 0.1, 1e-3)
+        st.step(0.05)
+        n = eng.fit(rel.int(), sub.int(), SparseTargets(off.int(), idx.int()), 0.1, 1e-3, normalize_grad=0.0)
+        eng.step(0.05)
+        assert abs(float(n) - float(n_ref)) / float(n_ref) < 1e-8
+        assert abs(float(eng.loss) - float(st.loss)) / float(st.loss) < 1e-10
+    f = [p.data for p in fs]
+    X = A.Point(pc.data, [f[0], f[1], f[1] if sym else f[2]], sym).to_dense()
+    Xr = st.x.to_dense()
+    assert float((X - Xr).norm() / Xr.norm()) < 1e-8
+    assert int(eng.adam[2]) == st.step_t
+
+
+@pytest.mark.parametrize("sym,beta,adam", [(False, 0.8, None), (True, None, None), (True, 0.9, (0.9, 0.99, 1e-8, 1))])
+def test_engine_checkpoint_resume_is_exact(sym, beta, adam):
+    """state_dict() / load_state_dict() of the engine (kept direction, its base point, transport Grams, Adam moments,
+    hyper-parameters): a run resumed from a checkpoint equals the uninterrupted run bit for bit
+    (reference: storage.py:61-83 drops the optimiser state and cannot be loaded)."""
+    N, M, rank, B, core, R, S, O, batches = _small_problem(sym, seed=9)
+    P = torch.nn.Parameter
+
+    def make(state=None):
+        pc = P(core.clone())
+        fs = [P(R.clone()), P(S.clone())] + ([] if sym else [P(O.clone())])
+        return pc, fs, StepEngine(pc, fs, sym, B, beta, ops=cpu_ops, adam=adam)
+
+    def run(eng, bs):
+        for rel, sub, off, idx in bs:
+            eng.fit(rel.int(), sub.int(), SparseTargets(off.int(), idx.int()), 0.1, 1e-3,
+                    normalize_grad=0.0 if adam else 1.0)
+            eng.step(0.3)
+
+    pc1, fs1, e1 = make()
+    run(e1, batches)
+    pc2, fs2, e2 = make()
+    run(e2, batches[:3])
+    sd = e2.state_dict()
+    params = [pc2.data.clone()] + [p.data.clone() for p in fs2]
+    import io
+    buf = io.BytesIO()
+    torch.save({"engine": sd, "params": params}, buf)         # through serialisation, as a checkpoint file would
+    buf.seek(0)
+    ck = torch.load(buf, weights_only=False)
+    pc3, fs3, e3 = make()
+    for p, v in zip([pc3] + fs3, ck["params"]):
+        p.data.copy_(v)
+    e3.load_state_dict(ck["engine"])
+    run(e3, batches[3:])
+    assert torch.equal(pc1.data, pc3.data)
+    for a, b in zip(fs1, fs3):
+        assert torch.equal(a.data, b.data)
+    with pytest.raises(ValueError):
+        make()[2].load_state_dict({**sd, "rank": (9, 9, 9)})
+
+
+def test_wn18rr_fixture_is_the_reference_vocabulary():
+    """tests/golden/wn18rr_ids.npz (the data the GPU box trains on) against the committed reference items of
+    dataset_wn18rr.npz (KG_dataset on the real files) -- and, when the checkout is here, against Data itself."""
+    from rtucker_b200.data import datasets_from_ids, wn18rr_fixture
+    ids = wn18rr_fixture()
+    assert ids is not None and ids["n_entities"] == 40943 and ids["n_relations"] == 22
+    tr, va, te = datasets_from_ids(ids, label_smoothing=0.1)
+    z = golden_util.load("dataset_wn18rr.npz")
+    assert len(tr) == int(z["n_train_items"]) == 103509 and len(va) == int(z["n_valid_items"]) and tr.num_triples() == 173670
+    assert len(te) == 6268
+    for name, ds in (("train", tr), ("valid", va)):
+        for k, item in enumerate(z[f"{name}_items"]):
+            f, off, idx = ds.host_batch([int(item)])
+            assert f[0].tolist() == z[f"{name}_features"][k].tolist()
+            assert idx.tolist() == sorted(z[f"{name}_targets"][k].tolist())

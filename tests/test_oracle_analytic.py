@@ -139,3 +139,49 @@ def test_live_reference_optimisers(mode, opt):
         assert float((Xr - st.x.to_dense()).norm() / Xr.norm()) < 1e-10
     finally:
         torch.set_default_dtype(torch.float32)
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference checkout not present (GPU box)")
+def test_live_reference_sftucker_adam():
+    """The analytic Adam twin against the reference's unmodified SFTuckerAdam (symmetric/optim.py:110-167) in fp64.
+    The class hard-codes ``device="cuda"`` for its scalar second moment (optim.py:118): that one allocation is
+    redirected to the CPU for the comparison."""
+    A.ELEMENTWISE_FP32 = False
+    torch.set_default_dtype(f64)
+    orig_zeros = torch.zeros
+    try:
+        ns = ref_harness.load("symmetric", "rsgd")
+        torch.manual_seed(3)
+        N, M, rank, B = 57, 6, (3, 5, 5), 16
+        model = ns.R_TuckER((N, M), rank)
+        model.double()
+        model.init(None)
+        torch.zeros = lambda *a, **k: orig_zeros(*a, **{kk: vv for kk, vv in k.items() if kk != "device"})
+        o = ns.optim.SFTuckerAdam([model.core, model.E.weight, model.R.weight], rank, 0.05, betas=(0.9, 0.99), eps=1e-8)
+        torch.zeros = orig_zeros
+        fs = [model.R.weight.data.clone(), model.E.weight.data.clone(), None]
+        fs[2] = fs[1]
+        st = A.AdamState(A.Point(model.core.data.clone(), fs, True), betas=(0.9, 0.99), eps=1e-8, live_point_quirk=True)
+        g = torch.Generator().manual_seed(5)
+        crit = torch.nn.BCELoss(reduction="mean")
+        for _ in range(4):
+            # the reference's update depends on the gauge of the point (see AdamState): the twin takes every step
+            # from the reference's own (core, factors), keeping its own momentum deltas and moments
+            e = model.E.weight.data.clone()
+            st.x = A.Point(model.core.data.clone(), [model.R.weight.data.clone(), e, e], True)
+            sub, rel = torch.randint(0, N, (B,), generator=g), torch.randint(0, M, (B,), generator=g)
+            off = torch.arange(0, 2 * B + 1, 2)
+            idx = torch.randint(0, N, (2 * B,), generator=g)
+            tg = A.dense_targets(B, N, off, idx, 0.1, f64)
+            score_fn = model(sub, rel)
+            loss_fn = lambda T: crit(score_fn(T), tg) + 1e-3 * T.norm() ** 2  # noqa: E731
+            n1 = o.fit(loss_fn, ns.train.extract_tensor(model))
+            o.step()
+            n2 = st.fit(rel, sub, off, idx, 0.1, 1e-3)
+            st.step(0.05)
+            assert abs(float(n1) - float(n2)) / float(n2) < 1e-9
+        Xr = ns.train.extract_tensor(model).to_dense()
+        assert float((Xr - st.x.to_dense()).norm() / Xr.norm()) < 1e-9
+    finally:
+        torch.zeros = orig_zeros
+        torch.set_default_dtype(torch.float32)
