@@ -1,19 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- train triples/s of the R-TuckER hot path (1-N fwd + bwd + RSGD step incl. retraction)
-and filtered-eval queries/s, on a synthetic graph of WN18RR shape (BASELINE.json configs[0]/metric).
+"""bench.py -- train triples/s of the R-TuckER hot path (1-N fwd + bwd + RSGD step incl. retraction) and
+filtered-eval queries/s (BASELINE.json metric), on the REAL WN18RR triples when the id fixture is present
+(tests/golden/wn18rr_ids.npz, written from the reference's data/WN18RR by tests/golden/make_golden.py), else on a
+seeded synthetic graph of the same shape.
 
     python bench.py --gpus 1 --steps K --warmup W            # this repo's CUDA path (one JSON line)
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (port, oracle/)
     torchrun ... bench.py --gpus N ...                       # entity-sharded over NCCL (strong scaling)
 
-A step = one optimiser step (fit + step) on one batch of 512 (s,r) queries.
-`value`  : triples/s with the batches already resident in HBM (CUDA events around K steps).
-`e2e`    : same metric through the public API (model(...) -> FusedLoss -> optimizer.fit/step) with the
-           batch coming from pinned HOST memory every step and the loss read back to the host.
-`roofline`: the fused score+BCE+backward kernel (algorithmic flops 6*B*N*r2) against the measured bf16
-           tensor peak of MEASURED_PEAKS.json (FP32-FFMA variant runs on the CUDA cores; the fraction
-           says how far it is from the tensor roofline the tcgen05 variant is judged on).
-`cpu_baseline`: the reference's step (oracle/reference_step.py port) timed on this host's cores.
+A step = one optimiser step (fit + step) on one batch of 512 (s, r) queries.
+`value`       triples/s with the batches already resident in HBM (CUDA events around K steps, CUDA graphs).
+`e2e`         same metric through the public API (model(...) -> FusedLoss -> optimizer.fit/step) with the batch coming
+              from pinned HOST memory every step and the loss read back to the host every step.
+`value_strict_fp32`  the same K steps with the fp32 FFMA score kernel (variant 0: 1e-5 parity path).
+`roofline`    the kernel FAMILY with the largest share of the step; `roofline_all` lists every family (score GEMMs
+              against the tensor peak, tall-skinny passes against HBM, N-independent stage as a latency-bound
+              share, query contraction, fused eval), each with its share of ms_per_step.
+`cpu_baseline`       the reference's step (oracle/reference_step.py port) on this host's cores, bounded sample.
+`torch_gpu_baseline` the same port with CUDA tensors: stock cuBLAS / cuSOLVER / ATen on this very GPU.
+`c5`          the synthetic 1M-entity / rank-(200,200,200) workload (BASELINE configs[4]) on the same ranks: the
+              curve north_star asks for, recorded by every driver run (1/2/4/8 GPUs).
 """
 import argparse
 import json
@@ -41,6 +47,8 @@ LABEL_SMOOTHING = 0.1
 MOMENTUM = 0.8
 LR = 109.09      # OneCycleLR(max_lr=600, div_factor=5.5) at epoch 1 (train.py:213-215)
 REG = 1e-11      # configs/base_config.py:19
+SEED = 322       # README.md:45
+FFMA_PEAK_TF = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal FP32 FFMA peak at the measured max clock (74.4)
 
 
 def synth_graph(w, seed=1234):
@@ -84,9 +92,26 @@ def batch_arrays(feats, off, idx, cnt, items):
     return feats[items], boff, idx[gather]
 
 
-def init_params(w, seed=20):
+def load_workload(name):
+    """(w, graph, data_label): graph = (features [Q,2], off, idx, cnt) of the train (s, r) -> objects vocabulary.
+    The WN18RR workloads use the real triples through the package's own SparseKGDataset when the fixture exists."""
+    w = dict(WORKLOADS[name])
+    if name in ("wn18rr", "wn18rr-sym"):
+        from rtucker_b200.data import datasets_from_ids, wn18rr_fixture
+        ids = wn18rr_fixture()
+        if ids is not None:
+            train, valid, test = datasets_from_ids(ids, label_smoothing=LABEL_SMOOTHING)
+            w["Q"] = len(train)
+            w["eval"] = test
+            return w, (train.features, train.off, train.idx, train.counts), \
+                "real WN18RR train triples (tests/golden/wn18rr_ids.npz, ids of the reference's data/WN18RR)"
+    return w, synth_graph(w), "synthetic"
+
+
+def init_params(w, seed=SEED):
     """R_TuckER.init: xavier core + QR-orthonormalised xavier factors on the CPU generator."""
     from rtucker_b200 import asymmetric, symmetric
+    np.random.seed(seed)
     torch.manual_seed(seed)
     mod = symmetric if w["sym"] else asymmetric
     model = mod.R_TuckER((w["N"], w["M"]), w["rank"])
@@ -125,30 +150,36 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_steps(w, graph, n_steps, warmup, threads=None):
-    """Times the reference's train step (port) on the host cores.  Dense targets are built outside the
-    timed region (the reference builds them in DataLoader worker processes)."""
+def reference_steps(w, graph, n_steps, warmup, threads=None, device="cpu"):
+    """Times the reference's train step (port, oracle/reference_step.py) on the host cores -- or, with
+    device="cuda", the same PyTorch code on CUDA tensors (stock cuBLAS / cuSOLVER).  Dense targets are built outside
+    the timed region (the reference builds them in DataLoader worker processes)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import reference_step as RS
     if threads:
         torch.set_num_threads(threads)
     feats, off, idx, cnt = graph
     model = init_params(w)
+    dev = torch.device(device)
+    P = lambda t: t.data.to(dev)  # noqa: E731
     if w["sym"]:
-        st = RS.ReferenceStepper(model.core.data, model.R.weight.data, model.E.weight.data, None, MOMENTUM)
+        st = RS.ReferenceStepper(P(model.core), P(model.R.weight), P(model.E.weight), None, None)
     else:
-        st = RS.ReferenceStepper(model.core.data, model.R.weight.data, model.S.weight.data, model.O.weight.data,
-                                 MOMENTUM)
+        st = RS.ReferenceStepper(P(model.core), P(model.R.weight), P(model.S.weight), P(model.O.weight), MOMENTUM)
     rng = np.random.default_rng(7)
     order = rng.permutation(len(cnt))
     triples, total = 0, 0.0
     for i in range(warmup + n_steps):
         items = order[i * BATCH:(i + 1) * BATCH]
         f, boff, bidx = batch_arrays(feats, off, idx, cnt, items)
-        tg = RS.dense_targets(w["N"], torch.from_numpy(boff.astype(np.int64)), torch.from_numpy(bidx), LABEL_SMOOTHING)
-        ft = torch.from_numpy(f.astype(np.int64))
+        tg = RS.dense_targets(w["N"], torch.from_numpy(boff.astype(np.int64)), torch.from_numpy(bidx), LABEL_SMOOTHING).to(dev)
+        ft = torch.from_numpy(f.astype(np.int64)).to(dev)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         st.train_step(ft[:, 0], ft[:, 1], tg, REG, LR)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if i >= warmup:
             total += dt
@@ -156,20 +187,23 @@ def cpu_reference_steps(w, graph, n_steps, warmup, threads=None):
     return triples / total, total / n_steps, torch.get_num_threads()
 
 
+def metric_name(data_label):
+    return "train triples/s (1-N fwd+bwd+RSGD step), WN18RR" + ("" if data_label.startswith("real") else " shape")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = WORKLOADS[args.workload]
-    graph = synth_graph(w)
+    w, graph, data_label = load_workload(args.workload)
     # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core it can get
-    tps, sps, cores = cpu_reference_steps(w, graph, args.steps, args.warmup, threads=os.cpu_count())
+    tps, sps, cores = reference_steps(w, graph, args.steps, args.warmup, threads=os.cpu_count())
     line = {
-        "impl": "reference", "metric": "train triples/s (1-N fwd+bwd+RSGD step), WN18RR shape",
+        "impl": "reference", "metric": metric_name(data_label),
         "value": tps, "unit": "triples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": config_dict(w, args, "reference CPU path"),
+        "dtype": "f32", "data": data_label,
+        "config": config_dict(w, args),
         "cpu_baseline": {"value": tps, "unit": "triples/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} full train steps of B={BATCH} (oracle/reference_step.py), dense targets built outside the timed region"},
         "e2e": {"value": tps, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -177,21 +211,262 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def ncu_traffic(workload, variant):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
-    --set full capture of the same workload (profiles/ncu_traffic.json); None if never captured."""
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed ncu --set full capture
+    (profiles/ncu_traffic.json); None if never captured."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.isfile(path):
-        return json.load(open(path)).get("%s:variant%d" % (workload, variant))
+        return json.load(open(path)).get(key)
     return None
 
 
-def config_dict(w, args, note):
-    return {"workload": f"{args.workload}: synthetic graph of that shape, N={w['N']} entities, M={w['M']} relations, "
-                        f"rank={w['rank']}, batch {BATCH}, {'SF-Tucker rgd' if w['sym'] else 'Tucker rsgd'} "
-                        f"beta={MOMENTUM}, label_smoothing={LABEL_SMOOTHING}, lr={LR}, reg={REG}",
-            "l2": "per-step working set (factors + tangent/momentum buffers) > 126 MB L2; no explicit flush",
-            "note": note}
+def config_dict(w, args):
+    return {"workload": f"{args.workload}: N={w['N']} entities, M={w['M']} relations, "
+                        f"rank={tuple(w['rank'])}, batch {BATCH}, {'SF-Tucker rgd' if w['sym'] else 'Tucker rsgd'} "
+                        f"beta={MOMENTUM}, label_smoothing={LABEL_SMOOTHING}, lr={LR}, reg={REG}, init seed {SEED}",
+            "l2": "per-step working set (factors + tangent/momentum buffers) > 126 MB L2; no explicit flush"}
+
+
+class Runner:
+    """One model + optimiser of a workload on this rank's entity shard, with pre-assembled batches."""
+
+    def __init__(self, w, graph, dev, world, rank, group, variant, use_graphs, n_batches):
+        from rtucker_b200 import asymmetric, symmetric
+        self.w, self.dev, self.world, self.group = w, dev, world, group
+        feats, off, idx, cnt = graph
+        model = init_params(w)
+        N = w["N"]
+        per = (N + world - 1) // world
+        self.n_begin, self.n_end = rank * per, min(N, (rank + 1) * per)
+        with torch.no_grad():
+            if w["sym"]:
+                model.E.weight.data = model.E.weight.data[self.n_begin:self.n_end].contiguous()
+            else:
+                model.S.weight.data = model.S.weight.data[self.n_begin:self.n_end].contiguous()
+                model.O.weight.data = model.O.weight.data[self.n_begin:self.n_end].contiguous()
+        self.model = model.to(dev)
+        mod = symmetric if w["sym"] else asymmetric
+        kw = dict(group=group, n_total=N, n_begin=self.n_begin, score_variant=variant, use_graphs=use_graphs)
+        if w["sym"]:
+            self.opt = mod.RGD([model.core, model.E.weight, model.R.weight], w["rank"], LR, **kw)
+        else:
+            self.opt = mod.RSGDwithMomentum([model.core, model.S.weight, model.R.weight, model.O.weight], w["rank"], LR,
+                                            MOMENTUM, **kw)
+        self.opt.param_groups[0]["lr"] = LR
+        rng = np.random.default_rng(7)
+        order = rng.permutation(len(cnt))
+        self.host_batches, self.triples = [], []
+        for i in range(n_batches):
+            items = order[(i * BATCH) % (len(order) - BATCH):][:BATCH]
+            f, boff, bidx = batch_arrays(feats, off, idx, cnt, items)
+            self.host_batches.append([torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (f, boff, bidx)])
+            self.triples.append(int(cnt[items].sum()))
+
+    def barrier(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(self, fd, od, xd):
+        from rtucker_b200.engine import SparseTargets
+        from rtucker_b200.optim import FusedLoss
+        score_fn = self.model(fd[:, 0], fd[:, 1])
+        self.opt.fit(FusedLoss(score_fn, SparseTargets(od, xd), LABEL_SMOOTHING, REG), None)
+        self.opt.step()
+
+    def max_over_ranks(self, ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_resident(self, warmup, steps):
+        """K steps on batches already in HBM; returns (ms total = max over ranks, triples)."""
+        dev_batches = [[t.to(self.dev) for t in hb] for hb in self.host_batches[:warmup + steps]]
+        for i in range(warmup):
+            self.one_step(*dev_batches[i])
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(warmup, warmup + steps):
+            self.one_step(*dev_batches[i])
+        e1.record()
+        self.barrier()
+        self.dev_batches = dev_batches
+        return self.max_over_ranks(e0.elapsed_time(e1)), sum(self.triples[warmup:warmup + steps])
+
+    def timed_e2e(self, first, steps):
+        h2d = d2h = 0
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(first, first + steps):
+            hb = self.host_batches[i]
+            db = [t.to(self.dev, non_blocking=True) for t in hb]
+            h2d = sum(t.numel() * t.element_size() for t in hb)
+            self.one_step(*db)
+            loss_host = self.opt.loss.cpu()       # device -> host read of the step's result
+            d2h = loss_host.numel() * loss_host.element_size()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1)), sum(self.triples[first:first + steps]), h2d, d2h
+
+    def eval_qps(self, n_batches, eval_ds=None):
+        """Filtered evaluation (fused score + rank) queries/s: the real test split when available, else the train
+        queries with their first known object as the target."""
+        from rtucker_b200.engine import SparseTargets
+        from rtucker_b200.evaluation import rank_batch
+        from rtucker_b200.train import extract_tensor
+        point = extract_tensor(self.model)
+        ebs = []
+        for i in range(n_batches):
+            if eval_ds is not None:
+                f3, boff, bidx = eval_ds.host_batch(np.arange(i * BATCH, min((i + 1) * BATCH, len(eval_ds))))
+                f3, boff, bidx = (torch.from_numpy(np.ascontiguousarray(a)) for a in (f3, boff, bidx))
+            else:
+                f, boff, bidx = self.host_batches[i]
+                f3 = torch.cat([f, bidx[boff[:-1].long()][:, None]], dim=1).contiguous()
+            ebs.append((f3.to(self.dev), SparseTargets(boff.to(self.dev), bidx.to(self.dev))))
+        rank_batch(point, ebs[0][0], ebs[0][1], self.n_begin, self.group)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for f3, flt in ebs:
+            rank_batch(point, f3, flt, self.n_begin, self.group)
+        e1.record()
+        self.barrier()
+        ms = self.max_over_ranks(e0.elapsed_time(e1))
+        return sum(b[0].shape[0] for b in ebs) / (ms * 1e-3), ms / len(ebs)
+
+
+def time_score_kernel(run, dev, variant, steps, large):
+    """The fused score kernel on its own, launched back to back on the step's inputs (CUDA events on the launching
+    stream; its working set -- O, packed images, dO, per-CTA H partials -- exceeds the L2)."""
+    from rtucker_b200 import lib, ops as _ops
+    w = run.w
+    fd, od, xd = run.dev_batches[0]
+    model = run.model
+    O_fac = model.E.weight.data if w["sym"] else model.O.weight.data
+    S_fac = model.E.weight.data if w["sym"] else model.S.weight.data
+    B_, r2_ = BATCH, w["rank"][2]
+    r_rows = _ops.gather_rows(model.R.weight.data, fd[:, 1].contiguous())
+    s_rows = _ops.gather_rows(S_fac, fd[:, 0].contiguous(), run.n_begin)
+    if run.world > 1:
+        torch.distributed.all_reduce(s_rows)
+    qq = _ops.query_fwd(model.core.data, r_rows, s_rows)
+    outs = (torch.empty(1, dtype=torch.float64, device=dev), torch.empty(B_, r2_, device=dev), torch.empty_like(O_fac))
+    v = variant
+    if v == 2 and not _ops.score_v3_supported(r2_):
+        v = 1
+    ws_s = torch.empty(int(lib().rt_score_bce_ws_bytes(B_, O_fac.shape[0], r2_, v)) + 16, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def run_score(phases=7):
+        _ops.score_bce_fwd_bwd(qq, None if v == 2 else qq, O_fac, od, xd, LABEL_SMOOTHING, n_total=w["N"], b_total=B_,
+                               n_begin=run.n_begin, variant=v, out=outs, ws=ws_s, o_absmax=1.0 if v == 2 else None,
+                               phases=phases)
+    reps = max(10, steps)
+
+    def timed(phases):
+        for _ in range(3):
+            run_score(phases)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            run_score(phases)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    run_score(7)
+    out = {"variant": v, "op_ms": timed(7), "kernel_ms": timed(2) if v == 2 else None, "launches_timed": reps, "large": None}
+    if large and v == 2:
+        try:
+            N1, r1m = 1000000, 200
+            O1 = torch.randn(N1, r1m, device=dev) * (1.0 / N1 ** 0.5)
+            q1 = torch.randn(B_, r1m, device=dev) * 4.0 * (N1 / r1m) ** 0.5      # logits ~ N(0, 4^2)
+            out1 = (torch.empty(1, dtype=torch.float64, device=dev), torch.empty(B_, r1m, device=dev), torch.empty_like(O1))
+            ws1 = torch.empty(int(lib().rt_score_bce_ws_bytes(B_, N1, r1m, 2)) + 16, dtype=torch.uint8, device=dev)
+
+            def run1(phases=7):
+                _ops.score_bce_fwd_bwd(q1, None, O1, od, xd, LABEL_SMOOTHING, n_total=N1, b_total=B_, variant=2,
+                                       out=out1, ws=ws1, o_absmax=1.0, phases=phases)
+            run1(7)
+            for _ in range(2):
+                run1(2)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                run1(2)
+            e1.record()
+            torch.cuda.synchronize()
+            out["large"] = {"kernel_ms": e0.elapsed_time(e1) / 5, "flops": 6.0 * B_ * N1 * r1m, "launches_timed": 5}
+            del O1, out1, ws1
+        except RuntimeError as exc:      # out of memory on a smaller part: the number is simply absent
+            out["large"] = {"error": str(exc)[:120]}
+    return out
+
+
+def rooflines(w, n_local, ms_step, stage_ms, score_timing, eval_ms, peaks):
+    """One entry per kernel family, each with its share of the step."""
+    r0, r1, r2 = w["rank"]
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tf_burst = float(peaks.get("bf16_tflops", 1590.0))
+    src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    st = stage_ms
+    tot_eager = sum(st.values()) or 1.0
+    share = lambda keys: sum(st.get(k, 0.0) for k in keys) / tot_eager  # noqa: E731
+    out = []
+    # (b) fused score + BCE + backward
+    flops_b = 6.0 * BATCH * n_local * r2
+    k_ms = (score_timing or {}).get("kernel_ms") or (score_timing or {}).get("op_ms") or st.get("score_bce_fwd_bwd")
+    ach = flops_b / (k_ms * 1e-3) / 1e12 if k_ms else None
+    vnt = (score_timing or {}).get("variant", 0)
+    peak_b = tf_burst if vnt else FFMA_PEAK_TF
+    entry_b = {"family": "b: fused 1-N score + BCE + backward (variant %d)" % vnt, "bound": "tensor", "achieved": ach,
+               "peak": peak_b, "unit": "TFLOP/s", "frac": ach / peak_b if ach else None,
+               "peak_source": (src + " bf16_tflops (burst: kernel timed alone)") if vnt else "nominal FP32 FFMA (148 SMs x 128 lanes x 2 x 1.965 GHz)",
+               "algorithmic_flops_per_launch": flops_b, "ms_per_launch": k_ms, "traffic": ncu_traffic("score_v3:wn18rr"),
+               "share_of_step": share(["score_bce_fwd_bwd"]), "timing": score_timing}
+    if score_timing and score_timing.get("large") and score_timing["large"].get("kernel_ms"):
+        lg = score_timing["large"]
+        a1 = lg["flops"] / (lg["kernel_ms"] * 1e-3) / 1e12
+        entry_b["same_kernel_on_1m_entities"] = {"ms_per_launch": lg["kernel_ms"], "achieved": a1, "frac": a1 / tf_burst,
+                                                 "unit": "TFLOP/s", "algorithmic_flops_per_launch": lg["flops"]}
+    out.append(entry_b)
+    # (c) tall-skinny passes: HBM roofline, 24 N r bytes per big factor and step (SURVEY 8d)
+    big = [r for r in ((r1, r2) if not w["sym"] else (r1,))]
+    bytes_c = sum(24.0 * n_local * r for r in big)
+    ts_keys = ["tall_skinny_fit", "retract_gram", "retract_apply", "write_back"]
+    ms_c = sum(st.get(k, 0.0) for k in ts_keys) - st.get("small_project", 0.0)
+    ach_c = bytes_c / (ms_c * 1e-3) / 1e9 if ms_c > 0 else None
+    out.append({"family": "c: tall-skinny projection / transport / retraction passes (N x r x r)", "bound": "hbm",
+                "achieved": ach_c, "peak": hbm, "unit": "GB/s", "frac": ach_c / hbm if ach_c else None,
+                "peak_source": src + " hbm_gbs", "algorithmic_bytes_per_step": bytes_c, "ms_per_step": ms_c,
+                "traffic": ncu_traffic("tall_skinny:wn18rr"), "share_of_step": ms_c / tot_eager,
+                "timing_note": "sum of the N-sized stages of stage_ms (eager launches, CUDA events)"})
+    # (c-small) N-independent stage
+    sm_keys = ["small_prepare", "small_grad", "small_project", "small_retract_hosvd"]
+    out.append({"family": "c-small: N-independent fp64 stage (Gram inverses, projection cores, HOSVD subspaces)",
+                "bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None,
+                "ms_per_step": sum(st.get(k, 0.0) for k in sm_keys), "share_of_step": share(sm_keys),
+                "note": "replicated on every rank; persistent DMMA executor + purification kernel, a few dozen grid-barrier rounds"})
+    # (a) query contraction
+    flops_a = 8.0 * BATCH * r0 * r1 * r2
+    ms_a = st.get("query_fwd", 0.0) + st.get("query_bwd", 0.0)
+    ach_a = flops_a / (ms_a * 1e-3) / 1e12 if ms_a > 0 else None
+    out.append({"family": "a: query contraction core x1 r x2 s, forward + backward", "bound": "fp32-ffma", "achieved": ach_a,
+                "peak": FFMA_PEAK_TF, "unit": "TFLOP/s", "frac": ach_a / FFMA_PEAK_TF if ach_a else None,
+                "peak_source": "nominal FP32 FFMA", "algorithmic_flops_per_step": flops_a, "ms_per_step": ms_a,
+                "share_of_step": share(["query_fwd", "query_bwd"])})
+    # (d) fused filtered evaluation
+    if eval_ms:
+        flops_d = 2.0 * BATCH * n_local * r2
+        ach_d = flops_d / (eval_ms * 1e-3) / 1e12
+        out.append({"family": "d: fused score + filtered rank (evaluation batch of 512)", "bound": "fp32-ffma",
+                    "achieved": ach_d, "peak": FFMA_PEAK_TF, "unit": "TFLOP/s", "frac": ach_d / FFMA_PEAK_TF,
+                    "peak_source": "nominal FP32 FFMA (ranks need fp32-accurate scores)", "algorithmic_flops_per_batch": flops_d,
+                    "ms_per_batch": eval_ms, "share_of_step": None})
+    return out
 
 
 def main():
@@ -205,9 +480,13 @@ def main():
                     help="fused score kernel: 0 = fp32 FFMA (1e-5 parity), 1 = tcgen05 TF32 (2e-3), "
                          "2 = warp-specialised tcgen05 with scaled fp16 operands (2e-3)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="reference steps timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--torch-gpu-steps", type=int, default=4, help="reference-port steps on CUDA tensors (0 = skip)")
     ap.add_argument("--eval-batches", type=int, default=8)
     ap.add_argument("--no-graphs", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-large-kernel", action="store_true", help="skip timing the fused kernel on the 1M-entity shard")
+    ap.add_argument("--no-strict", action="store_true", help="skip the strict-fp32 (variant 0) run")
+    ap.add_argument("--no-c5", action="store_true", help="skip the synthetic 1M-entity sub-record")
+    ap.add_argument("--c5-steps", type=int, default=5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -238,269 +517,136 @@ def main():
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
 
-    from rtucker_b200 import asymmetric, lib, symmetric
-    from rtucker_b200.engine import SparseTargets
-    from rtucker_b200.optim import FusedLoss
-    from rtucker_b200.evaluation import rank_batch
-    from rtucker_b200.manifold import SFTucker, Tucker
+    from rtucker_b200 import lib
 
-    w = WORKLOADS[args.workload]
-    graph = synth_graph(w)
-    feats, off, idx, cnt = graph
-    model = init_params(w)
-    N = w["N"]
-    # ---- entity sharding: contiguous row blocks of S/O (or E) per rank ----
-    per = (N + world - 1) // world
-    n_begin, n_end = rank * per, min(N, (rank + 1) * per)
-    with torch.no_grad():
-        if w["sym"]:
-            model.E.weight.data = model.E.weight.data[n_begin:n_end].contiguous()
-        else:
-            model.S.weight.data = model.S.weight.data[n_begin:n_end].contiguous()
-            model.O.weight.data = model.O.weight.data[n_begin:n_end].contiguous()
-    model.to(dev)
-    mod = symmetric if w["sym"] else asymmetric
-    kw = dict(group=group, n_total=N, n_begin=n_begin, score_variant=args.variant, use_graphs=(world == 1 and not args.no_graphs))
-    if w["sym"]:
-        opt = mod.RGD([model.core, model.E.weight, model.R.weight], w["rank"], LR, **kw)
-    else:
-        opt = mod.RSGDwithMomentum([model.core, model.S.weight, model.R.weight, model.O.weight], w["rank"], LR,
-                                   MOMENTUM, **kw)
-    opt.param_groups[0]["lr"] = LR
-
-    rng = np.random.default_rng(7)
-    order = rng.permutation(len(cnt))
+    w, graph, data_label = load_workload(args.workload)
+    use_graphs = (world == 1 and not args.no_graphs)
     total_steps = args.warmup + args.steps
-    host_batches, dev_batches, triples = [], [], []
-    for i in range(2 * total_steps):
-        items = order[(i * BATCH) % (len(order) - BATCH):][:BATCH]
-        f, boff, bidx = batch_arrays(feats, off, idx, cnt, items)
-        hb = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (f, boff, bidx)]
-        host_batches.append(hb)
-        triples.append(int(cnt[items].sum()))
-        if i < total_steps:
-            dev_batches.append([t.to(dev) for t in hb])
-    torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
-    def one_step(fd, od, xd):
-        score_fn = model(fd[:, 0], fd[:, 1])
-        opt.fit(FusedLoss(score_fn, SparseTargets(od, xd), LABEL_SMOOTHING, REG), None)
-        opt.step()
+    run = Runner(w, graph, dev, world, rank, group, args.variant, use_graphs, 2 * total_steps)
 
     # ---- device-resident timing (CUDA graphs replay fit + step; inputs already in HBM) ----
-    for i in range(args.warmup):
-        one_step(*dev_batches[i])
-    eng = opt._engine
-    launches0 = lib().rt_launch_count()
     clocks = ClockSampler()
-    barrier()
     clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.warmup, total_steps):
-        one_step(*dev_batches[i])
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    launches0 = lib().rt_launch_count()
+    ms, n_tr = run.timed_resident(args.warmup, args.steps)
     launches_eager = int(lib().rt_launch_count() - launches0)
-    n_tr = sum(triples[args.warmup:total_steps])
-    t_all = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t_all, op=torch.distributed.ReduceOp.MAX)
-    ms = float(t_all.item())
     value = n_tr / (ms * 1e-3)
+    eng = run.opt._engine
 
     # ---- per-stage profile pass: same steps launched eagerly with CUDA-event brackets around every stage
     #      (the graph path cannot be bracketed); also counts the kernels of one step ----
     prof_steps = min(args.steps, 10)
     eng.timers = {}
     l0 = lib().rt_launch_count()
-    barrier()
+    run.barrier()
     for i in range(prof_steps):
-        one_step(*dev_batches[args.warmup + i])
-    barrier()
+        run.one_step(*run.dev_batches[args.warmup + i])
+    run.barrier()
     launches_per_step = int(lib().rt_launch_count() - l0) // prof_steps
     stage_ms = eng.stage_ms()
     eng.timers = None
-    launches = launches_per_step * args.steps if launches_eager == 0 else launches_eager
+    launches = launches_per_step * args.steps if launches_eager <= 2 * args.steps else launches_eager
 
     # ---- end to end: host batches in, loss out, every step ----
-    h2d = d2h = 0
-    barrier()
-    e0.record()
-    for i in range(total_steps, total_steps + args.steps):
-        hb = host_batches[i]
-        db = [t.to(dev, non_blocking=True) for t in hb]
-        h2d = sum(t.numel() * t.element_size() for t in hb)
-        one_step(*db)
-        loss_host = opt.loss.cpu()       # device -> host read of the step's result
-        d2h = loss_host.numel() * loss_host.element_size()
-    e1.record()
-    barrier()
+    ms_e2e, tr_e2e, h2d, d2h = run.timed_e2e(total_steps, args.steps)
     clock_info = clocks.stop()
-    ms_e2e = e0.elapsed_time(e1)
-    t_all = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t_all, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = sum(triples[total_steps:total_steps + args.steps]) / (float(t_all.item()) * 1e-3)
+    e2e_value = tr_e2e / (ms_e2e * 1e-3)
 
-    # ---- filtered evaluation (fused score + rank), queries/s ----
-    eval_qps = None
+    # ---- filtered evaluation ----
+    eval_qps = eval_ms = None
     if args.eval_batches > 0:
-        point = (SFTucker(model.core.data, [model.R.weight.data], 2, model.E.weight.data) if w["sym"] else
-                 Tucker(model.core.data, [model.R.weight.data, model.S.weight.data, model.O.weight.data]))
-        ebs = []
-        for i in range(args.eval_batches):
-            f, boff, bidx = host_batches[i]
-            tgt = bidx[boff[:-1].long()]   # first known object of each query as the target
-            f3 = torch.cat([f, tgt[:, None]], dim=1).contiguous().to(dev)
-            ebs.append((f3, SparseTargets(boff.to(dev), bidx.to(dev))))
-        rank_batch(point, ebs[0][0], ebs[0][1], n_begin, group)
-        barrier()
-        e0.record()
-        for f3, flt in ebs:
-            rank_batch(point, f3, flt, n_begin, group)
-        e1.record()
-        barrier()
-        eval_qps = BATCH * len(ebs) / (e0.elapsed_time(e1) * 1e-3)
+        eval_qps, eval_ms = run.eval_qps(args.eval_batches, w.get("eval"))
 
-    # ---- the fused score kernel on its own, launched back to back on the step's inputs (CUDA events on the
-    #      launching stream; its working set -- O, packed images, dO, per-CTA H partials -- exceeds the L2) ----
-    score_timing = None
-    if rank == 0 or world > 1:
-        from rtucker_b200 import ops as _ops
-        fd, od, xd = dev_batches[0]
-        O_fac = model.E.weight.data if w["sym"] else model.O.weight.data
-        B_, r2_ = BATCH, w["rank"][2]
-        # the query rows of a real batch at the current (trained-for-a-few-steps) point, exactly what the step feeds
-        # the kernel: q = core x1 R[rel] x2 S[sub]
-        S_fac = model.E.weight.data if w["sym"] else model.S.weight.data
-        r_rows = _ops.gather_rows(model.R.weight.data, fd[:, 1].contiguous())
-        s_rows = _ops.gather_rows(S_fac, fd[:, 0].contiguous(), n_begin)
-        if world > 1:
-            torch.distributed.all_reduce(s_rows)
-        qq = _ops.query_fwd(model.core.data, r_rows, s_rows)
-        outs = (torch.empty(1, dtype=torch.float64, device=dev), torch.empty(B_, r2_, device=dev),
-                torch.empty_like(O_fac))
-        v = args.variant
-        if v == 2 and not _ops.score_v3_supported(r2_):
-            v = 1
-        ws_s = torch.empty(int(lib().rt_score_bce_ws_bytes(B_, O_fac.shape[0], r2_, v)) + 16, dtype=torch.uint8, device=dev)
-        def run_score(phases=7):
-            _ops.score_bce_fwd_bwd(qq, None if v == 2 else qq, O_fac, od, xd, LABEL_SMOOTHING, n_total=N, b_total=B_,
-                                   n_begin=n_begin, variant=v, out=outs, ws=ws_s, o_absmax=1.0 if v == 2 else None,
-                                   phases=phases)
-        reps = max(10, args.steps)
-        def timed(phases):
-            for _ in range(3):
-                run_score(phases)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(reps):
-                run_score(phases)
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / reps
-        run_score(7)
-        score_timing = {"op_ms": timed(7), "kernel_ms": timed(2) if v == 2 else None, "launches_timed": reps}
-        # the same kernel on the 1M-entity / rank-200 shard of BASELINE configs[4] (single GPU only): at the WN18RR
-        # size a launch is 12 (tile, chunk) pairs per SM, so prologue, tail and first-touch of the H partials weigh in
-        roofline_1m = None
-        if world == 1 and v == 2 and args.workload != "synthetic-1m" and not args.no_large_kernel:
-            try:
-                N1, r1m = 1000000, 200
-                O1 = torch.randn(N1, r1m, device=dev) * (1.0 / N1 ** 0.5)
-                q1 = torch.randn(B_, r1m, device=dev) * 4.0 * (N1 / r1m) ** 0.5      # logits ~ N(0, 4^2)
-                out1 = (torch.empty(1, dtype=torch.float64, device=dev), torch.empty(B_, r1m, device=dev), torch.empty_like(O1))
-                ws1 = torch.empty(int(lib().rt_score_bce_ws_bytes(B_, N1, r1m, 2)) + 16, dtype=torch.uint8, device=dev)
-                def run1(phases=7):
-                    _ops.score_bce_fwd_bwd(q1, None, O1, od, xd, LABEL_SMOOTHING, n_total=N1, b_total=B_, variant=2,
-                                           out=out1, ws=ws1, o_absmax=1.0, phases=phases)
-                run1(7)
-                for _ in range(2):
-                    run1(2)
-                torch.cuda.synchronize()
-                e0.record()
-                for _ in range(5):
-                    run1(2)
-                e1.record()
-                torch.cuda.synchronize()
-                k_ms = e0.elapsed_time(e1) / 5
-                roofline_1m = {"kernel_ms": k_ms, "flops": 6.0 * B_ * N1 * r1m, "launches_timed": 5}
-                del O1, out1, ws1
-            except RuntimeError as exc:      # out of memory on a smaller part: the number is simply absent
-                roofline_1m = {"error": str(exc)[:120]}
-        score_timing["large"] = roofline_1m
+    score_timing = time_score_kernel(run, dev, args.variant, args.steps,
+                                     large=(world == 1 and args.workload != "synthetic-1m" and not args.no_large_kernel))
+
+    # ---- strict fp32 (variant 0) on the same batches ----
+    strict = None
+    if not args.no_strict and args.variant != 0:
+        del run.dev_batches
+        run0 = Runner(w, graph, dev, world, rank, group, 0, use_graphs, total_steps)
+        ms0, tr0 = run0.timed_resident(args.warmup, args.steps)
+        strict = {"value": tr0 / (ms0 * 1e-3), "ms_per_step": ms0 / args.steps,
+                  "note": "score kernel variant 0 (fp32 FFMA, 1e-5 parity path), everything else identical"}
+        del run0
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4]: synthetic 1M entities, rank (200,200,200), on the same ranks ----
+    c5 = None
+    if not args.no_c5 and args.workload != "synthetic-1m":
+        try:
+            w5 = dict(WORKLOADS["synthetic-1m"])
+            g5 = synth_graph(w5)
+            n5 = 3 + args.c5_steps
+            run5 = Runner(w5, g5, dev, world, rank, group, args.variant, False, n5)
+            ms5, tr5 = run5.timed_resident(3, args.c5_steps)
+            q5, _ = run5.eval_qps(2)
+            c5 = {"workload": "synthetic-1m: N=1,000,000 entities, M=1000 relations, rank (200,200,200), batch 512, rsgd",
+                  "value": tr5 / (ms5 * 1e-3), "unit": "triples/s", "ms_per_step": ms5 / args.c5_steps, "steps": args.c5_steps,
+                  "warmup": 3, "eval_queries_per_s": q5, "n_gpus": world, "cuda_graphs": False}
+            del run5
+            torch.cuda.empty_cache()
+        except RuntimeError as exc:
+            c5 = {"error": str(exc)[:200]}
 
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     if rank != 0:
         return
-    # ---- roofline of the fused score kernel ----
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(peaks_path):
-        peaks = json.load(open(peaks_path))
-        peak_tf, peak_src = float(peaks["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained"
-    else:
-        peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
-    r2 = w["rank"][2]
-    flops = 6.0 * BATCH * (n_end - n_begin) * r2
-    score_ms = stage_ms.get("score_bce_fwd_bwd")
-    if score_timing is not None:
-        score_ms = score_timing["kernel_ms"] if score_timing.get("kernel_ms") else score_timing["op_ms"]
-    achieved = flops / (score_ms * 1e-3) / 1e12 if score_ms else None
-    roofline = {"kernel": "fused 1-N score + BCE + backward, variant %d (%s)" % (
-                    args.variant, {0: "score_kernel, fp32 FFMA", 1: "score_tc_kernel, tcgen05 TF32",
-                                   2: "score_v3_kernel, warp-specialised tcgen05 kind::f16 + its pack / reduce launches"}[args.variant]),
-                "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf if achieved else None, "traffic": ncu_traffic(args.workload, args.variant),
-                "peak_source": peak_src, "algorithmic_flops_per_launch": flops, "ms_per_launch": score_ms,
-                "timing": score_timing,
-                "same_kernel_on_1m_entities": (None if not (score_timing and score_timing.get("large") and score_timing["large"].get("kernel_ms")) else {
-                    "workload": "BASELINE configs[4] shard: N=1,000,000 entities, r2=200, B=512, one GPU",
-                    "ms_per_launch": score_timing["large"]["kernel_ms"],
-                    "achieved": score_timing["large"]["flops"] / (score_timing["large"]["kernel_ms"] * 1e-3) / 1e12,
-                    "frac": score_timing["large"]["flops"] / (score_timing["large"]["kernel_ms"] * 1e-3) / 1e12 / peak_tf,
-                    "unit": "TFLOP/s", "algorithmic_flops_per_launch": score_timing["large"]["flops"]}),
-                "timing_note": "ms_per_launch = the fused kernel alone (kernel_ms: %d back-to-back launches between CUDA "
-                               "events, on the query rows of a real batch at the current point); op_ms adds its operand "
-                               "packing and H-reduction launches; in-step stage time is stage_ms.score_bce_fwd_bwd. The "
-                               "epilogue has a warp-uniform short path for logits in (-27.7, 16.6): a launch on inputs with "
-                               "many saturated logits is up to 1.6x slower (tools/zdist.py)"
-                               % (score_timing["launches_timed"] if score_timing else 0)}
 
-    cpu = None
-    if args.cpu_steps > 0 and world == 1:
-        tps, sps, cores = cpu_reference_steps(w, graph, args.cpu_steps, 1, threads=os.cpu_count())
-        cpu = {"value": tps, "unit": "triples/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_steps} full train steps of B={BATCH} after 1 warm-up (oracle/reference_step.py: "
-                         f"the reference's autodiff-through-rank-2r step), {sps:.3f} s/step; dense targets built outside the timed region"}
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_path)) if os.path.isfile(peaks_path) else {}
+    n_local = run.n_end - run.n_begin
+    roof_all = rooflines(w, n_local, ms / args.steps, stage_ms, score_timing, eval_ms, peaks)
+    measurable = [r for r in roof_all if r.get("frac") is not None and r.get("share_of_step") is not None]
+    dominant = max(measurable, key=lambda r: r["share_of_step"]) if measurable else roof_all[0]
+    roofline = {k: dominant.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+    roofline.update({"kernel": dominant["family"], "share_of_step": dominant["share_of_step"],
+                     "peak_source": dominant.get("peak_source"),
+                     "note": "the measurable kernel family with the largest share of the step; every family is in roofline_all"})
+
+    cpu = gpu_torch = None
+    if world == 1:
+        if args.cpu_steps > 0:
+            tps, sps, cores = reference_steps(w, graph, args.cpu_steps, 1, threads=os.cpu_count())
+            cpu = {"value": tps, "unit": "triples/s", "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_steps} full train steps of B={BATCH} after 1 warm-up (oracle/reference_step.py: "
+                             f"the reference's autodiff-through-rank-2r step), {sps:.3f} s/step; dense targets built outside the timed region"}
+        if args.torch_gpu_steps > 0:
+            try:
+                tps, sps, _ = reference_steps(w, graph, args.torch_gpu_steps, 2, device="cuda")
+                gpu_torch = {"value": tps, "unit": "triples/s", "ms_per_step": sps * 1e3, "kind": "port on CUDA tensors",
+                             "sample": f"{args.torch_gpu_steps} steps after 2 warm-ups of the same reference-step port with every tensor "
+                                       "on this GPU (stock cuBLAS / cuSOLVER / ATen, dense 512 x N targets resident on the device)"}
+            except RuntimeError as exc:
+                gpu_torch = {"error": str(exc)[:200]}
 
     line = {
-        "metric": "train triples/s (1-N fwd+bwd+RSGD step), WN18RR shape", "value": value, "unit": "triples/s",
+        "metric": metric_name(data_label), "value": value, "unit": "triples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "dtype_note": "fused score kernel: fp16 tensor-core operands scaled by powers of two (11 significant bits), fp32 "
-                      "accumulation; tall-skinny passes fp32; N-independent stage fp64",
-        "config": config_dict(w, args, "entity-sharded over %d GPU(s)" % world),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (score GEMMs: f16 operands / f32 accumulate; N-independent stage f64)" if args.variant == 2 else
+                 ("f32 (score GEMMs tf32)" if args.variant == 1 else "f32"),
+        "data": data_label,
+        "config": dict(config_dict(w, args), note="entity-sharded over %d GPU(s)" % world),
         "queries_per_s": BATCH * args.steps / (ms * 1e-3),
         "eval_queries_per_s": eval_qps,
+        "eval_note": "filtered ranking of the real test split (first batches)" if w.get("eval") is not None else "train queries re-ranked",
+        "value_strict_fp32": strict,
         "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "gpu_launches_note": "kernels of this library executed in the timed region (%d per step; replayed from 2 CUDA graphs per step when graphs are on)" % launches_per_step,
         "cuda_graphs": bool(eng.use_graphs and eng._graphs),
         "roofline": roofline,
+        "roofline_all": roof_all,
         "stage_ms": stage_ms,
         "stage_ms_note": "mean ms per stage over %d EAGERLY launched steps (CUDA events on the launching stream): stages made "
-                         "of many short launches include host launch gaps, so the sum exceeds ms_per_step, which is "
-                         "measured on the CUDA-graph path" % prof_steps,
+                         "of several launches include host launch gaps, so the sum exceeds ms_per_step, which is "
+                         "measured on the CUDA-graph path; shares in roofline_all are shares of this sum" % prof_steps,
         "cpu_baseline": cpu,
+        "torch_gpu_baseline": gpu_torch,
+        "c5": c5,
         "clocks": clock_info,
     }
     print(json.dumps(line))
