@@ -173,6 +173,19 @@ size_t rt_apply_tc_ws_bytes(int rc, int nk, const int* rk_host);
 int rt_apply_tc(float* Y, int64_t ldy, int n, int rc, const float* X0, int64_t ldx0, const double* a0_dev,
                 int nk, const float* const* X_host, const int64_t* ldx_host, const int* rk_host,
                 const double* const* K_host, void* ws, void* stream);
+/* Several independent updates of the same width rc in ONE persistent launch (the subject and the object factor of
+ * a step).  Per job: Y = a0 * X0 + sum_t X_t . K_t as above; Y may alias X0 AND any X_t (each row tile is read
+ * completely before it is written); copy_out[t] (optional) receives the raw X_t while it streams through -- the
+ * "old point" / "kept direction" copies of RSGDwithMomentum.step (asymmetric/optim.py:109-114) without extra passes. */
+typedef struct rt_apply_job {
+  float* Y; int64_t ldy; int n;
+  const float* X0; int64_t ldx0; const double* a0_dev;
+  int nk;
+  const float* X[4]; int64_t ldx[4]; int rk[4]; const double* K[4];
+  float* copy_out[4]; int64_t ldcopy[4];
+} rt_apply_job;
+size_t rt_apply_multi_ws_bytes(int njobs, const rt_apply_job* jobs, int rc);
+int rt_apply_multi(int njobs, const rt_apply_job* jobs, int rc, void* ws, void* stream);
 int rt_gram_tc_supported(int ra, int rb);
 size_t rt_gram_tc_ws_bytes(int n, int ra, int rb);
 int rt_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int n, int ra, int rb,

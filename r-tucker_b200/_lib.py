@@ -14,6 +14,13 @@ _lib = None
 
 vp, i32, i64, f32, f64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 
+class ApplyJob(C.Structure):
+    """struct rt_apply_job of include/rtucker.h"""
+    _fields_ = [("Y", vp), ("ldy", i64), ("n", i32), ("X0", vp), ("ldx0", i64), ("a0_dev", vp), ("nk", i32),
+                ("X", vp * 4), ("ldx", i64 * 4), ("rk", i32 * 4), ("K", vp * 4), ("copy_out", vp * 4),
+                ("ldcopy", i64 * 4)]
+
+
 # name -> (restype, argtypes); mirrors include/rtucker.h one to one
 PROTOTYPES = {
     "rt_abi_version": (i32, []),
@@ -42,6 +49,8 @@ PROTOTYPES = {
     "rt_apply_tc_ws_bytes": (sz, [i32, i32, C.POINTER(i32)]),
     "rt_apply_tc": (i32, [vp, i64, i32, i32, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(i32),
                           C.POINTER(vp), vp, vp]),
+    "rt_apply_multi_ws_bytes": (sz, [i32, C.POINTER(ApplyJob), i32]),
+    "rt_apply_multi": (i32, [i32, C.POINTER(ApplyJob), i32, vp, vp]),
     "rt_gram_tc_supported": (i32, [i32, i32]),
     "rt_gram_tc_ws_bytes": (sz, [i32, i32, i32]),
     "rt_gram_tc": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp]),

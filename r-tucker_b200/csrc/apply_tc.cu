@@ -1,0 +1,549 @@
+// Tall-skinny factor updates on the tensor cores (tcgen05, TF32 with a 3-product hi/lo split) at fp32 accuracy.
+//
+//   Y[n, rc] = a0 * X0 + sum_t X_t[n, rk_t] . K_t[rk_t, rc]          (K_t fp64, r x r)
+//
+// = the N-sized factor updates of the Riemannian gradient / momentum transport / retraction
+// (reference call sites src/model/asymmetric/optim.py:86-92,106-114, symmetric/optim.py:80-86,100-107).
+// Several independent updates ("jobs": the subject and the object factor) run in ONE persistent launch.
+//
+// Accuracy.  x = x_hi + x_lo (both TF32, round-to-nearest) and x.y ~ x_lo.y_hi + x_hi.y_lo + x_hi.y_hi loses 2^-24
+// per product, but the tensor core's fp32 accumulator TRUNCATES: measured bias -0.4 ulp per MMA instruction, i.e.
+// -1.8e-6 / -4e-6 / -6e-6 relative for 1 / 2 / 3 terms of K = 200 (tools/tc_acc.py).  So an accumulator in tensor
+// memory only ever holds the sum over GB*KB = 32 contraction elements (started from zero); two such accumulators
+// alternate, and the epilogue warps add each finished partial sum to an fp32 running sum in registers with
+// round-to-nearest.  Result: the accuracy of the FFMA kernel (a few 1e-7 norm-wise).
+//
+// Roles (one persistent CTA per SM, 16 warps, register file re-partitioned with setmaxnreg).  Warps 0-7, epilogue:
+// drain finished partial sums (tcgen05.ld) into 104 fp32 registers per thread, at the end of a row tile add
+// a0 * X0 and store Y.  Warps 8-11, producers: load the X blocks from global memory (coalesced float4, PF blocks in
+// flight in registers), split them into the hi / lo operand images in shared memory, optionally write the raw block
+// to a second destination (the "old point" / "kept direction" copies of the optimiser, which would otherwise be
+// separate passes).  Warp 12 (one lane) issues the MMAs; warp 13 (one lane) streams the pre-split K images with
+// bulk async copies (TMA, mbarrier complete_tx).
+#include "common.h"
+#include "tc.cuh"
+
+namespace {
+using namespace rt::tc;
+
+constexpr int kEpiWarps = 8, kProdWarps = 4, kMmaWarp = 12, kLoadWarp = 13;
+constexpr int kThreads = 512;       // 16 warps = 4 warpgroups: epilogue (2), producers (1), MMA + loader + 2 idle (1)
+constexpr int kRegsEpi = 168, kRegsOther = 88;                  // setmaxnreg: 256 * 168 + 256 * 88 = 64 K registers
+constexpr int TM = 128;             // rows per tile
+constexpr int KB = 16;              // contraction elements per staged block (2 MMA k-steps)
+constexpr int GB = 2;               // blocks per partial sum held in tensor memory
+constexpr int PF = 3;               // X blocks in flight per producer thread (registers)
+constexpr int XPT = TM * (KB / 4) / (kProdWarps * 32);          // float4 per producer thread and block
+constexpr int MAX_STAGES = 6;
+constexpr uint32_t RS = 128;
+constexpr uint32_t CS_X = TM * 16 + 32;                 // chunk stride of the X images: (CS_X / 16) % 8 == 2 keeps the
+                                                        // 16-byte stores of a quarter warp on distinct banks
+constexpr uint32_t X_HALF = (KB / 4) * CS_X;            // one image (hi or lo) of a block: 8320 bytes
+constexpr int RCP_MAX = 256;
+constexpr int MAX_JOBS = 4, MAX_TERMS = 4;
+constexpr size_t SMEM_LIMIT = 226 * 1024;
+
+struct Job {
+  float* Y; int64_t ldy;
+  const float* X0; int64_t ldx0; const double* a0;
+  const float* X[MAX_TERMS]; int64_t ldx[MAX_TERMS];
+  float* copy[MAX_TERMS]; int64_t ldc[MAX_TERMS];
+  int rk[MAX_TERMS]; int blk_end[MAX_TERMS];        // blk_end[t]: first block index after term t
+  int n, nk, nblk, kblk0, tile0, ntiles;
+};
+struct Args {
+  Job job[MAX_JOBS];
+  int njobs, ntiles, rc, rcp, nstages;
+  const unsigned char* Kimg;          // [total blocks][hi | lo][KB/4 chunks][cs_k bytes]
+  uint32_t cs_k, kimg_bytes, stage_bytes;
+  int debug;                          // profiling build only (RT_APPLY_DEBUG): 1 no X loads, 2 no K loads, 4 no MMAs, 8 ld.cg
+};
+struct PackArgs {
+  const double* K[MAX_JOBS * MAX_TERMS]; int rk[MAX_JOBS * MAX_TERMS]; int blk0[MAX_JOBS * MAX_TERMS + 1];
+  int nterms, rc, rcp; unsigned char* img; uint32_t cs_k, kimg_bytes;
+};
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+
+// same split with the round-to-nearest (ties away) done on the bit pattern: add half an ulp of TF32, clear 13 bits
+// (Inf / NaN inputs are not special-cased: they poison the row either way)
+__device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+}
+
+// image of block `blk`: element (c, kk) = K_t[kb*KB + kk][c], K-major B operand (rows = c), hi then lo
+__global__ void pack_K_kernel(PackArgs a) {
+  const int blk = blockIdx.x;
+  int t = 0;
+  while (t + 1 < a.nterms && blk >= a.blk0[t + 1]) ++t;
+  const int kb = blk - a.blk0[t];
+  const double* __restrict__ K = a.K[t];
+  const int rk = a.rk[t];
+  unsigned char* img = a.img + (size_t)blk * a.kimg_bytes;
+  const uint32_t half = (KB / 4) * a.cs_k;
+  for (int e = threadIdx.x; e < KB * a.rcp; e += blockDim.x) {
+    const int kk = e / a.rcp, c = e - kk * a.rcp;
+    const int k = kb * KB + kk;
+    float v = 0.0f;
+    if (k < rk && c < a.rc) v = (float)K[(int64_t)k * a.rc + c];
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    const uint32_t off = (uint32_t)(kk >> 2) * a.cs_k + (uint32_t)(c >> 3) * RS + (uint32_t)(c & 7) * 16u + (uint32_t)(kk & 3) * 4u;
+    *reinterpret_cast<uint32_t*>(img + off) = hi;
+    *reinterpret_cast<uint32_t*>(img + half + off) = lo;
+  }
+}
+
+#ifdef RT_APPLY_PROF
+#include <stdlib.h>
+#define DBG(bit) ((a.debug >> (bit)) & 1)
+#else
+#define DBG(bit) 0
+#endif
+#ifdef RT_APPLY_PROF
+#define PROF_DECL long long pt0 = clock64(), pw0 = 0, pw1 = 0, pw2 = 0, ptmp = 0
+#define PROF_BEGIN ptmp = clock64()
+#define PROF_END(x) x += clock64() - ptmp
+#define PROF_PRINT(role) if (blockIdx.x == 0 || blockIdx.x == 100) printf("cta %d %s: total %lld wait0 %lld wait1 %lld wait2 %lld\n", blockIdx.x, role, clock64() - pt0, pw0, pw1, pw2)
+#else
+#define PROF_DECL
+#define PROF_BEGIN
+#define PROF_END(x)
+#define PROF_PRINT(role)
+#endif
+
+// position in this CTA's flattened sequence of (tile, block) pairs
+struct Cursor {
+  int tile, job, blk, nblk, kblk0;
+  __device__ __forceinline__ bool valid(const Args& a) const { return tile < a.ntiles; }
+  __device__ __forceinline__ void set_job(const Args& a) {
+    if (tile < a.ntiles) {
+      job = 0;
+      while (job + 1 < a.njobs && tile >= a.job[job + 1].tile0) ++job;
+      nblk = a.job[job].nblk;
+      kblk0 = a.job[job].kblk0;
+    }
+  }
+  __device__ __forceinline__ void init(const Args& a) { tile = blockIdx.x; blk = 0; job = 0; nblk = 1; kblk0 = 0; set_job(a); }
+  __device__ __forceinline__ void next(const Args& a) {
+    if (++blk == nblk) { blk = 0; tile += gridDim.x; set_job(a); }
+  }
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+
+// HC8 = 8-column groups of the accumulator owned by one epilogue warp (rcp / 16): 13 for r = 200, 16 = any rcp <= 256
+template <int HC8>
+__global__ void __launch_bounds__(kThreads, 1)
+apply_tc_kernel(const __grid_constant__ Args a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NS = a.nstages;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&bar_full[s], kProdWarps + 1); mbar_init(&bar_empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kEpiWarps); }
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(&tmem_slot);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int halfcols = a.rcp >> 1;                 // columns of the accumulator owned by one epilogue warp
+  // the launch gives every thread 128 registers; the epilogue warps need 104 accumulators + a 32-register drain batch
+
+  if (warp < kEpiWarps) {
+    // ================= epilogue: partial sums -> fp32 running sum (round to nearest) -> Y =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" :: "n"(kRegsEpi));
+    const int quarter = warp & 3, half = warp >> 2;
+    constexpr int NACC = HC8 * 8;
+    float acc[NACC];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) acc[j] = 0.0f;
+    PROF_DECL;
+    int g = 0;                                       // finished partial sums so far (accumulator = g & 1)
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      int job = 0;
+      while (job + 1 < a.njobs && tile >= a.job[job + 1].tile0) ++job;
+      const Job& J = a.job[job];
+      const int ngroups = (J.nblk + GB - 1) / GB;
+      for (int grp = 0; grp < ngroups; ++grp, ++g) {
+        const int ab = g & 1;
+        PROF_BEGIN;
+        mbar_wait(&bar_acc_full[ab], (uint32_t)(g >> 1) & 1u);
+        PROF_END(pw0);
+        fence_after_sync();
+        const bool first = grp == 0;                 // first partial sum of the tile: set, do not add
+        const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * 256 + half * halfcols);
+#pragma unroll
+        for (int cb = 0; cb < HC8 / 4; ++cb) {
+          if (cb * 32 < halfcols) {
+            uint32_t v[32];
+            tmem_ld32(tbase + (uint32_t)(cb * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              acc[cb * 32 + j] = first ? __uint_as_float(v[j]) : acc[cb * 32 + j] + __uint_as_float(v[j]);
+          }
+        }
+#pragma unroll
+        for (int c8 = (HC8 / 4) * 4; c8 < HC8; ++c8) {
+          if (c8 * 8 < halfcols) {
+            uint32_t v[8];
+            tmem_ld8(tbase + (uint32_t)(c8 * 8), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              acc[c8 * 8 + j] = first ? __uint_as_float(v[j]) : acc[c8 * 8 + j] + __uint_as_float(v[j]);
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_acc_empty[ab]);
+      }
+      PROF_BEGIN;
+      const int row0 = (tile - J.tile0) * TM;
+      const int row = quarter * 32 + lane;
+      if (row0 + row < J.n) {
+        const float a0 = J.a0 ? (float)(*J.a0) : 1.0f;
+        float* y = J.Y + (int64_t)(row0 + row) * J.ldy + half * halfcols;
+        const float* x0 = J.X0 ? J.X0 + (int64_t)(row0 + row) * J.ldx0 + half * halfcols : nullptr;
+        const int cmax = min(halfcols, a.rc - half * halfcols);     // valid columns of this half
+        const bool vec = ((J.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(J.Y) & 15) == 0) &&
+                         (!x0 || (((J.ldx0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(J.X0) & 15) == 0)));
+#pragma unroll
+        for (int j = 0; j < NACC; j += 4) {
+          if (j < cmax) {
+            if (vec && j + 4 <= cmax) {
+              float4 r = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+              if (x0) {
+                const float4 x = *reinterpret_cast<const float4*>(x0 + j);
+                r.x = fmaf(a0, x.x, r.x); r.y = fmaf(a0, x.y, r.y); r.z = fmaf(a0, x.z, r.z); r.w = fmaf(a0, x.w, r.w);
+              }
+              *reinterpret_cast<float4*>(y + j) = r;
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (j + u < cmax) y[j + u] = x0 ? fmaf(a0, x0[j + u], acc[j + u]) : acc[j + u];
+            }
+          }
+        }
+      }
+      PROF_END(pw1);
+    }
+    if (tid == 0) { PROF_PRINT("epilogue (acc_full, store)"); }
+  } else if (warp < kEpiWarps + kProdWarps) {
+    // ================= producers: X block -> hi / lo operand images (+ optional raw copy) =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
+    const int ptid = tid - kEpiWarps * 32;             // 0 .. kProdWarps*32-1
+    const int ch = ptid & 3, r0 = ptid >> 2;           // this thread: 16-byte chunk `ch` of rows r0, r0+RSTEP, ...
+    constexpr int RSTEP = kProdWarps * 8;              // rows between two items of a thread
+    const uint32_t sm_off = (uint32_t)ch * CS_X + (uint32_t)(r0 >> 3) * RS + (uint32_t)(r0 & 7) * 16u;
+    // blocks this CTA will produce
+    int todo = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      int job = 0;
+      while (job + 1 < a.njobs && tile >= a.job[job + 1].tile0) ++job;
+      todo += a.job[job].nblk;
+    }
+    // ---- load side: a (tile, term, k-block) walk whose per-term state lives in registers ----
+    int l_tile = blockIdx.x - gridDim.x, l_job = 0, l_t = 0, l_nk = 0, l_kb = 0, l_nkb = 0;
+    int l_k = 0, l_rk = 0, l_nitems = 0, l_left = todo;
+    bool l_fast = false;
+    const float* l_p = nullptr; float* l_q = nullptr;
+    int64_t l_pstep = 0, l_qstep = 0;
+    int l_row = 0;
+    float4 xf[PF][XPT];
+    float* cq[PF]; int64_t cqstep[PF]; int cni[PF];    // raw-copy destination of the block held in slot u (cni < 0: slow path)
+    auto load_next = [&](float4 (&x)[XPT], float*& q, int64_t& qstep, int& ni_copy) {
+      if (l_kb == l_nkb) {                             // next term, or next tile
+        if (++l_t >= l_nk) {
+          l_tile += gridDim.x;
+          l_job = 0;
+          while (l_job + 1 < a.njobs && l_tile >= a.job[l_job + 1].tile0) ++l_job;
+          const Job& J = a.job[l_job];
+          l_nk = J.nk; l_t = 0;
+          l_row = (l_tile - J.tile0) * TM + r0;
+          const int left = min(TM, J.n - (l_tile - J.tile0) * TM) - r0;
+          l_nitems = left <= 0 ? 0 : (left + RSTEP - 1) / RSTEP;
+        }
+        const Job& J = a.job[l_job];
+        const float* X = J.X[l_t];
+        const int64_t ld = J.ldx[l_t];
+        l_rk = J.rk[l_t];
+        l_kb = 0; l_nkb = J.blk_end[l_t] - (l_t ? J.blk_end[l_t - 1] : 0);
+        l_k = 4 * ch;
+        l_p = X + (int64_t)l_row * ld + l_k;
+        l_pstep = (int64_t)RSTEP * ld;
+        l_fast = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((l_rk & 3) == 0);
+        l_q = nullptr; l_qstep = 0;
+        if (J.copy[l_t]) {
+          l_q = J.copy[l_t] + (int64_t)l_row * J.ldc[l_t] + l_k;
+          l_qstep = (int64_t)RSTEP * J.ldc[l_t];
+          l_fast = l_fast && ((J.ldc[l_t] & 3) == 0) && ((reinterpret_cast<uintptr_t>(J.copy[l_t]) & 15) == 0);
+        }
+      }
+      q = l_q; qstep = l_qstep;
+      if (l_fast) {
+        const int ni = (l_k < l_rk) ? l_nitems : 0;
+        ni_copy = ni;
+        const int nl = DBG(0) ? 0 : ni;
+#pragma unroll
+        for (int i = 0; i < XPT; ++i)
+          x[i] = i < nl ? __ldg(reinterpret_cast<const float4*>(l_p + i * l_pstep)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        ni_copy = -1 - (l_nitems + 16 * max(0, min(4, l_rk - l_k)));
+#pragma unroll
+        for (int i = 0; i < XPT; ++i) {
+          const float* p = l_p + i * l_pstep;
+          const bool on = i < l_nitems && !DBG(0);
+          x[i].x = (on && l_k + 0 < l_rk) ? __ldg(p + 0) : 0.f;
+          x[i].y = (on && l_k + 1 < l_rk) ? __ldg(p + 1) : 0.f;
+          x[i].z = (on && l_k + 2 < l_rk) ? __ldg(p + 2) : 0.f;
+          x[i].w = (on && l_k + 3 < l_rk) ? __ldg(p + 3) : 0.f;
+        }
+      }
+      ++l_kb; l_k += KB; l_p += KB; if (l_q) l_q += KB;
+      --l_left;
+    };
+    PROF_DECL;
+    int ps = 0; uint32_t pphase = 0;                   // stage / parity of the produce side
+    bool wrapped = false;
+    auto produce = [&](const float4 (&x)[XPT], float* q, int64_t qstep, int ni_copy) {
+      PROF_BEGIN;
+      if (wrapped) mbar_wait(&bar_empty[ps], pphase ^ 1u);
+      PROF_END(pw0);
+      PROF_BEGIN;
+      unsigned char* st = smem + (size_t)ps * a.stage_bytes + sm_off;
+#pragma unroll
+      for (int i = 0; i < XPT; ++i) {
+        const float4 v = x[i];
+        uint4 h, l;
+        if (DBG(5)) { h = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)); l = h; }
+        else {
+        split_tf32_fast(v.x, h.x, l.x); split_tf32_fast(v.y, h.y, l.y);
+        split_tf32_fast(v.z, h.z, l.z); split_tf32_fast(v.w, h.w, l.w);
+        }
+        *reinterpret_cast<uint4*>(st + i * (RSTEP / 8) * RS) = h;
+        *reinterpret_cast<uint4*>(st + X_HALF + i * (RSTEP / 8) * RS) = l;
+      }
+      if (q) {                                         // raw copy of the block (the data is in registers by now)
+        if (ni_copy >= 0) {
+#pragma unroll
+          for (int i = 0; i < XPT; ++i)
+            if (i < ni_copy) *reinterpret_cast<float4*>(q + i * qstep) = x[i];
+        } else {                                       // unaligned / ragged: ni_copy = -1 - (nitems + 16 * valid k)
+          const int code = -1 - ni_copy, nitems = code & 15, kleft = code >> 4;
+#pragma unroll
+          for (int i = 0; i < XPT; ++i) {
+            float* qq = q + i * qstep;
+            const bool on = i < nitems;
+            if (on && 0 < kleft) qq[0] = x[i].x;
+            if (on && 1 < kleft) qq[1] = x[i].y;
+            if (on && 2 < kleft) qq[2] = x[i].z;
+            if (on && 3 < kleft) qq[3] = x[i].w;
+          }
+        }
+      }
+      if (!DBG(4)) fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[ps]);
+      PROF_END(pw1);
+      if (++ps == NS) { ps = 0; pphase ^= 1u; wrapped = true; }
+    };
+#pragma unroll
+    for (int u = 0; u < PF; ++u)
+      if (l_left > 0) load_next(xf[u], cq[u], cqstep[u], cni[u]);
+    while (todo > 0) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        if (todo > 0) {
+          produce(xf[u], cq[u], cqstep[u], cni[u]);
+          --todo;
+          if (l_left > 0) load_next(xf[u], cq[u], cqstep[u], cni[u]);
+        }
+      }
+    }
+    if (ptid == 0) { PROF_PRINT("producer (empty, produce)"); }
+  } else if (warp == kMmaWarp) {
+    // ================= MMA issuer =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(TM, a.rcp, false, false);
+      Cursor c;
+      c.init(a);
+      int g = 0;
+      PROF_DECL;
+      int s = 0; uint32_t phase = 0;
+      for (; c.valid(a); c.next(a)) {
+        const bool group_start = (c.blk % GB) == 0;
+        const bool group_end = c.blk == c.nblk - 1 || ((c.blk + 1) % GB) == 0;
+        const int ab = g & 1;
+        PROF_BEGIN;
+        if (group_start && g >= 2) mbar_wait(&bar_acc_empty[ab], (uint32_t)((g >> 1) - 1) & 1u);
+        PROF_END(pw1);
+        PROF_BEGIN;
+        mbar_wait(&bar_full[s], phase);
+        PROF_END(pw0);
+        fence_after_sync();
+        const uint32_t aXh = smem_u32(smem + (size_t)s * a.stage_bytes), aXl = aXh + X_HALF;
+        const uint32_t aKh = aXh + 2 * X_HALF, aKl = aKh + (KB / 4) * a.cs_k;
+        const uint32_t d = tmem + (uint32_t)(ab * 256);
+#pragma unroll
+        for (int ks = 0; ks < KB / 8; ++ks) {
+          if (DBG(2) && !(group_start && ks == 0)) continue;
+          const uint64_t dXh = make_desc(aXh + ks * 2 * CS_X, CS_X, RS), dXl = make_desc(aXl + ks * 2 * CS_X, CS_X, RS);
+          const uint64_t dKh = make_desc(aKh + ks * 2 * a.cs_k, a.cs_k, RS), dKl = make_desc(aKl + ks * 2 * a.cs_k, a.cs_k, RS);
+          mma_tf32(d, dXl, dKh, idesc, !(group_start && ks == 0));     // small terms first
+          mma_tf32(d, dXh, dKl, idesc, true);
+          mma_tf32(d, dXh, dKh, idesc, true);
+        }
+        mma_commit(&bar_empty[s]);
+        if (group_end) { mma_commit(&bar_acc_full[ab]); ++g; }
+        if (++s == NS) { s = 0; phase ^= 1u; }
+      }
+      PROF_PRINT("mma (full, acc_empty)");
+    }
+    __syncwarp();
+  } else if (warp == kLoadWarp) {
+    // ================= K image loader =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
+    if (lane == 0) {
+      Cursor c;
+      c.init(a);
+      PROF_DECL;
+      int s = 0; uint32_t phase = 0; bool wrapped = false;
+      for (; c.valid(a); c.next(a)) {
+        PROF_BEGIN;
+        if (wrapped) mbar_wait(&bar_empty[s], phase ^ 1u);
+        PROF_END(pw0);
+        if (DBG(1) && wrapped) mbar_arrive(&bar_full[s]);
+        else {
+          mbar_expect_tx(&bar_full[s], a.kimg_bytes);
+          bulk_g2s(smem + (size_t)s * a.stage_bytes + 2 * X_HALF,
+                   a.Kimg + (size_t)(c.kblk0 + c.blk) * a.kimg_bytes, a.kimg_bytes, &bar_full[s]);
+        }
+        if (++s == NS) { s = 0; phase ^= 1u; wrapped = true; }
+      }
+      PROF_PRINT("loader (empty)");
+    }
+    __syncwarp();
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));     // idle warps of the last warpgroup
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem);
+}
+
+struct Plan { int rcp, nstages; uint32_t cs_k, kimg_bytes, stage_bytes; size_t smem; };
+Plan make_plan(int rc) {
+  Plan p;
+  p.rcp = (rc + 15) / 16 * 16;
+  p.cs_k = (uint32_t)p.rcp * 16u + 16u;
+  p.kimg_bytes = 2u * (KB / 4) * p.cs_k;
+  p.stage_bytes = 2 * X_HALF + p.kimg_bytes;
+  int ns = (int)(SMEM_LIMIT / p.stage_bytes);
+  p.nstages = ns > MAX_STAGES ? MAX_STAGES : ns;
+  p.smem = (size_t)p.nstages * p.stage_bytes;
+  return p;
+}
+
+}  // namespace
+
+// ---- C ABI -------------------------------------------------------------------------------------------
+extern "C" int rt_apply_tc_supported(int rc, int nk, const int* rk_host) {
+  if (rc < 1 || rc > RCP_MAX || nk < 1 || nk > MAX_TERMS) return 0;
+  for (int t = 0; t < nk; ++t)
+    if (rk_host[t] < 1) return 0;
+  return make_plan(rc).nstages >= 3 ? 1 : 0;
+}
+
+extern "C" size_t rt_apply_tc_ws_bytes(int rc, int nk, const int* rk_host) {
+  const Plan p = make_plan(rc);
+  size_t blocks = 0;
+  for (int t = 0; t < nk; ++t) blocks += rt::cdiv(rk_host[t], KB);
+  return blocks * p.kimg_bytes + 256;
+}
+
+extern "C" size_t rt_apply_multi_ws_bytes(int njobs, const rt_apply_job* jobs, int rc) {
+  const Plan p = make_plan(rc);
+  size_t blocks = 0;
+  for (int j = 0; j < njobs; ++j)
+    for (int t = 0; t < jobs[j].nk; ++t) blocks += rt::cdiv(jobs[j].rk[t], KB);
+  return blocks * p.kimg_bytes + 256;
+}
+
+extern "C" int rt_apply_multi(int njobs, const rt_apply_job* jobs, int rc, void* ws, void* stream) {
+  RT_REQUIRE(njobs >= 1 && njobs <= MAX_JOBS, "rt_apply_multi: 1..%d jobs per launch, got %d", MAX_JOBS, njobs);
+  RT_REQUIRE(ws != nullptr, "rt_apply_multi: workspace is NULL");
+  const Plan p = make_plan(rc);
+  cudaStream_t s = (cudaStream_t)stream;
+  Args a{};
+  PackArgs pk{};
+  a.rc = rc; a.rcp = p.rcp; a.nstages = p.nstages; a.cs_k = p.cs_k; a.kimg_bytes = p.kimg_bytes;
+  a.stage_bytes = p.stage_bytes; a.Kimg = (const unsigned char*)ws;
+  int tiles = 0, blocks = 0, nj = 0, nterms = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const rt_apply_job& in = jobs[j];
+    RT_REQUIRE(rt_apply_tc_supported(rc, in.nk, in.rk), "rt_apply_multi: unsupported shape rc=%d nk=%d", rc, in.nk);
+    if (in.n == 0) continue;
+    Job& J = a.job[nj++];
+    J.Y = in.Y; J.ldy = in.ldy; J.X0 = in.X0; J.ldx0 = in.ldx0; J.a0 = in.a0_dev; J.n = in.n; J.nk = in.nk;
+    J.kblk0 = blocks; J.tile0 = tiles; J.ntiles = rt::cdiv(in.n, TM);
+    int b = 0;
+    for (int t = 0; t < MAX_TERMS; ++t) {
+      const bool on = t < in.nk;
+      J.X[t] = on ? in.X[t] : nullptr; J.ldx[t] = on ? in.ldx[t] : 0; J.rk[t] = on ? in.rk[t] : 0;
+      J.copy[t] = on ? in.copy_out[t] : nullptr; J.ldc[t] = on ? in.ldcopy[t] : 0;
+      if (on) {
+        RT_REQUIRE(in.copy_out[t] != in.Y || in.copy_out[t] == nullptr, "rt_apply_multi: copy_out may not alias Y");
+        pk.K[nterms] = in.K[t]; pk.rk[nterms] = in.rk[t]; pk.blk0[nterms] = blocks + b; ++nterms;
+        b += rt::cdiv(in.rk[t], KB);
+      }
+      J.blk_end[t] = b;
+    }
+    J.nblk = b;
+    blocks += b;
+    tiles += J.ntiles;
+  }
+  if (nj == 0) return 0;
+  a.njobs = nj; a.ntiles = tiles;
+#ifdef RT_APPLY_PROF
+  a.debug = getenv("RT_APPLY_DEBUG") ? atoi(getenv("RT_APPLY_DEBUG")) : 0;
+#endif
+  pk.blk0[nterms] = blocks; pk.nterms = nterms; pk.rc = rc; pk.rcp = p.rcp; pk.img = (unsigned char*)ws;
+  pk.cs_k = p.cs_k; pk.kimg_bytes = p.kimg_bytes;
+  pack_K_kernel<<<blocks, 256, 0, s>>>(pk);
+  RT_LAUNCH_CHECK();
+  const int grid = tiles < rt::sm_count() ? tiles : rt::sm_count();
+  if (p.rcp == 208) {
+    RT_CHECK_CUDA(rt::ensure_dyn_smem((const void*)apply_tc_kernel<13>, SMEM_LIMIT));
+    apply_tc_kernel<13><<<grid, kThreads, p.smem, s>>>(a);
+  } else {
+    RT_CHECK_CUDA(rt::ensure_dyn_smem((const void*)apply_tc_kernel<16>, SMEM_LIMIT));
+    apply_tc_kernel<16><<<grid, kThreads, p.smem, s>>>(a);
+  }
+  RT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rt_apply_tc(float* Y, int64_t ldy, int n, int rc, const float* X0, int64_t ldx0, const double* a0_dev,
+                           int nk, const float* const* X_host, const int64_t* ldx_host, const int* rk_host,
+                           const double* const* K_host, void* ws, void* stream) {
+  RT_REQUIRE(rt_apply_tc_supported(rc, nk, rk_host), "rt_apply_tc: unsupported shape rc=%d nk=%d", rc, nk);
+  rt_apply_job j{};
+  j.Y = Y; j.ldy = ldy; j.n = n; j.X0 = X0; j.ldx0 = ldx0; j.a0_dev = a0_dev; j.nk = nk;
+  for (int t = 0; t < nk; ++t) { j.X[t] = X_host[t]; j.ldx[t] = ldx_host[t]; j.rk[t] = rk_host[t]; j.K[t] = K_host[t]; }
+  return rt_apply_multi(1, &j, rc, ws, stream);
+}

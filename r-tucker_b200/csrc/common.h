@@ -46,6 +46,24 @@ inline int sm_count() {
   return n;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (kernel, device) instead of on every launch
+inline cudaError_t ensure_dyn_smem(const void* func, size_t bytes) {
+  constexpr int kSlots = 64, kDevs = 16;
+  static const void* funcs[kSlots];
+  static size_t done[kSlots][kDevs];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int slot = 0;
+  while (slot < kSlots && funcs[slot] && funcs[slot] != func) ++slot;
+  if (slot < kSlots && dev < kDevs) {
+    if (funcs[slot] == func && done[slot][dev] >= bytes) return cudaSuccess;
+    funcs[slot] = func;
+  }
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && slot < kSlots && dev < kDevs) done[slot][dev] = bytes;
+  return e;
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -1,8 +1,7 @@
 // Tall-skinny passes on the tensor cores: tcgen05 TF32 with a 3-product split (x = x_hi + x_lo,
 // x.y ~ x_hi.y_hi + x_hi.y_lo + x_lo.y_hi), i.e. fp32-level accuracy (~1e-6 relative) at tensor-core rate.
 //
-//   apply:  Y[n, rc]  = a0 * X0 + sum_t X_t[n, rk_t] . K_t[rk_t, rc]     (factor updates of project / round,
-//           reference call sites src/model/asymmetric/optim.py:86,106-114)
+//   (the factor updates Y = a0 X0 + sum_t X_t K_t live in apply_tc.cu)
 //   gram :  C[ra, rb] = A[n, ra]^T B[n, rb]                                (Gram products of grad / norm / project)
 //
 // Both keep their accumulators in tensor memory and stage K-major operands in the interleaved
@@ -30,171 +29,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-
-// ---------------------------------------------------------------------------------------------------
-// apply
-// ---------------------------------------------------------------------------------------------------
-struct ApplyTcArgs {
-  float* Y; int64_t ldy; int n, rc, rcp;
-  const float* X0; int64_t ldx0; const double* a0;
-  const float* X[4]; int64_t ldx[4]; int rk[4]; int nblk[4]; int blk0[4];   // per term: k-blocks and first block id
-  int nk, nblocks;
-  const unsigned char* Kimg;    // [nblocks][2 (hi, lo)][KB/4 chunks][cs_k bytes]
-  uint32_t cs_k, kimg_bytes;    // chunk stride of the K^T image (rcp*16 + 16), bytes of one block image (hi+lo)
-};
-
-// K^T image: for block `blk` of term t (k in [kb*32, kb*32+32)): element (c, kk) = K_t[kb*32+kk][c] split hi/lo
-__global__ void pack_K_kernel(ApplyTcArgs a, const double* const* Kptr_unused, const double* K0, const double* K1,
-                              const double* K2, const double* K3) {
-  const double* Ks[4] = {K0, K1, K2, K3};
-  const int blk = blockIdx.x;
-  int t = 0;
-  while (t + 1 < a.nk && blk >= a.blk0[t + 1]) ++t;
-  const int kb = blk - a.blk0[t];
-  unsigned char* img = const_cast<unsigned char*>(a.Kimg) + (size_t)blk * a.kimg_bytes;
-  const uint32_t half = (KB / 4) * a.cs_k;
-  for (int e = threadIdx.x; e < KB * a.rcp; e += blockDim.x) {
-    const int kk = e / a.rcp, c = e - kk * a.rcp;
-    const int k = kb * KB + kk;
-    float v = 0.0f;
-    if (k < a.rk[t] && c < a.rc) v = (float)Ks[t][(int64_t)k * a.rc + c];
-    uint32_t hi, lo;
-    split_tf32(v, hi, lo);
-    const uint32_t off = (uint32_t)(kk >> 2) * a.cs_k + (uint32_t)(c >> 3) * RS + (uint32_t)(c & 7) * 16u + (uint32_t)(kk & 3) * 4u;
-    *reinterpret_cast<uint32_t*>(img + off) = hi;
-    *reinterpret_cast<uint32_t*>(img + half + off) = lo;
-  }
-}
-
-__global__ void __launch_bounds__(kThreads, 1)
-apply_tc_kernel(ApplyTcArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_stage[2], bar_done;
-  __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int quarter = warp & 3, half = warp >> 2;
-  const uint32_t stage_bytes = 2 * X_BYTES + a.kimg_bytes;
-  if (tid == 0) { mbar_init(&bar_stage[0], 1); mbar_init(&bar_stage[1], 1); mbar_init(&bar_done, 1); fence_mbar_init(); }
-  if (warp == 0) tmem_alloc<256>(&tmem_slot);
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = tmem_slot;
-  const int row0 = blockIdx.x * TM;
-  const int rows_valid = min(TM, a.n - row0);
-  const uint32_t idesc = make_idesc_tf32(TM, a.rcp, false, false);
-  uint32_t ph[2] = {0u, 0u};
-  int used[2] = {0, 0};
-
-  // register prefetch of the next X block: 4 x float4 per thread (128 rows x 8 chunks = 1024 chunks)
-  float4 xf[4];
-  auto load_x = [&](int blk) {
-    int t = 0;
-    while (t + 1 < a.nk && blk >= a.blk0[t + 1]) ++t;
-    const int kb = blk - a.blk0[t];
-    const float* X = a.X[t];
-    const int64_t ld = a.ldx[t];
-    const int rk = a.rk[t];
-    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int e = it * kThreads + tid;
-      const int row = e >> 3, ch = e & 7;
-      const int k = kb * KB + 4 * ch;
-      xf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < rows_valid && k < rk) {
-        const float* p = X + (int64_t)(row0 + row) * ld + k;
-        if (vec && k + 4 <= rk) xf[it] = __ldg(reinterpret_cast<const float4*>(p));
-        else {
-          xf[it].x = __ldg(p);
-          if (k + 1 < rk) xf[it].y = __ldg(p + 1);
-          if (k + 2 < rk) xf[it].z = __ldg(p + 2);
-          if (k + 3 < rk) xf[it].w = __ldg(p + 3);
-        }
-      }
-    }
-  };
-  if (a.nblocks > 0) load_x(0);
-  for (int blk = 0; blk < a.nblocks; ++blk) {
-    const int s = blk & 1;
-    unsigned char* st = smem + (size_t)s * stage_bytes;
-    if (used[s]) { mbar_wait(&bar_stage[s], ph[s]); ph[s] ^= 1u; used[s] = 0; }
-    // K^T image (hi, lo) of this block: straight async copy
-    {
-      const unsigned char* src = a.Kimg + (size_t)blk * a.kimg_bytes;
-      const uint32_t dst = smem_u32(st + 2 * X_BYTES);
-      for (uint32_t o = tid * 16u; o < a.kimg_bytes; o += kThreads * 16u) cp_async16(dst + o, src + o);
-    }
-    // X block: split hi / lo from the prefetched registers
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int e = it * kThreads + tid;
-      const int row = e >> 3, ch = e & 7;
-      uint32_t h[4], l[4];
-      split_tf32(xf[it].x, h[0], l[0]); split_tf32(xf[it].y, h[1], l[1]);
-      split_tf32(xf[it].z, h[2], l[2]); split_tf32(xf[it].w, h[3], l[3]);
-      const uint32_t off = (uint32_t)ch * CS_X + (uint32_t)(row >> 3) * RS + (uint32_t)(row & 7) * 16u;
-      *reinterpret_cast<uint4*>(st + off) = make_uint4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<uint4*>(st + X_BYTES + off) = make_uint4(l[0], l[1], l[2], l[3]);
-    }
-    if (blk + 1 < a.nblocks) load_x(blk + 1);
-    cp_async_wait_all();
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      const uint32_t aXh = smem_u32(st), aXl = aXh + X_BYTES;
-      const uint32_t aKh = aXh + 2 * X_BYTES, aKl = aKh + (KB / 4) * a.cs_k;
-#pragma unroll
-      for (int ks = 0; ks < KB / 8; ++ks) {
-        const uint64_t dXh = make_desc(aXh + ks * 2 * CS_X, CS_X, RS), dXl = make_desc(aXl + ks * 2 * CS_X, CS_X, RS);
-        const uint64_t dKh = make_desc(aKh + ks * 2 * a.cs_k, a.cs_k, RS), dKl = make_desc(aKl + ks * 2 * a.cs_k, a.cs_k, RS);
-        mma_tf32(tmem, dXl, dKh, idesc, (blk | ks) != 0);     // small terms first
-        mma_tf32(tmem, dXh, dKl, idesc, true);
-        mma_tf32(tmem, dXh, dKh, idesc, true);
-      }
-      mma_commit(&bar_stage[s]);
-      if (blk == a.nblocks - 1) mma_commit(&bar_done);
-    }
-    used[s] = 1;
-  }
-  // ---- epilogue: D (+ a0 * X0) -> Y ----
-  if (a.nblocks > 0) { mbar_wait(&bar_done, 0); fence_after_sync(); }
-  const float a0 = a.a0 ? (float)(*a.a0) : 1.0f;
-  const int row = quarter * 32 + lane;
-  const bool row_ok = row < rows_valid;
-  for (int c0 = half * 32; c0 < a.rcp; c0 += 64) {
-    uint32_t v[32];
-    if (a.nblocks > 0) {
-      if (a.rcp - c0 >= 32) tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-      else {
-        uint32_t w[16];
-        tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, w);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { v[j] = w[j]; v[j + 16] = 0u; }
-      }
-      tmem_ld_wait();
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0u;
-    }
-    if (row_ok) {
-      float* y = a.Y + (int64_t)(row0 + row) * a.ldy + c0;
-      const float* x0 = a.X0 ? a.X0 + (int64_t)(row0 + row) * a.ldx0 + c0 : nullptr;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (c0 + j < a.rc) {
-          float r = __uint_as_float(v[j]);
-          if (x0) r = fmaf(a0, x0[j], r);
-          y[j] = r;
-        }
-      }
-    }
-  }
-  fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // gram
@@ -345,52 +179,6 @@ GramTcPlan gram_tc_plan(int n, int ra, int rb) {
 }  // namespace
 
 // ---- C ABI -------------------------------------------------------------------------------------------
-extern "C" int rt_apply_tc_supported(int rc, int nk, const int* rk_host) {
-  if (rc < 1 || rc > RCP_MAX || nk < 1 || nk > 4) return 0;
-  const int rcp = (rc + 15) / 16 * 16;
-  const size_t kimg = 2 * (size_t)(KB / 4) * (rcp * 16 + 16);
-  return 2 * (2 * (size_t)X_BYTES + kimg) <= 220 * 1024 ? 1 : 0;
-}
-
-extern "C" size_t rt_apply_tc_ws_bytes(int rc, int nk, const int* rk_host) {
-  const int rcp = (rc + 15) / 16 * 16;
-  size_t blocks = 0;
-  for (int t = 0; t < nk; ++t) blocks += rt::cdiv(rk_host[t], KB);
-  return blocks * 2 * (size_t)(KB / 4) * (rcp * 16 + 16) + 256;
-}
-
-extern "C" int rt_apply_tc(float* Y, int64_t ldy, int n, int rc, const float* X0, int64_t ldx0, const double* a0_dev,
-                           int nk, const float* const* X_host, const int64_t* ldx_host, const int* rk_host,
-                           const double* const* K_host, void* ws, void* stream) {
-  RT_REQUIRE(rt_apply_tc_supported(rc, nk, rk_host), "rt_apply_tc: unsupported shape rc=%d nk=%d", rc, nk);
-  RT_REQUIRE(ws != nullptr, "rt_apply_tc: workspace is NULL");
-  if (n == 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  ApplyTcArgs a{};
-  a.Y = Y; a.ldy = ldy; a.n = n; a.rc = rc; a.rcp = (rc + 15) / 16 * 16;
-  a.X0 = X0; a.ldx0 = ldx0; a.a0 = a0_dev; a.nk = nk;
-  int blocks = 0;
-  for (int t = 0; t < 4; ++t) {
-    a.X[t] = t < nk ? X_host[t] : nullptr; a.ldx[t] = t < nk ? ldx_host[t] : 0; a.rk[t] = t < nk ? rk_host[t] : 0;
-    a.blk0[t] = blocks; a.nblk[t] = t < nk ? rt::cdiv(rk_host[t], KB) : 0;
-    blocks += a.nblk[t];
-    if (t < nk) RT_REQUIRE(a.X[t] != Y, "rt_apply_tc: Y may alias X0 only");
-  }
-  a.nblocks = blocks;
-  a.cs_k = (uint32_t)a.rcp * 16u + 16u;
-  a.kimg_bytes = 2u * (KB / 4) * a.cs_k;
-  a.Kimg = (const unsigned char*)ws;
-  const double* K[4] = {nullptr, nullptr, nullptr, nullptr};
-  for (int t = 0; t < nk; ++t) K[t] = K_host[t];
-  pack_K_kernel<<<blocks, 256, 0, s>>>(a, nullptr, K[0], K[1], K[2], K[3]);
-  RT_LAUNCH_CHECK();
-  const size_t smem = 2 * (2 * (size_t)X_BYTES + a.kimg_bytes);
-  RT_CHECK_CUDA(cudaFuncSetAttribute(apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  apply_tc_kernel<<<rt::cdiv(n, TM), kThreads, smem, s>>>(a);
-  RT_LAUNCH_CHECK();
-  return 0;
-}
-
 extern "C" int rt_gram_tc_supported(int ra, int rb) {
   if (ra < 1 || ra > 256 || rb < 1 || rb > 256) return 0;
   GramTcPlan p = gram_tc_plan(1024, ra, rb);

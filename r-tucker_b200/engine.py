@@ -140,6 +140,24 @@ class StepEngine:
     def _entity_factor_ids(self):
         return (1, 2) if not self.sym else (1,)
 
+    def _tc_jobs(self, jobs):
+        """True when all ``jobs`` = [(Y, X0, a0, terms)] can share ONE tcgen05 launch (ops.apply_multi)."""
+        ops = self.ops
+        if not jobs or not hasattr(ops, "apply_multi") or len({j[0].shape[1] for j in jobs}) != 1:
+            return False
+        return all(ops.apply_tc_ok(Y.shape[0], Y.shape[1], [t[0].shape[1] for t in terms])
+                   for Y, _, _, terms in jobs)
+
+    def _apply_jobs(self, jobs):
+        """Y = a0*X0 + sum X_k K_k for several factors: one persistent tensor-core launch when the shapes allow it
+        (wide entity factors), the FFMA kernel per factor otherwise (thin ranks, the relation factor)."""
+        if self._tc_jobs(jobs):
+            self.ops.apply_multi(jobs)
+        else:
+            for Y, X0, a0, terms in jobs:
+                self.ops.apply(Y, X0, a0, [(t[0], t[1]) for t in terms])
+        return [j[0] for j in jobs]
+
     def _U(self, k):
         return self.params[k].data
 
@@ -195,15 +213,17 @@ class StepEngine:
         dV_g = [None] * self.nf
         dV_g[0] = ops.apply(self.spare[0], None, None, [(R, P_R)])
         ops.scatter_rows_add(dV_g[0], rel_idx, drA)
+        obj_terms = [(dO_raw, small.ainv(2)), (O, P_O)] if fold_a else None
         if not sym:
-            dV_g[1] = ops.apply(self.spare[1], None, None, [(S, P_S)])
-            ops.scatter_rows_add(dV_g[1], sub_idx, dsA, self.n_begin)
-            dV_g[2] = (ops.apply(dOp, None, None, [(dO_raw, small.ainv(2)), (O, P_O)]) if fold_a else
-                       ops.apply(dOp, dOp, None, [(O, P_O)]))
+            jobs = [(self.spare[1], None, None, [(S, P_S)]),
+                    (dOp, None, None, obj_terms) if fold_a else (dOp, dOp, None, [(O, P_O)])]
         else:
-            dV_g[1] = (ops.apply(dOp, None, None, [(dO_raw, small.ainv(2)), (S, P_S)]) if fold_a else
-                       ops.apply(dOp, dOp, None, [(S, P_S)]))
-            ops.scatter_rows_add(dV_g[1], sub_idx, dsA, self.n_begin)
+            obj_terms = [(dO_raw, small.ainv(2)), (S, P_S)] if fold_a else None
+            jobs = [(dOp, None, None, obj_terms) if fold_a else (dOp, dOp, None, [(S, P_S)])]
+        out = self._apply_jobs(jobs)
+        for k, v in zip(self._entity_factor_ids(), out):
+            dV_g[k] = v
+        ops.scatter_rows_add(dV_g[1], sub_idx, dsA, self.n_begin)
         # ---- norm of the Riemannian gradient ----
         grams = [ops.gram(v, v) for v in dV_g]
         self._allreduce(*[grams[k] for k in self._entity_factor_ids()])
@@ -220,10 +240,13 @@ class StepEngine:
                 pS_beta, K, L = small.project(core, self.core_old, self.dS_dir_old, M[0], M[1],
                                               M[2] if not sym else M[1], self.hyper)
             dS_dir = ops.core_axpby(dS_g, alpha, pS_beta, out=self.dS_dir)
-            for k in range(self.nf):
+
+            def mom(k):
                 rk = self.rank[k]
-                ops.apply(dV_new[k], dV_g[k], alpha,
-                          [(self.U_old[k], K[k][:rk]), (self.dV_dir[k], K[k][rk:]), (self._U(k), L[k])])
+                return (dV_new[k], dV_g[k], alpha,
+                        [(self.U_old[k], K[k][:rk]), (self.dV_dir[k], K[k][rk:]), (self._U(k), L[k])])
+            self._apply_jobs([mom(0)])
+            self._apply_jobs([mom(k) for k in self._entity_factor_ids()])
         else:
             dS_dir = ops.core_axpby(dS_g, alpha, None, out=self.dS_dir)
             for k in range(self.nf):
@@ -252,16 +275,26 @@ class StepEngine:
             core_new, Z1, Z2, _ = small.retract(core, dS_dir, grams[0], grams[1],
                                                 grams[2] if not sym else grams[1], self.hyper,
                                                 transport_out=self.M_next if self.beta is not None else None)
-        new_U = []
+        keep = self.beta is not None
+        ent = list(self._entity_factor_ids())
+
+        def job(k, in_place):
+            tU = (self._U(k), Z1[k], self.U_old[k]) if (keep and in_place) else (self._U(k), Z1[k])
+            tV = (dV[k], Z2[k], self.dV_dir[k]) if (keep and in_place) else (dV[k], Z2[k])
+            return (self._U(k) if in_place else self.spare[k], None, None, [tU, tV])
+        # wide entity factors: ONE tensor-core launch updates the factor in place (each row tile is read completely
+        # before it is written) and writes the "old point" / "kept direction" copies while the operands stream by:
+        # reference p.data.add_(new - p) and the kept direction, optim.py:109-114, without extra passes
+        fused = self._tc_jobs([job(k, True) for k in ent])
+        legacy = [k for k in range(self.nf) if not (fused and k in ent)]
         with self._stage("retract_apply"):
-            for k in range(self.nf):
-                # spare[k] held dV_g during fit(); it is free again now
-                new_U.append(ops.apply(self.spare[k], None, None, [(self._U(k), Z1[k]), (dV[k], Z2[k])]))
+            if fused:
+                self.ops.apply_multi([job(k, True) for k in ent])
+            new_U = {k: ops.apply(self.spare[k], None, None, job(k, False)[3]) for k in legacy}
         # ---- the current point becomes the "old" point of the kept direction; parameters written back
         #      in place (reference: p.data.add_(new - p), optim.py:111-114) ----
-        keep = self.beta is not None
         with self._stage("write_back"):
-            for k in range(self.nf):
+            for k in legacy:
                 if keep:
                     self.U_old[k].copy_(self.params[k].data)
                     self.dV_dir[k].copy_(dV[k])

@@ -155,8 +155,11 @@ def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None,
 
 
 # ---------------------------------------------------------------- (c) tall-skinny
-# tall-skinny passes on tcgen05 (3xTF32, ~3e-6 accuracy) instead of fp32 FFMA (~3e-7): RT_TALLSKINNY_TC=1 opts in
-USE_TENSOR_CORES = os.environ.get("RT_TALLSKINNY_TC", "0") == "1"
+# The N x r x r passes run on tcgen05 (3xTF32 with round-to-nearest partial-sum accumulation: fp32 accuracy, see
+# csrc/apply_tc.cu) whenever the shape is wide enough to fill an MMA tile; thin ranks (d_e = 20) and short factors
+# (the relation factor) stay on the fp32 FFMA kernels.  RT_TALLSKINNY_TC=0 forces the FFMA kernels everywhere.
+USE_TENSOR_CORES = os.environ.get("RT_TALLSKINNY_TC", "1") == "1"
+TC_MIN_ROWS, TC_MIN_WIDTH = 1024, 64
 
 
 def gram(A, B, out=None, ws=None, precise=False, tc=None):
@@ -166,7 +169,7 @@ def gram(A, B, out=None, ws=None, precise=False, tc=None):
     rb = B.shape[1]
     assert B.shape[0] == n and A.stride(1) == 1 and B.stride(1) == 1
     out = out if out is not None else torch.empty(ra, rb, dtype=f64, device=A.device)
-    tc = USE_TENSOR_CORES if tc is None else tc
+    tc = False if tc is None else tc
     if tc and not precise and n >= 1024 and lib().rt_gram_tc_supported(ra, rb):
         ws = _ws(lib().rt_gram_tc_ws_bytes(n, ra, rb), A.device)
         check(lib().rt_gram_tc(ptr(A), A.stride(0), ptr(B), B.stride(0), n, ra, rb, ptr(_c(out, f64)), ptr(ws),
@@ -178,23 +181,61 @@ def gram(A, B, out=None, ws=None, precise=False, tc=None):
     return out
 
 
+def apply_tc_ok(n, rc, rks):
+    """True when Y[n,rc] = ... + sum X_k[n,rk] K_k runs on the tcgen05 kernel (apply_multi)."""
+    nk = len(rks)
+    if not (USE_TENSOR_CORES and 1 <= nk <= 4 and n >= TC_MIN_ROWS and rc >= TC_MIN_WIDTH):
+        return False
+    return bool(lib().rt_apply_tc_supported(rc, nk, (C.c_int * nk)(*rks)))
+
+
+def apply_multi(jobs):
+    """One persistent tcgen05 launch for several updates of the same width:
+    jobs = [(Y, X0, a0_dev, [(X_k, K_k[, copy_out_k]), ...]), ...];  Y_j = a0_j*X0_j + sum_k X_k @ K_k.
+    Y may alias X0 and any X_k; copy_out_k (optional, same shape as X_k) receives a copy of X_k."""
+    from ._lib import ApplyJob
+    nj = len(jobs)
+    arr = (ApplyJob * nj)()
+    rc = jobs[0][0].shape[1]
+    keep = []
+    for j, (Y, X0, a0, terms) in enumerate(jobs):
+        require_cuda(Y, X0, a0, *[t for term in terms for t in term])
+        n = Y.shape[0]
+        assert Y.shape[1] == rc and Y.dtype == f32 and Y.stride(1) == 1 and 1 <= len(terms) <= 4
+        J = arr[j]
+        J.Y, J.ldy, J.n = Y.data_ptr(), Y.stride(0), n
+        J.X0, J.ldx0 = (X0.data_ptr(), X0.stride(0)) if X0 is not None else (None, 0)
+        J.a0_dev = a0.data_ptr() if a0 is not None else None
+        J.nk = len(terms)
+        for t, term in enumerate(terms):
+            x, k = term[0], term[1]
+            cp = term[2] if len(term) > 2 else None
+            assert x.dtype == f32 and x.stride(1) == 1 and x.shape[0] == n and k.shape == (x.shape[1], rc)
+            J.X[t], J.ldx[t], J.rk[t], J.K[t] = x.data_ptr(), x.stride(0), x.shape[1], _c(k, f64).data_ptr()
+            if cp is not None:
+                assert cp.shape == x.shape and cp.dtype == f32 and cp.stride(1) == 1
+                J.copy_out[t], J.ldcopy[t] = cp.data_ptr(), cp.stride(0)
+    ws = _ws(lib().rt_apply_multi_ws_bytes(nj, arr, rc), jobs[0][0].device)
+    check(lib().rt_apply_multi(nj, arr, rc, ptr(ws), stream_ptr()), "rt_apply_multi")
+    return [job[0] for job in jobs]
+
+
 def apply(Y, X0, a0_dev, terms, tc=None):
     """Y = a0*X0 + sum_k X_k @ K_k;  terms = [(X_k f32 [n,rk], K_k f64 [rk,rc]), ...]."""
     require_cuda(Y, X0, a0_dev, *[t for pair in terms for t in pair])
     n, rc = Y.shape
     nk = len(terms)
+    for x, k in terms:
+        assert x.dtype == f32 and x.stride(1) == 1 and k.shape == (x.shape[1], rc) and x.shape[0] == n
+    use_tc = apply_tc_ok(n, rc, [x.shape[1] for x, _ in terms]) if tc is None else \
+        (tc and nk >= 1 and bool(lib().rt_apply_tc_supported(rc, nk, (C.c_int * nk)(*[x.shape[1] for x, _ in terms]))))
+    if use_tc:
+        apply_multi([(Y, X0, a0_dev, terms)])
+        return Y
     Xp = (C.c_void_p * max(nk, 1))(*[x.data_ptr() for x, _ in terms])
     ld = (C.c_int64 * max(nk, 1))(*[x.stride(0) for x, _ in terms])
     rk = (C.c_int * max(nk, 1))(*[x.shape[1] for x, _ in terms])
     Kp = (C.c_void_p * max(nk, 1))(*[_c(k, f64).data_ptr() for _, k in terms])
-    for x, k in terms:
-        assert x.dtype == f32 and x.stride(1) == 1 and k.shape == (x.shape[1], rc) and x.shape[0] == n
-    tc = USE_TENSOR_CORES if tc is None else tc
-    if tc and nk >= 1 and n >= 1024 and lib().rt_apply_tc_supported(rc, nk, rk):
-        ws = _ws(lib().rt_apply_tc_ws_bytes(rc, nk, rk), Y.device)
-        check(lib().rt_apply_tc(ptr(Y), Y.stride(0), n, rc, ptr(X0), X0.stride(0) if X0 is not None else 0,
-                                ptr(a0_dev), nk, Xp, ld, rk, Kp, ptr(ws), stream_ptr()), "rt_apply_tc")
-        return Y
     check(lib().rt_apply(ptr(Y), Y.stride(0), n, rc, ptr(X0), X0.stride(0) if X0 is not None else 0,
                          ptr(a0_dev), nk, Xp, ld, rk, Kp, stream_ptr()), "rt_apply")
     return Y
