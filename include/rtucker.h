@@ -165,9 +165,8 @@ int rt_apply(float* Y, int64_t ldy, int n, int rc,
              int nk, const float* const* X_host, const int64_t* ldx_host, const int* rk_host,
              const double* const* K_host, void* stream);
 
-/* Tensor-core (tcgen05, TF32 with a 3-product hi/lo split => fp32-level accuracy) variants of the two
- * passes above.  *_supported returns 1 if the shape fits (ranks <= 256); same results as rt_gram(precise=0)
- * / rt_apply to ~1e-6 relative. */
+/* Tensor-core (tcgen05, TF32 with a 3-product hi/lo split, partial sums added with round-to-nearest => the accuracy
+ * of the FFMA kernel, a few 1e-7) variant of rt_apply.  *_supported returns 1 if the shape fits (width <= 256). */
 int rt_apply_tc_supported(int rc, int nk, const int* rk_host);
 size_t rt_apply_tc_ws_bytes(int rc, int nk, const int* rk_host);
 int rt_apply_tc(float* Y, int64_t ldy, int n, int rc, const float* X0, int64_t ldx0, const double* a0_dev,
@@ -186,10 +185,6 @@ typedef struct rt_apply_job {
 } rt_apply_job;
 size_t rt_apply_multi_ws_bytes(int njobs, const rt_apply_job* jobs, int rc);
 int rt_apply_multi(int njobs, const rt_apply_job* jobs, int rc, void* ws, void* stream);
-int rt_gram_tc_supported(int ra, int rb);
-size_t rt_gram_tc_ws_bytes(int n, int ra, int rb);
-int rt_gram_tc(const float* A, int64_t lda, const float* B, int64_t ldb, int n, int ra, int rb,
-               double* out, void* ws, void* stream);
 
 /* ---- (c) N-independent ("small") stage ----------------------------------------------- */
 /*

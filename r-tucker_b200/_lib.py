@@ -51,9 +51,6 @@ PROTOTYPES = {
                           C.POINTER(vp), vp, vp]),
     "rt_apply_multi_ws_bytes": (sz, [i32, C.POINTER(ApplyJob), i32]),
     "rt_apply_multi": (i32, [i32, C.POINTER(ApplyJob), i32, vp, vp]),
-    "rt_gram_tc_supported": (i32, [i32, i32]),
-    "rt_gram_tc_ws_bytes": (sz, [i32, i32, i32]),
-    "rt_gram_tc": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp]),
     "rt_small_ws_bytes": (sz, [i32, i32, i32, i32]),
     "rt_small_prepare": (i32, [vp, i32, i32, i32, i32, vp, vp]),
     "rt_small_ainv_offset": (sz, [i32, i32, i32, i32]),

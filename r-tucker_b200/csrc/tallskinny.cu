@@ -6,6 +6,7 @@
 // Bound: HBM for thin ranks; at r ~ 200 the N x r x r products are FP32-FFMA bound
 // (2*N*ra*rb flops per Gram, 2*N*rk*rc per update term).
 #include "common.h"
+#include <algorithm>
 
 namespace {
 
@@ -359,11 +360,18 @@ extern "C" int rt_apply_v2(float* Y, int64_t ldy, int n, int rc, const float* X0
                            int nk, const float* const* X_host, const int64_t* ldx_host, const int* rk_host,
                            const double* const* K_host, void* stream);
 
+namespace rt {
+bool gram_sym_supported(int r);
+size_t gram_sym_ws_bytes(int n, int r);
+int gram_sym(const float* X, int64_t ld, int n, int r, double* out, void* ws, cudaStream_t s);
+}  // namespace rt
+
 extern "C" size_t rt_gram_ws_bytes(int n, int ra, int rb) {
   if (n <= 0 || ra <= 0 || rb <= 0) return 0;
   GramPlan p = gram_plan(n, ra, rb);
   const size_t v1 = (size_t)p.nsplit * ra * rb * sizeof(double), v2 = rt_gram_v2_ws_bytes(n, ra, rb);
-  return v1 > v2 ? v1 : v2;
+  const size_t v3 = (ra == rb && rt::gram_sym_supported(ra)) ? rt::gram_sym_ws_bytes(n, ra) : 0;
+  return std::max(v1, std::max(v2, v3));
 }
 
 extern "C" int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb, int n, int ra,
@@ -376,6 +384,9 @@ extern "C" int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb,
     return 0;
   }
   RT_REQUIRE(ws != nullptr, "rt_gram: workspace is NULL");
+  // A^T A (the norm and retraction Grams of a step): upper triangle on the fp64 tensor cores, exact accumulation
+  if (A == B && lda == ldb && ra == rb && rt::gram_sym_supported(ra) && n >= 64)
+    return rt::gram_sym(A, lda, n, ra, out, ws, s);
   if (!precise) return rt_gram_v2(A, lda, B, ldb, n, ra, rb, out, ws, stream);
   GramPlan p = gram_plan(n, ra, rb);
   dim3 grid(p.tiles_a * p.tiles_b, p.nsplit);

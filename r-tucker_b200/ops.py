@@ -162,19 +162,14 @@ USE_TENSOR_CORES = os.environ.get("RT_TALLSKINNY_TC", "1") == "1"
 TC_MIN_ROWS, TC_MIN_WIDTH = 1024, 64
 
 
-def gram(A, B, out=None, ws=None, precise=False, tc=None):
-    """out[ra,rb] (f64) = A^T B over the rows (precise: exact fp64 accumulation)."""
+def gram(A, B, out=None, ws=None, precise=False):
+    """out[ra,rb] (f64) = A^T B over the rows (precise: exact fp64 accumulation; A is B always takes the exact
+    symmetric DMMA kernel, csrc/gram_sym.cu)."""
     require_cuda(A, B)
     n, ra = A.shape
     rb = B.shape[1]
     assert B.shape[0] == n and A.stride(1) == 1 and B.stride(1) == 1
     out = out if out is not None else torch.empty(ra, rb, dtype=f64, device=A.device)
-    tc = False if tc is None else tc
-    if tc and not precise and n >= 1024 and lib().rt_gram_tc_supported(ra, rb):
-        ws = _ws(lib().rt_gram_tc_ws_bytes(n, ra, rb), A.device)
-        check(lib().rt_gram_tc(ptr(A), A.stride(0), ptr(B), B.stride(0), n, ra, rb, ptr(_c(out, f64)), ptr(ws),
-                               stream_ptr()), "rt_gram_tc")
-        return out
     ws = ws if ws is not None else _ws(lib().rt_gram_ws_bytes(n, ra, rb), A.device)
     check(lib().rt_gram(ptr(A), A.stride(0), ptr(B), B.stride(0), n, ra, rb, ptr(_c(out, f64)),
                         int(bool(precise)), ptr(ws), stream_ptr()), "rt_gram")

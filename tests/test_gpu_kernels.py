@@ -464,16 +464,19 @@ def test_score_bce_v3_saturation_and_sharding(cuda_device):
 
 # ------------------------------------------------------------------------------------------------
 # tcgen05 (3xTF32) variants of the tall-skinny passes: fp32-level accuracy required
-@pytest.mark.parametrize("n,ra,rb", [(4097, 200, 200), (40943, 200, 200), (5000, 20, 20), (3000, 10, 40), (2048, 256, 64), (70001, 130, 200)])
-def test_gram_tcgen05(cuda_device, n, ra, rb):
+@pytest.mark.parametrize("n,r", [(4097, 200), (40943, 200), (5000, 20), (3000, 10), (2048, 256), (70001, 130), (64, 33)])
+def test_gram_symmetric_exact(cuda_device, n, r):
+    """A^T A on the fp64 tensor cores (csrc/gram_sym.cu): fp64-exact accumulation, symmetric, deterministic."""
     from rtucker_b200 import ops
-    g = torch.Generator().manual_seed(n + ra + 3)
-    A = torch.randn(n, ra, generator=g)
-    Bm = torch.randn(n, rb, generator=g) + 0.3
-    ref = A.double().T @ Bm.double()
-    out = ops.gram(A.to(cuda_device), Bm.to(cuda_device), tc=True)
-    assert relerr(out, ref) < 5e-6, relerr(out, ref)
-    assert torch.equal(out, ops.gram(A.to(cuda_device), Bm.to(cuda_device), tc=True))
+    g = torch.Generator().manual_seed(n + r + 3)
+    A = (torch.randn(n, r, generator=g) + 0.3) * torch.logspace(0, -4, r)
+    ref = A.double().T @ A.double()
+    Ad = A.to(cuda_device)
+    for precise in (False, True):
+        out = ops.gram(Ad, Ad, precise=precise)
+        scale = torch.sqrt(torch.outer(ref.diag(), ref.diag()))
+        assert float(((out.cpu() - ref) / scale).abs().max()) < 1e-13
+        assert torch.equal(out, out.T) and torch.equal(out, ops.gram(Ad, Ad, precise=precise))
 
 
 @pytest.mark.parametrize("n,rc,rks", [(4097, 200, [200, 200, 200]), (40943, 200, [200, 200]), (3000, 20, [20]),
