@@ -439,11 +439,26 @@ def rooflines(w, n_local, ms_step, stage_ms, score_timing, eval_ms, peaks):
     ts_keys = ["tall_skinny_fit", "retract_gram", "retract_apply", "write_back"]
     ms_c = sum(st.get(k, 0.0) for k in ts_keys) - st.get("small_project", 0.0)
     ach_c = bytes_c / (ms_c * 1e-3) / 1e9 if ms_c > 0 else None
+    # the same passes as arithmetic: 13 N x r x r products (gradient 3, momentum 6, retraction 4) on tcgen05 as 3 TF32
+    # MMAs each, and 4 exact Grams (upper triangle) on the fp64 tensor cores
+    n_terms = 13 if not w["sym"] else 7
+    n_grams = 4 if not w["sym"] else 2
+    rr = float(big[0])
+    flops_apply = n_terms * 2.0 * n_local * rr * rr
+    flops_gram = n_grams * 2.0 * n_local * rr * (rr + 1) / 2
+    tf32_3x_peak = tf_burst / 2.0 / 3.0
+    t_floor_ms = (flops_apply / (tf32_3x_peak * 1e12) + flops_gram / 45e12) * 1e3
     out.append({"family": "c: tall-skinny projection / transport / retraction passes (N x r x r)", "bound": "hbm",
                 "achieved": ach_c, "peak": hbm, "unit": "GB/s", "frac": ach_c / hbm if ach_c else None,
                 "peak_source": src + " hbm_gbs", "algorithmic_bytes_per_step": bytes_c, "ms_per_step": ms_c,
                 "traffic": ncu_traffic("tall_skinny:wn18rr"), "share_of_step": ms_c / tot_eager,
-                "timing_note": "sum of the N-sized stages of stage_ms (eager launches, CUDA events)"})
+                "timing_note": "sum of the N-sized stages of stage_ms (CUDA events)",
+                "arithmetic_view": {
+                    "note": "at r = 200 these passes are arithmetic-bound at fp32 accuracy, not HBM-bound: fp32-accurate "
+                            "products cost 3 TF32 MMAs each (peak = bf16 peak / 2 / 3), the Cholesky of the retraction needs an "
+                            "exactly accumulated Gram (fp64 tensor cores, 45 TFLOP/s nominal)",
+                    "flops_products_per_step": flops_apply, "flops_grams_per_step": flops_gram,
+                    "floor_ms": t_floor_ms, "frac_of_floor": t_floor_ms / ms_c if ms_c > 0 else None}})
     # (c-small) N-independent stage
     sm_keys = ["small_prepare", "small_grad", "small_project", "small_retract_hosvd"]
     out.append({"family": "c-small: N-independent fp64 stage (Gram inverses, projection cores, HOSVD subspaces)",

@@ -158,7 +158,7 @@ struct Ctx {
       err = 1; return;
     }
     void* args[] = {(void*)&prog};
-    if (cudaLaunchCooperativeKernel((const void*)small_exec_kernel, dim3(rt::sm_count()), dim3(kExecThreads), args,
+    if (cudaLaunchCooperativeKernel((const void*)small_exec_kernel, dim3(kExecCtasPerSm * rt::sm_count()), dim3(kExecThreads), args,
                                     smem, s) != cudaSuccess) err = 1;
     ++rt::g_launches;
   }

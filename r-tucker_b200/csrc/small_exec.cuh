@@ -340,7 +340,11 @@ __device__ __forceinline__ void dotfin_unit(const EwPart& op, double* sh) {
   }
 }
 
-__global__ void __launch_bounds__(kExecThreads, 1)
+// Two CTAs per SM: a unit is a chain of latency-bound phases (operand fetch from L2, 16 DMMAs per k-step, the
+// cross-warp reduction), so a second resident CTA overlaps them (measured: -15 % on the whole small stage, with the
+// 128-register cap costing a few hundred bytes of spills in the GEMM unit; tools/prof_one_step.py + RT_EXEC_PROF).
+constexpr int kExecCtasPerSm = 2;
+__global__ void __launch_bounds__(kExecThreads, kExecCtasPerSm)
 small_exec_kernel(const __grid_constant__ Program prog) {
   extern __shared__ __align__(16) double xsm[];      // [8][32][XLD] warp partials
   __shared__ double sh_red[kExecWarps];
@@ -348,6 +352,12 @@ small_exec_kernel(const __grid_constant__ Program prog) {
   unsigned int bar_target = 0u;
   const int nops = prog.nops;
   int i = 0;
+#ifdef RT_EXEC_PROF
+  long long lv_t0 = clock64();
+  __shared__ long long lv_cycles[64];
+  __shared__ int lv_first[64], lv_last[64];
+  int n_lv = 0;
+#endif
   while (i < nops) {
     const int lv = prog.ops[i].level;
     int j = i, total = 0;
@@ -378,9 +388,35 @@ small_exec_kernel(const __grid_constant__ Program prog) {
         default: break;
       }
     }
+#ifdef RT_EXEC_PROF
+    const int i_first = i;
+#endif
     i = j;
     if (i < nops) exec_barrier(prog.bar, bar_target);
+#ifdef RT_EXEC_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const long long now = clock64();
+      if (n_lv < 64) { lv_cycles[n_lv] = now - lv_t0; lv_first[n_lv] = i_first; lv_last[n_lv] = j; ++n_lv; }
+      lv_t0 = clock64();
+    }
+#endif
   }
+#ifdef RT_EXEC_PROF
+  // per-level times of this program (CTA 0's clock, 1.9 GHz assumed); printed after the last level so that the
+  // printf cost (~30 us each) does not perturb the measurement
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int l = 0; l < n_lv; ++l) {
+      int ng = 0, ug = 0, K = 0, m = 0, n = 0, total = 0;
+      for (int q = lv_first[l]; q < lv_last[l]; ++q) {
+        total += prog.ops[q].units;
+        if (prog.ops[q].kind == OP_GEMM) { ++ng; ug += prog.ops[q].units; K = prog.ops[q].g.K1 * prog.ops[q].g.K2; m = prog.ops[q].g.m; n = prog.ops[q].g.n; }
+      }
+      printf("  level %2d: %2d ops (%d gemm, %d gemm units, last m=%d n=%d K=%d) %4d units  %7.1f us\n", l, lv_last[l] - lv_first[l], ng, ug, m, n, K, total,
+             (double)lv_cycles[l] / 1.9e3);
+    }
+    printf("program end (%d ops)\n", nops);
+  }
+#endif
 }
 
 }  // namespace small

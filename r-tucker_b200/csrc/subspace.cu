@@ -171,7 +171,10 @@ __device__ __forceinline__ void sym_tile(int u, int T, int& ti, int& tj) {   // 
   tj = ti + u;
 }
 
-__global__ void __launch_bounds__(kSubThreads, 1)
+// One CTA per SM: with two (296 CTAs, 128 registers) a round costs 18 us instead of 9 (spills in the tile routine and a
+// grid barrier twice as wide outweigh the second wave), tools/subspace_bench.py.
+constexpr int kSubCtasPerSm = 1;
+__global__ void __launch_bounds__(kSubThreads, kSubCtasPerSm)
 subspace_kernel(SubBatch batch) {
   extern __shared__ __align__(16) double ssm[];          // [8][32][SLD] warp partials
   __shared__ double sh_red[kSubWarps];
@@ -448,7 +451,7 @@ int subspace_batch(int count, const double* const* N, const int* n, const int* r
   RT_CHECK_CUDA(cudaMemsetAsync(b.bar, 0, 256, s));
   const size_t smem = sizeof(double) * kSubWarps * ST * SLD;
   RT_CHECK_CUDA(cudaFuncSetAttribute(subspace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = sm_count();
+  int grid = kSubCtasPerSm * sm_count();
   if (grid > 1024) grid = 1024;
   void* args[] = {(void*)&b};
   RT_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)subspace_kernel, dim3(grid), dim3(kSubThreads), args, smem, s));
