@@ -491,15 +491,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="wn18rr", choices=list(WORKLOADS))
-    ap.add_argument("--variant", type=int, default=2,
-                    help="fused score kernel: 0 = fp32 FFMA (1e-5 parity), 1 = tcgen05 TF32 (2e-3), "
+    ap.add_argument("--variant", type=int, default=0,
+                    help="fused score kernel: 0 = fp32 FFMA (1e-5 parity; the default: the only variant that trains from the "
+                         "reference's initialisation, profiles/r02_train_wn18rr_head_v*.json), 1 = tcgen05 TF32 (2e-3), "
                          "2 = warp-specialised tcgen05 with scaled fp16 operands (2e-3)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="reference steps timed for cpu_baseline (0 = skip)")
     ap.add_argument("--torch-gpu-steps", type=int, default=4, help="reference-port steps on CUDA tensors (0 = skip)")
     ap.add_argument("--eval-batches", type=int, default=8)
     ap.add_argument("--no-graphs", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-large-kernel", action="store_true", help="skip timing the fused kernel on the 1M-entity shard")
-    ap.add_argument("--no-strict", action="store_true", help="skip the strict-fp32 (variant 0) run")
+    ap.add_argument("--no-strict", action="store_true", help="skip the run with the other score kernel (variant 2 <-> 0)")
     ap.add_argument("--no-c5", action="store_true", help="skip the synthetic 1M-entity sub-record")
     ap.add_argument("--c5-steps", type=int, default=5)
     args = ap.parse_args()
@@ -535,7 +536,7 @@ def main():
     from rtucker_b200 import lib
 
     w, graph, data_label = load_workload(args.workload)
-    use_graphs = (world == 1 and not args.no_graphs)
+    use_graphs = not args.no_graphs and (world == 1 or os.environ.get("RT_GRAPH_NCCL", "1") == "1")
     total_steps = args.warmup + args.steps
     run = Runner(w, graph, dev, world, rank, group, args.variant, use_graphs, 2 * total_steps)
 
@@ -575,14 +576,21 @@ def main():
     score_timing = time_score_kernel(run, dev, args.variant, args.steps,
                                      large=(world == 1 and args.workload != "synthetic-1m" and not args.no_large_kernel))
 
-    # ---- strict fp32 (variant 0) on the same batches ----
-    strict = None
-    if not args.no_strict and args.variant != 0:
+    # ---- the other score kernel on the same batches ----
+    strict = fast = None
+    if not args.no_strict:
+        other = 2 if args.variant == 0 else 0
         del run.dev_batches
-        run0 = Runner(w, graph, dev, world, rank, group, 0, use_graphs, total_steps)
+        run0 = Runner(w, graph, dev, world, rank, group, other, use_graphs, total_steps)
         ms0, tr0 = run0.timed_resident(args.warmup, args.steps)
-        strict = {"value": tr0 / (ms0 * 1e-3), "ms_per_step": ms0 / args.steps,
-                  "note": "score kernel variant 0 (fp32 FFMA, 1e-5 parity path), everything else identical"}
+        rec = {"value": tr0 / (ms0 * 1e-3), "ms_per_step": ms0 / args.steps}
+        if other == 0:
+            strict = dict(rec, note="score kernel variant 0 (fp32 FFMA, 1e-5 parity path), everything else identical")
+        else:
+            fast = dict(rec, note="score kernel variant 2 (fp16-operand tcgen05, 2e-3 kernel tolerance), everything else identical. "
+                                  "NOT the headline: on real WN18RR from the reference's initialisation it does not learn (valid MRR "
+                                  "stays at chance while variant 0 reaches 0.067 in 30 epochs, profiles/r02_train_wn18rr_head_v*.json): "
+                                  "the 11-bit rounding of the entity factor leaks the large in-span part of dL/dO into the tangent space")
         del run0
         torch.cuda.empty_cache()
 
@@ -641,14 +649,16 @@ def main():
         "metric": metric_name(data_label), "value": value, "unit": "triples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 (score GEMMs: f16 operands / f32 accumulate; N-independent stage f64)" if args.variant == 2 else
-                 ("f32 (score GEMMs tf32)" if args.variant == 1 else "f32"),
+        "dtype": "f32 (score GEMMs: f16 operands / f32 accumulate; N x r x r passes 3xTF32; N-independent stage f64)" if args.variant == 2 else
+                 ("f32 (score GEMMs tf32)" if args.variant == 1 else
+                  "f32 (score GEMMs fp32 FFMA; N x r x r passes 3xTF32 with round-to-nearest partial sums = fp32 accuracy; Grams and N-independent stage f64)"),
         "data": data_label,
         "config": dict(config_dict(w, args), note="entity-sharded over %d GPU(s)" % world),
         "queries_per_s": BATCH * args.steps / (ms * 1e-3),
         "eval_queries_per_s": eval_qps,
         "eval_note": "filtered ranking of the real test split (first batches)" if w.get("eval") is not None else "train queries re-ranked",
         "value_strict_fp32": strict,
+        "value_variant2": fast,
         "e2e": {"value": e2e_value, "unit": "triples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "gpu_launches_note": "kernels of this library executed in the timed region (%d per step; replayed from 2 CUDA graphs per step when graphs are on)" % launches_per_step,

@@ -129,21 +129,18 @@ int rt_score_bce_fwd_bwd(const float* q, const float* qp, const float* O,
                          double* loss_sum, float* H, float* dO,
                          int variant, void* ws, void* stream);
 /* Variant 2 called directly.  o_absmax_hint > 0 promises max |O| <= hint (1.0 for the orthonormal factors of a
- * point on the manifold) and saves the pass that measures it; <= 0 measures it on the device. */
+ * point on the manifold) and saves the pass that measures it; <= 0 measures it on the device.
+ * centre_state (device float[2], may be NULL): [1] = the mean of p - t measured by the previous call (caller-owned,
+ * persistent across steps; initialise to 0.5).  The fp16 gradient operand G is stored centred by that value and the
+ * rank-one part is added back exactly in fp32: without it the 11-bit operand rounds away the 1e-4 deviations of
+ * p around 0.5 that carry the whole signal at the start of training (measured: no learning from the xavier/QR
+ * initialisation).  NULL = no centring. */
 int rt_score_bce_v3_supported(int r2);
 size_t rt_score_bce_v3_ws_bytes(int B, int n_local, int r2);
 int rt_score_bce_v3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
                     int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
-                    float o_absmax_hint, double* loss_sum, float* H, float* dO, void* ws, void* stream);
-/* Same call restricted to some of its phases (bit 0: operand scaling + packing, bit 1: the fused kernel,
- * bit 2: H / loss reduction); a single phase needs a workspace prepared by the earlier ones on the same inputs.
- * bench.py times the fused kernel alone this way. */
-int rt_score_bce_v3_phases(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
-                           int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
-                           float o_absmax_hint, double* loss_sum, float* H, float* dO, void* ws, void* stream,
-                           int phases);
-/* Debug: per-CTA, per-role (producer, MMA issuer, epilogue, flush) cycle counters [grid][4][10] int64; NULL = off. */
-int rt_score_v3_set_profile(long long* dev_buf);
+                    float o_absmax_hint, double* loss_sum, float* H, float* dO, float* centre_state, void* ws,
+                    void* stream);
 
 /* ---- (c) tall-skinny passes over the N x r factors ----------------------------------- */
 /* out[ra, rb] (fp64) = A[n, :ra]^T  B[n, :rb]   (deterministic two-stage reduction).
@@ -287,18 +284,6 @@ int rt_eigh(double* A, int n, double* w, double* V, void* ws, void* stream);
 size_t rt_dominant_subspace_ws_bytes(int n, int r);
 int rt_dominant_subspace(const double* A, int n, int r, double* Y, int* info, void* ws, void* stream);
 
-/* Known-answer self test of the tcgen05 building blocks: D[128,N] = op(A) op(B)^T in TF32
- * (a_mn/b_mn select MN-major operands given as [K][M] / [K][N]); used by tests/test_gpu_tc.py. */
-int rt_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn, int flags,
-                   void* stream);
-/* Same with fp16 operands (kind::f16), the building block of variant 2; and a known-answer test of the
- * shared->global bulk copies: out[0:n] = a (bulk store) then out += b (bulk fp32 add-reduction at the L2). */
-int rt_tc_selftest16(const float* A, const float* B, float* D, int N, int K, int a_mn, int b_mn, int flags,
-                     void* stream);
-int rt_bulk_reduce_selftest(const float* a, const float* b, float* out, int n, void* stream);
-/* Debug: issue `reps` back-to-back kind::f16 MMAs (M = 128, N, K = 16) on shared-memory operands in the K-major
- * (0) or MN-major (1) view; out_dev[0] = cycles to issue, out_dev[1] = cycles until all have completed. */
-int rt_mma_probe(int N, int ksteps, int a_mn, int b_mn, int reps, long long* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

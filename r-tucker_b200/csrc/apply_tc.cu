@@ -22,6 +22,8 @@
 // bulk async copies (TMA, mbarrier complete_tx).
 #include "common.h"
 #include "tc.cuh"
+#include <algorithm>
+#include <math.h>
 
 namespace {
 using namespace rt::tc;
@@ -57,6 +59,13 @@ struct Args {
   const unsigned char* Kimg;          // [total blocks][hi | lo][KB/4 chunks][cs_k bytes]
   uint32_t cs_k, kimg_bytes, stage_bytes;
   int debug;                          // profiling build only (RT_APPLY_DEBUG): 1 no X loads, 2 no K loads, 4 no MMAs, 8 ld.cg
+  // ---- rank mode (MODE 1): rows = entities of the shard, columns of job j = queries [256 j, 256 j + 256) ----
+  const float* thr;                   // [3][Bp]: lo, hi, eqlo logit thresholds per query (Bp = 256 * njobs)
+  const int32_t* target;              // [B] global id of the target entity
+  int B, n_begin;
+  int32_t* greater; int32_t* equal; int32_t* equal_before;
+  int2* cand; int* cand_count; int cand_cap;   // (local entity, query) pairs whose probability must be recomputed exactly
+  double* loss_sum;                   // sum of softplus(z) over every valid (entity, query)
 };
 struct PackArgs {
   const double* K[MAX_JOBS * MAX_TERMS]; int rk[MAX_JOBS * MAX_TERMS]; int blk0[MAX_JOBS * MAX_TERMS + 1];
@@ -141,7 +150,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 }
 
 // HC8 = 8-column groups of the accumulator owned by one epilogue warp (rcp / 16): 13 for r = 200, 16 = any rcp <= 256
-template <int HC8>
+template <int HC8, int MODE = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 apply_tc_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -171,6 +180,12 @@ apply_tc_kernel(const __grid_constant__ Args a) {
 #pragma unroll
     for (int j = 0; j < NACC; ++j) acc[j] = 0.0f;
     PROF_DECL;
+    int cnt[MAX_JOBS][4];                            // rank mode: "greater" counts of columns lane, lane + 32, ... per job
+    double lacc = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < MAX_JOBS; ++jj)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cnt[jj][u] = 0;
     int g = 0;                                       // finished partial sums so far (accumulator = g & 1)
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       int job = 0;
@@ -212,6 +227,62 @@ apply_tc_kernel(const __grid_constant__ Args a) {
         if (lane == 0) mbar_arrive(&bar_acc_empty[ab]);
       }
       PROF_BEGIN;
+      if (MODE == 1) {
+        // ---- filtered-ranking epilogue: acc[c] = logit of (entity row, query column) ----
+        const int e_loc = (tile - J.tile0) * TM + quarter * 32 + lane;       // entity (row) of this thread
+        const bool rv = e_loc < J.n;
+        const int e_glob = a.n_begin + e_loc;
+        const int q0 = job * 256 + half * halfcols;                          // first query of this warp's columns
+        const int Bp = 256 * a.njobs;
+        const float* lo_p = a.thr + q0;
+        const float* hi_p = a.thr + Bp + q0;
+        const float* eq_p = a.thr + 2 * Bp + q0;
+        float lsum = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NACC; ++c) {
+          const int b = q0 + c;
+          const float z = acc[c];
+          const float lo = __ldg(lo_p + c), hi = __ldg(hi_p + c), eqlo = __ldg(eq_p + c);   // uniform over the warp
+          const bool on = rv && b < a.B;
+          const unsigned gm = __ballot_sync(0xffffffffu, on && z > hi);
+          const bool eqd = on && z > eqlo;                                   // certainly p == 1 == p_target
+          const bool cd = on && !eqd && z >= lo && z <= hi;
+          const unsigned em = __ballot_sync(0xffffffffu, eqd);
+          const unsigned cm = __ballot_sync(0xffffffffu, cd);
+          if (lane == (c & 31)) {
+#pragma unroll
+            for (int jj = 0; jj < MAX_JOBS; ++jj)
+              if (jj == job) cnt[jj][c >> 5] += __popc(gm);
+          }
+          if (em) {
+            const int t = __ldg(a.target + b);
+            const unsigned em2 = __ballot_sync(0xffffffffu, eqd && e_glob != t);
+            const unsigned bm = __ballot_sync(0xffffffffu, eqd && e_glob < t);
+            if (lane == 0) {
+              if (em2) atomicAdd(a.equal + b, __popc(em2));
+              if (bm) atomicAdd(a.equal_before + b, __popc(bm));
+            }
+          }
+          if (cm) {
+            if (cd) {
+              const int pos = atomicAdd(a.cand_count, 1);
+              if (pos < a.cand_cap) a.cand[pos] = make_int2(e_loc, b);
+            }
+          }
+          if (on) {
+            // -log(1 - p) with the reference's fp32 semantics: p = 1 / (1 + expf(-z)) is exactly 1 as soon as
+            // expf(-z) <= 2^-24, i.e. z >= 24 ln 2, and BCELoss clamps log(1 - p) = -inf at -100; below that it is
+            // softplus(z)
+            // softplus(z); for z >= 0 through the fp32 probability itself -- 1 - p is quantised to multiples of 2^-24
+            // there and log(1 - p) inherits it (up to 0.35 per element near saturation: 2e-4 of the batch's BCE)
+            const float en = __expf(-fabsf(z));
+            const float p32 = __frcp_rn(1.0f + en);
+            const float sp = z >= 0.0f ? -__logf(1.0f - p32) : __logf(1.0f + en);
+            lsum += (z >= 16.635532f) ? 100.0f : sp;
+          }
+        }
+        lacc += (double)lsum;
+      } else {
       const int row0 = (tile - J.tile0) * TM;
       const int row = quarter * 32 + lane;
       if (row0 + row < J.n) {
@@ -239,7 +310,20 @@ apply_tc_kernel(const __grid_constant__ Args a) {
           }
         }
       }
+      }
       PROF_END(pw1);
+    }
+    if (MODE == 1) {
+#pragma unroll
+      for (int jj = 0; jj < MAX_JOBS; ++jj)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int b = jj * 256 + half * halfcols + u * 32 + lane;
+          if (jj < a.njobs && u * 32 < halfcols && b < a.B && cnt[jj][u]) atomicAdd(a.greater + b, cnt[jj][u]);
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lacc += __shfl_xor_sync(0xffffffffu, lacc, o);
+      if (lane == 0 && lacc != 0.0) atomicAdd(a.loss_sum, lacc);
     }
     if (tid == 0) { PROF_PRINT("epilogue (acc_full, store)"); }
   } else if (warp < kEpiWarps + kProdWarps) {
@@ -459,7 +543,227 @@ Plan make_plan(int rc) {
   return p;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rank mode: filtered ranking without the B x N probability matrix (reference: filter_predictions + metrics,
+// src/utils/utils.py:15-22, src/utils/metrics.py:4-22, on the scores of R_TuckER.py:47-48).
+//
+// The reference ranks fp32 probabilities p = sigmoid(z) with z an fp32 dot product.  The tensor-core pass computes
+// every logit to ~4e-7 relative (3xTF32 + round-to-nearest partial sums) and classifies it against per-query logit
+// thresholds derived from the target's probability: above `hi` the entity certainly has p > p_t, below `lo`
+// certainly p < p_t, above `eqlo` (only when p_t == 1) certainly p == 1 == p_t.  Everything in between -- a few
+// entities per query -- goes to a candidate list and is recomputed by rank_candidates_kernel with the EXACT fp32
+// arithmetic of the dense path (k ascending, one fmaf accumulator, 1 / (1 + expf(-z))), so the counts equal the ones
+// the fp32 kernel produces.  Filtered entities are corrected from their exact probabilities afterwards.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float exact_logit(const float* __restrict__ q, const float* __restrict__ o, int r2) {
+  float z = 0.0f;                                   // same order as score_dense_kernel / target_prob_kernel
+  for (int k = 0; k < r2; ++k) z = fmaf(__ldg(q + k), __ldg(o + k), z);
+  return z;
+}
+__device__ __forceinline__ float sigmoid_ref(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// max_j ||O_j||^2 over the shard (bounds the error of a logit); out is a float bit pattern updated with atomicMax
+__global__ void rank_rownorm_kernel(const float* __restrict__ O, int n_local, int r2, unsigned int* out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float best = 0.0f;
+  for (int j = warp; j < n_local; j += nwarps) {
+    float s = 0.0f;
+    for (int k = lane; k < r2; k += 32) { const float v = __ldg(O + (int64_t)j * r2 + k); s = fmaf(v, v, s); }
+    s = rt::warp_sum(s);
+    best = fmaxf(best, s);
+  }
+  if (lane == 0) atomicMax(out, __float_as_uint(best));
+}
+
+// thresholds thr[3][Bp] (lo, hi, eqlo) of every query from p_target; queries >= B get an empty band
+__global__ void rank_thresholds_kernel(const float* __restrict__ q, const float* __restrict__ p_target, int B, int Bp,
+                                       int r2, const unsigned int* __restrict__ onorm2, float* __restrict__ thr) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= Bp) return;
+  float lo = INFINITY, hi = INFINITY, eqlo = INFINITY;
+  if (b < B) {
+    float s = 0.0f;
+    for (int k = lane; k < r2; k += 32) { const float v = __ldg(q + (int64_t)b * r2 + k); s = fmaf(v, v, s); }
+    s = rt::warp_sum(s);
+    // |z_fp32 - z_tensor| <= (r2 * 2^-24 + 1e-6) * ||q|| ||o||  (fp32 recurrence + 3xTF32); factor 2 of safety
+    const double margin = 2.0 * ((double)r2 * 5.96e-8 + 1e-6) * sqrt((double)s) * sqrt((double)__uint_as_float(*onorm2)) + 1e-6;
+    const float pt = __ldg(p_target + b);
+    if (pt >= 1.0f) {                 // saturated target: nothing is greater; z > 18 certainly gives p == 1
+      lo = 15.0f; hi = INFINITY; eqlo = (float)(18.5 + margin);
+    } else if (pt <= 0.0f) {          // p_t == 0: ties only with other underflowed probabilities
+      lo = -INFINITY; hi = (float)(-80.0 + margin);
+    } else {
+      const double u = (double)nextafterf(pt, 2.0f) - (double)pt;
+      const double plo = (double)pt - 2.0 * u, phi = (double)pt + 2.0 * u;
+      lo = plo > 0.0 ? (float)(log(plo / (1.0 - plo)) - margin - 1e-6) : -INFINITY;
+      hi = phi < 1.0 ? (float)(log(phi / (1.0 - phi)) + margin + 1e-6) : 19.0f;
+      lo = nextafterf(lo, -INFINITY); hi = nextafterf(hi, INFINITY);
+    }
+  }
+  if (lane == 0) { thr[b] = lo; thr[Bp + b] = hi; thr[2 * Bp + b] = eqlo; }
+}
+
+// K images of the query chunks: job j, block kb: element (c, kk) = q[256 j + c][kb * KB + kk]
+__global__ void rank_pack_q_kernel(const float* __restrict__ q, int B, int r2, int nblk, int rcp, unsigned char* img,
+                                   uint32_t cs_k, uint32_t kimg_bytes) {
+  const int blk = blockIdx.x, job = blk / nblk, kb = blk - job * nblk;
+  unsigned char* out = img + (size_t)blk * kimg_bytes;
+  const uint32_t half = (KB / 4) * cs_k;
+  for (int e = threadIdx.x; e < KB * rcp; e += blockDim.x) {
+    const int c = e / KB, kk = e - c * KB;
+    const int b = job * 256 + c, k = kb * KB + kk;
+    const float v = (b < B && k < r2) ? __ldg(q + (int64_t)b * r2 + k) : 0.0f;
+    uint32_t hi, lo;
+    split_tf32(v, hi, lo);
+    const uint32_t off = (uint32_t)(kk >> 2) * cs_k + (uint32_t)(c >> 3) * RS + (uint32_t)(c & 7) * 16u + (uint32_t)(kk & 3) * 4u;
+    *reinterpret_cast<uint32_t*>(out + off) = hi;
+    *reinterpret_cast<uint32_t*>(out + half + off) = lo;
+  }
+}
+
+__global__ void rank_candidates_kernel(const float* __restrict__ q, const float* __restrict__ O, int r2, int n_begin,
+                                       const int32_t* __restrict__ target, const float* __restrict__ p_target,
+                                       const int2* __restrict__ cand, const int* __restrict__ cand_count, int cap,
+                                       int32_t* greater, int32_t* equal, int32_t* equal_before, int* overflow) {
+  const int n = *cand_count;
+  if (n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *overflow = 1; return; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int2 c = cand[i];
+    const int j = n_begin + c.x, b = c.y, t = __ldg(target + b);
+    if (j == t) continue;
+    const float p = sigmoid_ref(exact_logit(q + (int64_t)b * r2, O + (int64_t)c.x * r2, r2));
+    const float pt = __ldg(p_target + b);
+    if (p > pt) atomicAdd(greater + b, 1);
+    else if (p == pt) { atomicAdd(equal + b, 1); if (j < t) atomicAdd(equal_before + b, 1); }
+  }
+}
+
+// one warp per query: entities of the filter list count as p' = 0 (utils.py:19) and as positives of the BCE
+__global__ void rank_filter_fix_kernel(const float* __restrict__ q, const float* __restrict__ O, int B, int r2,
+                                       int n_begin, int n_local, const int32_t* __restrict__ target,
+                                       const float* __restrict__ p_target, const int32_t* __restrict__ flt_off,
+                                       const int32_t* __restrict__ flt_idx, int32_t* greater, int32_t* equal,
+                                       int32_t* equal_before, double* loss_sum, const int* __restrict__ overflow) {
+  if (*overflow) return;                              // the fp32 kernel redoes the batch
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int t = __ldg(target + b);
+  const float pt = __ldg(p_target + b);
+  int dg = 0, de = 0, db = 0;
+  double dl = 0.0;
+  for (int i = __ldg(flt_off + b) + lane; i < __ldg(flt_off + b + 1); i += 32) {
+    const int f = __ldg(flt_idx + i), fl = f - n_begin;
+    if (fl < 0 || fl >= n_local) continue;
+    const float z = exact_logit(q + (int64_t)b * r2, O + (int64_t)fl * r2, r2);
+    const float p = sigmoid_ref(z);
+    const float lp = fmaxf(logf(p), -100.0f), lq = fmaxf(log1pf(-p), -100.0f);
+    dl += (double)(-lp) - (double)(-lq);              // the pass over all entities charged -log(1 - p)
+    if (f != t) {
+      dg -= (p > pt);
+      const int was_eq = (p == pt), is_eq = (0.0f == pt);
+      de += is_eq - was_eq;
+      db += (f < t) ? (is_eq - was_eq) : 0;
+    }
+  }
+  dg = rt::warp_sum(dg); de = rt::warp_sum(de); db = rt::warp_sum(db);
+  dl = rt::warp_sum(dl);
+  if (lane == 0) {
+    if (dg) atomicAdd(greater + b, dg);
+    if (de) atomicAdd(equal + b, de);
+    if (db) atomicAdd(equal_before + b, db);
+    if (dl != 0.0) atomicAdd(loss_sum, dl);
+  }
+}
+
+__global__ void rank_finish_kernel(const double* loss_sum, double* bce_sum, const int* overflow) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && !*overflow && bce_sum) *bce_sum = *loss_sum;
+}
+__global__ void rank_reset_if_overflow_kernel(int B, int32_t* greater, int32_t* equal, int32_t* equal_before,
+                                              const int* overflow) {
+  if (!*overflow) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    greater[i] = 0; equal[i] = 0; equal_before[i] = 0;
+  }
+}
+
+struct RankLayout { size_t scal, thr, kimg, cand, total; int cap, nblk, njobs, Bp; };
+RankLayout rank_layout(int B, int n_local, int r2) {
+  RankLayout L;
+  const Plan p = make_plan(256);
+  L.njobs = rt::cdiv(B, 256); L.Bp = 256 * L.njobs; L.nblk = rt::cdiv(r2, KB);
+  const long long all = (long long)B * n_local;
+  L.cap = (int)std::min<long long>(std::max<long long>(all / 8, 1 << 16), 1 << 22);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += rt::align_up(bytes, 256); return at; };
+  L.scal = take(256);                                 // [0] cand_count, [1] overflow, [2] max ||O_j||^2, [4..5] loss (double)
+  L.thr = take(sizeof(float) * 3 * L.Bp);
+  L.kimg = take((size_t)L.njobs * L.nblk * p.kimg_bytes);
+  L.cand = take(sizeof(int2) * (size_t)L.cap);
+  L.total = o;
+  return L;
+}
+
 }  // namespace
+
+namespace rt {
+bool rank_tc_supported(int B, int n_local, int r2) {
+  return B >= 1 && B <= 256 * MAX_JOBS && r2 >= 64 && r2 <= 1024 && n_local >= 1024 && make_plan(256).nstages >= 3;
+}
+size_t rank_tc_ws_bytes(int B, int n_local, int r2) { return rank_layout(B, n_local, r2).total; }
+// Counts and BCE of one evaluation batch on the tensor cores; *overflow_flag (device int inside ws, returned) is set
+// when the candidate list did not fit: the caller then runs the fp32 kernel gated on that flag.
+int rank_tc(const float* q, const float* O, int B, int r2, int n_begin, int n_local, const int32_t* target,
+            const float* p_target, const int32_t* flt_off, const int32_t* flt_idx, int32_t* greater, int32_t* equal,
+            int32_t* equal_before, double* bce_sum, void* ws, cudaStream_t s, const int** overflow_flag) {
+  const RankLayout L = rank_layout(B, n_local, r2);
+  const Plan p = make_plan(256);
+  char* base = (char*)ws;
+  int* scal = (int*)(base + L.scal);
+  double* loss = (double*)(base + L.scal + 16);
+  float* thr = (float*)(base + L.thr);
+  RT_CHECK_CUDA(cudaMemsetAsync(scal, 0, 256, s));
+  rank_rownorm_kernel<<<rt::sm_count() * 4, 256, 0, s>>>(O, n_local, r2, (unsigned int*)(scal + 2));
+  RT_LAUNCH_CHECK();
+  rank_thresholds_kernel<<<rt::cdiv(L.Bp, 8), 256, 0, s>>>(q, p_target, B, L.Bp, r2, (const unsigned int*)(scal + 2), thr);
+  RT_LAUNCH_CHECK();
+  rank_pack_q_kernel<<<L.njobs * L.nblk, 256, 0, s>>>(q, B, r2, L.nblk, p.rcp, (unsigned char*)(base + L.kimg), p.cs_k,
+                                                       p.kimg_bytes);
+  RT_LAUNCH_CHECK();
+  Args a{};
+  a.rc = 256; a.rcp = p.rcp; a.nstages = p.nstages; a.cs_k = p.cs_k; a.kimg_bytes = p.kimg_bytes;
+  a.stage_bytes = p.stage_bytes; a.Kimg = (const unsigned char*)(base + L.kimg);
+  a.njobs = L.njobs;
+  const int tiles_per_job = rt::cdiv(n_local, TM);
+  for (int j = 0; j < L.njobs; ++j) {
+    Job& J = a.job[j];
+    J.n = n_local; J.nk = 1; J.X[0] = O; J.ldx[0] = r2; J.rk[0] = r2;
+    for (int t = 0; t < MAX_TERMS; ++t) J.blk_end[t] = L.nblk;
+    J.nblk = L.nblk; J.kblk0 = j * L.nblk; J.tile0 = j * tiles_per_job; J.ntiles = tiles_per_job;
+  }
+  a.ntiles = L.njobs * tiles_per_job;
+  a.thr = thr; a.target = target; a.B = B; a.n_begin = n_begin;
+  a.greater = greater; a.equal = equal; a.equal_before = equal_before;
+  a.cand = (int2*)(base + L.cand); a.cand_count = scal; a.cand_cap = L.cap; a.loss_sum = loss;
+  const int grid = a.ntiles < rt::sm_count() ? a.ntiles : rt::sm_count();
+  RT_CHECK_CUDA(rt::ensure_dyn_smem((const void*)apply_tc_kernel<16, 1>, SMEM_LIMIT));
+  apply_tc_kernel<16, 1><<<grid, kThreads, p.smem, s>>>(a);
+  RT_LAUNCH_CHECK();
+  rank_candidates_kernel<<<rt::sm_count() * 2, 256, 0, s>>>(q, O, r2, n_begin, target, p_target, a.cand, scal, L.cap,
+                                                            greater, equal, equal_before, scal + 1);
+  RT_LAUNCH_CHECK();
+  rank_filter_fix_kernel<<<rt::cdiv(B, 8), 256, 0, s>>>(q, O, B, r2, n_begin, n_local, target, p_target, flt_off, flt_idx,
+                                                        greater, equal, equal_before, loss, scal + 1);
+  RT_LAUNCH_CHECK();
+  rank_finish_kernel<<<1, 32, 0, s>>>(loss, bce_sum, scal + 1);
+  RT_LAUNCH_CHECK();
+  rank_reset_if_overflow_kernel<<<rt::cdiv(B, 256), 256, 0, s>>>(B, greater, equal, equal_before, scal + 1);
+  RT_LAUNCH_CHECK();
+  *overflow_flag = scal + 1;
+  return 0;
+}
+}  // namespace rt
 
 // ---- C ABI -------------------------------------------------------------------------------------------
 extern "C" int rt_apply_tc_supported(int rc, int nk, const int* rk_host) {

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include "../../include/rtucker.h"
+#include "../../include/rtucker_debug.h"
 
 namespace rt {
 

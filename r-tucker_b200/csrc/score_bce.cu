@@ -15,6 +15,7 @@
 // H_chunk += G O_tile (accumulated in this CTA's private workspace slice, summed over CTAs in a
 // fixed order afterwards)  and  dO_tile += G^T QP_chunk (registers, across the chunk loop).
 #include "common.h"
+#include <stdlib.h>
 #include <math.h>
 
 namespace {
@@ -51,6 +52,7 @@ struct ScoreArgs {
   int32_t* equal;
   int32_t* equal_before;
   int n_tiles;
+  const int* gate;      // eval only: when not NULL the launch is a no-op unless *gate != 0 (fallback of the tcgen05 ranking)
 };
 
 // acc[i][jj] += sum_k Gk[k][ty*4+i] * Mk[k][tx+16*jj],  k < 64
@@ -76,6 +78,7 @@ template <int CPT, bool EVAL>
 __global__ void __launch_bounds__(256, 1)
 score_kernel(ScoreArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (EVAL && a.gate && *a.gate == 0) return;
   const int r2 = a.r2;
   const int ldw = row_ld(r2, CPT);
   const int k_end = (r2 + 3) / 4 * 4;
@@ -409,7 +412,8 @@ extern "C" int rt_score_bce_v3_supported(int r2);
 extern "C" size_t rt_score_bce_v3_ws_bytes(int B, int n_local, int r2);
 extern "C" int rt_score_bce_v3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
                                int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
-                               float o_absmax_hint, double* loss_sum, float* H, float* dO, void* ws, void* stream);
+                               float o_absmax_hint, double* loss_sum, float* H, float* dO, float* centre_state, void* ws,
+                               void* stream);
 
 extern "C" size_t rt_score_bce_ws_bytes(int B, int n_local, int r2, int variant) {
   if (variant == 1) return rt_score_bce_tc_ws_bytes(B, n_local, r2);
@@ -433,7 +437,7 @@ extern "C" int rt_score_bce_fwd_bwd(const float* q, const float* qp, const float
     RT_REQUIRE(qp == nullptr || qp == q, "rt_score_bce_fwd_bwd: variant 2 computes dO = G^T q only (pass qp = NULL and "
                "fold the right factor into the following rt_apply)");
     return rt_score_bce_v3(q, O, B, r2, n_begin, n_local, n_total, b_total, tgt_off, tgt_idx, label_smoothing, 0.0f,
-                           loss_sum, H, dO, ws, stream);
+                           loss_sum, H, dO, nullptr, ws, stream);
   }
   RT_REQUIRE(variant == 0, "rt_score_bce_fwd_bwd: unknown variant %d", variant);
   cudaStream_t s = (cudaStream_t)stream;
@@ -469,9 +473,31 @@ extern "C" int rt_target_prob(const float* q, const float* O, int B, int r2, int
   return 0;
 }
 
+namespace rt {
+bool rank_tc_supported(int B, int n_local, int r2);
+size_t rank_tc_ws_bytes(int B, int n_local, int r2);
+int rank_tc(const float* q, const float* O, int B, int r2, int n_begin, int n_local, const int32_t* target,
+            const float* p_target, const int32_t* flt_off, const int32_t* flt_idx, int32_t* greater, int32_t* equal,
+            int32_t* equal_before, double* bce_sum, void* ws, cudaStream_t s, const int** overflow_flag);
+}  // namespace rt
+__global__ void gated_reduce_loss_kernel(const double* __restrict__ partial, int n, double* __restrict__ out,
+                                         const int* __restrict__ gate) {
+  if (*gate == 0 || threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += partial[i];
+  out[0] = s;
+}
+// RT_RANK_TC=0 keeps the evaluation on the fp32 FFMA kernel (A/B timing, cross-checks)
+static bool rank_tc_enabled() {
+  static const bool v = [] { const char* e = getenv("RT_RANK_TC"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 extern "C" size_t rt_score_rank_ws_bytes(int B, int n_local, int r2) {
   Plan p = make_plan(n_local, r2, true);
-  return (size_t)p.grid * sizeof(double) + 256;
+  size_t bytes = (size_t)p.grid * sizeof(double) + 256;
+  if (rt::rank_tc_supported(B, n_local, r2)) bytes += rt::rank_tc_ws_bytes(B, n_local, r2);
+  return bytes;
 }
 
 extern "C" int rt_score_rank_fused(const float* q, const float* O, int B, int r2, int n_begin,
@@ -486,6 +512,16 @@ extern "C" int rt_score_rank_fused(const float* q, const float* O, int B, int r2
   RT_CHECK_CUDA(cudaMemsetAsync(equal, 0, sizeof(int32_t) * B, s));
   RT_CHECK_CUDA(cudaMemsetAsync(equal_before, 0, sizeof(int32_t) * B, s));
   Plan p = make_plan(n_local, r2, true);
+  // wide ranks, long shards: logits on the tensor cores (3xTF32), exact fp32 recomputation of the few entities whose
+  // probability could tie with or cross the target's (apply_tc.cu, rank mode); the fp32 kernel below then only
+  // runs -- gated on a device flag, no host synchronisation -- when that candidate list overflowed
+  const int* gate = nullptr;
+  if (rank_tc_enabled() && rt::rank_tc_supported(B, n_local, r2)) {
+    char* tc_ws = (char*)ws + rt::align_up((size_t)p.grid * sizeof(double) + 256, 256);
+    int rc = rt::rank_tc(q, O, B, r2, n_begin, n_local, target, p_target, flt_off, flt_idx, greater, equal,
+                         equal_before, bce_sum, tc_ws, s, &gate);
+    if (rc) return rc;
+  }
   ScoreArgs a{};
   a.q = q; a.qp = q; a.O = O;
   a.B = B; a.r2 = r2; a.n_begin = n_begin; a.n_local = n_local; a.n_total = n_local;
@@ -495,10 +531,12 @@ extern "C" int rt_score_rank_fused(const float* q, const float* O, int B, int r2
   a.target = target; a.p_target = p_target;
   a.greater = greater; a.equal = equal; a.equal_before = equal_before;
   a.n_tiles = p.n_tiles;
+  a.gate = gate;
   int rc = dispatch<true>(a, p, s);
   if (rc) return rc;
   if (bce_sum) {
-    reduce_loss_kernel<<<1, 32, 0, s>>>(a.loss_partial, p.grid, bce_sum, 0);
+    if (gate) gated_reduce_loss_kernel<<<1, 32, 0, s>>>(a.loss_partial, p.grid, bce_sum, gate);
+    else reduce_loss_kernel<<<1, 32, 0, s>>>(a.loss_partial, p.grid, bce_sum, 0);
     RT_LAUNCH_CHECK();
   }
   return 0;

@@ -54,6 +54,8 @@ struct V3Args {
   float t_pos, t_neg, inv_count;
   float* H_ws;                // [grid][n_chunks][r2p * 128] partial H in flush layout
   double* loss_partial;       // [grid]
+  double* gsum_partial;       // [grid] sum of (p - t) over the valid elements (next launch's centre)
+  const float* cq;            // [r2p] centre * inv_count * sum_b q[b, :]: what the centring removed from every dO row
   float* dO;                  // [n_local][r2]
   uint32_t OB, QB;
   long long* prof;            // optional [grid][4 roles][10] cycle counters (debug, rt_score_v3_set_profile)
@@ -124,7 +126,7 @@ score_v3_kernel(V3Args a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t ofull[2], oempty[2], qfull[2], qempty[2], zfull, zfree, gfull, gfree, d2full, d2free, d3full, d3free;
   __shared__ uint32_t tmem_slot;
-  __shared__ double red[kEpiWarps];
+  __shared__ double red[kEpiWarps], redg[kEpiWarps];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* sO[2] = {smem, smem + a.OB};
   unsigned char* sQ[2] = {smem + 2 * a.OB, smem + 2 * a.OB + a.QB};
@@ -263,7 +265,13 @@ score_v3_kernel(V3Args a) {
     const float nk = -zs * 1.4426950408889634f;   // e^{-z} = 2^x, x = raw * nk
     // fast path window: y = x - 8 with |y| < 32, i.e. z in (-27.7, 16.6): p != 1 and p (1 - p) > 1e-12, so none of
     // the reference's saturation branches is taken (the generic path below handles everything else)
-    const float gneg = -a.t_neg * G_SCALE;
+    // G is stored CENTRED: (p - t) - centre, centre = scal[2] = last launch's mean of p - t.  fp16 keeps 11 bits: at
+    // the start of training every p is 0.5 +- 1e-4 and the information is in the deviations, which fp16 (spacing
+    // 2.4e-4 at 0.5) would round away; the rank-one part  centre * (column sums of O, sum of the query rows)  is added
+    // back exactly in fp32 (reduce_H_v3_kernel, the dO stores of the flush warps)
+    const float centre = a.scal[2];
+    const float gneg = -(a.t_neg + centre) * G_SCALE;
+    float gsum = 0.0f;
     // target lists of this thread's rows (one per chunk) stay in registers: bounds + the first two entries
     int ce0[kMaxCachedChunks], ce1[kMaxCachedChunks], ci0[kMaxCachedChunks], ci1[kMaxCachedChunks];
 #pragma unroll
@@ -276,7 +284,7 @@ score_v3_kernel(V3Args a) {
         if (ce1[c] > ce0[c] + 1) ci1[c] = a.idx[ce0[c] + 1];
       }
     }
-    double loss_acc = 0.0;
+    double loss_acc = 0.0, g_acc = 0.0;
     int pair = 0;
     Prof pf; pf.start(PROF && a.prof != nullptr && warp == 2 && lane == 0);
     int lt_e = 0;
@@ -351,6 +359,7 @@ score_v3_kernel(V3Args a) {
               for (int u = 0; u < 2; ++u) {
                 const float s = fmaf(ex2_approx(y[j + u]), 256.0f, 1.0f);    // 1 + e^{-z}
                 const float p = rcp_approx(s);
+                gsum += p;
                 prod *= s;
                 if ((j + u) % 3 == 2 || j + u == 15) { A1 += lg2_approx(prod); prod = 1.0f; }
                 Y2 += y[j + u];
@@ -379,7 +388,7 @@ score_v3_kernel(V3Args a) {
                 const float pq = (1.0f - p) * p;
                 float gv = p - t;
                 if (pq < 1e-12f) gv *= pq * 1e12f;
-                if (valid) Ls -= t * lp + (1.0f - t) * lq; else gv = 0.0f;
+                if (valid) { Ls -= t * lp + (1.0f - t) * lq; gsum += gv + a.t_neg; gv -= centre; } else gv = 0.0f;
                 gq[u] = gv * G_SCALE;
               }
               gp[(16 * g + j) >> 1] = pack_half2(gq[0], gq[1]);
@@ -390,6 +399,8 @@ score_v3_kernel(V3Args a) {
         {
           const float zsum = -0.6931471805599453f * (Y2 + 8.0f * (float)nfast);
           loss_acc += (double)(0.6931471805599453f * A1 + (1.0f - a.t_neg) * zsum + Ls);
+          g_acc += (double)gsum;
+          gsum = 0.0f;
         }
         pf.lap(3);
         if (pair > 0) mbar_wait(&gfree, (pair - 1) & 1);     // GEMM2/3 of the previous pair no longer read G
@@ -408,7 +419,8 @@ score_v3_kernel(V3Args a) {
     }
     if (PROF && pf.on) pf.dump(a.prof + ((size_t)blockIdx.x * 4 + 2) * 10);
     const double wsum = rt::warp_sum(loss_acc);
-    if (lane == 0) red[warp - 2] = wsum;
+    const double gws = rt::warp_sum(g_acc);
+    if (lane == 0) { red[warp - 2] = wsum; redg[warp - 2] = gws; }
   } else {
     // ============================== flush: D2 -> H partial of this CTA, D3 -> dO ==============================
     // H partial: thread (row r) owns H_ws[cta][chunk][quad][r][0..3]; the first visit of a chunk stores, later ones add
@@ -494,25 +506,23 @@ score_v3_kernel(V3Args a) {
           pf.lap(9);
           if (r < n_valid) {
             float* drow = a.dO + (size_t)(n0 + r) * a.r2 + 32 * h;
+            const float* cq = a.cq + 32 * h;           // the rank-one part removed by the centring (same for every row)
+            auto val = [&](int j) { return fmaf(__uint_as_float(v[j]), dscale, __ldg(cq + j)); };
             if (vec8_ok) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 if (8 * j < ncol)
-                  st_v8(drow + 8 * j, __uint_as_float(v[8 * j]) * dscale, __uint_as_float(v[8 * j + 1]) * dscale,
-                        __uint_as_float(v[8 * j + 2]) * dscale, __uint_as_float(v[8 * j + 3]) * dscale,
-                        __uint_as_float(v[8 * j + 4]) * dscale, __uint_as_float(v[8 * j + 5]) * dscale,
-                        __uint_as_float(v[8 * j + 6]) * dscale, __uint_as_float(v[8 * j + 7]) * dscale);
+                  st_v8(drow + 8 * j, val(8 * j), val(8 * j + 1), val(8 * j + 2), val(8 * j + 3), val(8 * j + 4),
+                        val(8 * j + 5), val(8 * j + 6), val(8 * j + 7));
             } else if (vec_ok) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
                 if (4 * j < ncol)
-                  *reinterpret_cast<float4*>(drow + 4 * j) =
-                      make_float4(__uint_as_float(v[4 * j]) * dscale, __uint_as_float(v[4 * j + 1]) * dscale,
-                                  __uint_as_float(v[4 * j + 2]) * dscale, __uint_as_float(v[4 * j + 3]) * dscale);
+                  *reinterpret_cast<float4*>(drow + 4 * j) = make_float4(val(4 * j), val(4 * j + 1), val(4 * j + 2), val(4 * j + 3));
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < ncol) drow[j] = __uint_as_float(v[j]) * dscale;
+                if (j < ncol) drow[j] = val(j);
             }
           }
           if (h + 1 < np) ld_piece(C::D3_COL, h + 1, v);
@@ -527,9 +537,10 @@ score_v3_kernel(V3Args a) {
   fence_before_sync();
   __syncthreads();
   if (tid == 0) {
-    double s = 0.0;
-    for (int w = 0; w < kEpiWarps; ++w) s += red[w];
+    double s = 0.0, sg = 0.0;
+    for (int w = 0; w < kEpiWarps; ++w) { s += red[w]; sg += redg[w]; }
     a.loss_partial[blockIdx.x] = s;
+    a.gsum_partial[blockIdx.x] = sg;
   }
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
@@ -556,8 +567,21 @@ __device__ __forceinline__ float scale_for(float amax) {
 // fp16 images of the query chunks (CTA i packs the image elements i, i + gridDim, ...).
 __global__ void __launch_bounds__(512)
 prep_q_kernel(const float* __restrict__ q, int B, int r2, int ncb, int n_chunks, const unsigned* __restrict__ absbits,
-              float o_hint, float* __restrict__ scal, unsigned char* __restrict__ Qpk, uint32_t QB) {
+              float o_hint, float* __restrict__ scal, unsigned char* __restrict__ Qpk, uint32_t QB,
+              const float* __restrict__ centre_state, float inv_count, float* __restrict__ cq) {
   __shared__ float wmax[16];
+  if (blockIdx.x == 0) {
+    // centre of this launch (the mean of p - t the previous launch measured) and the rank-one term it removes from
+    // every dO row: centre * inv_count * sum_b q[b, :]   (fixed summation order: deterministic)
+    const float c = centre_state ? centre_state[1] : 0.0f;
+    for (int col = threadIdx.x; col < 8 * ncb; col += 512) {
+      float sacc = 0.0f;
+      if (col < r2)
+        for (int b = 0; b < B; ++b) sacc += __ldg(q + (size_t)b * r2 + col);
+      cq[col] = c * inv_count * sacc;
+    }
+    if (threadIdx.x == 0) scal[2] = c;
+  }
   __shared__ float s_scale;
   float m = 0.0f;
   const size_t n = (size_t)B * r2;
@@ -620,9 +644,17 @@ prep_q_kernel(const float* __restrict__ q, int B, int r2, int ncb, int n_chunks,
 // ncb 8-column blocks, zero padded, scaled by scal[which]
 __global__ void __launch_bounds__(256)
 pack16_kernel(const float* __restrict__ src, int n_rows, int r2, int rows_per, int ncb, const float* __restrict__ scal,
-              int which, unsigned char* __restrict__ dst, uint32_t img_bytes) {
+              int which, unsigned char* __restrict__ dst, uint32_t img_bytes, float* __restrict__ tile_colsum) {
   const float s = scal[which];
   const int row0 = blockIdx.x * rows_per;
+  if (tile_colsum) {                       // column sums of this tile's rows in row order (deterministic)
+    for (int col = threadIdx.x; col < 8 * ncb; col += 256) {
+      float acc = 0.0f;
+      if (col < r2)
+        for (int row = 0; row < rows_per && row0 + row < n_rows; ++row) acc += __ldg(src + (size_t)(row0 + row) * r2 + col);
+      tile_colsum[(size_t)blockIdx.x * (8 * ncb) + col] = acc;
+    }
+  }
   unsigned char* img = dst + (size_t)blockIdx.x * img_bytes;
   const uint32_t CS = (uint32_t)rows_per * 16u;
   const bool vec_ok = (r2 % 4 == 0);
@@ -649,11 +681,23 @@ pack16_kernel(const float* __restrict__ src, int n_rows, int r2, int rows_per, i
   }
 }
 
+// hc[col] = centre * inv_count * sum over the tiles of their column sums (fixed order)
+__global__ void colsum_reduce_kernel(const float* __restrict__ tile_colsum, int n_tiles, int r2p, const float* __restrict__ scal,
+                                     float inv_count, float* __restrict__ hc) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= r2p) return;
+  float acc = 0.0f;
+  for (int t = 0; t < n_tiles; ++t) acc += tile_colsum[(size_t)t * r2p + col];
+  hc[col] = scal[2] * inv_count * acc;
+}
+
 // H[b][c] = sum over the CTAs' partial slices, loss = sum of the CTAs' partial sums; both in a fixed order
 // (deterministic).  Block = 32 positions (b, column quad) x 8 slices of the part index; block 0 also sums the loss.
 __global__ void __launch_bounds__(256)
 reduce_H_v3_kernel(const float* __restrict__ H_ws, int nparts, int n_chunks, int r2p, int B, int r2,
-                   float* __restrict__ H, const double* __restrict__ loss_partial, double* __restrict__ loss_out) {
+                   float* __restrict__ H, const double* __restrict__ loss_partial, double* __restrict__ loss_out,
+                   const float* __restrict__ hc, const double* __restrict__ gsum_partial, double valid_count, float t_neg,
+                   float* __restrict__ centre_state) {
   __shared__ float4 part[8][32];
   const int px = threadIdx.x & 31, ks = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + px;
@@ -677,18 +721,22 @@ reduce_H_v3_kernel(const float* __restrict__ H_ws, int nparts, int n_chunks, int
     for (int k = 1; k < 8; ++k) { const float4 v = part[k][px]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
     const int b = c * TB + bl;
     if (b < B) {
-      float* o = H + (size_t)b * r2 + 4 * q;
-      if (4 * q + 0 < r2) o[0] = s.x;
-      if (4 * q + 1 < r2) o[1] = s.y;
-      if (4 * q + 2 < r2) o[2] = s.z;
-      if (4 * q + 3 < r2) o[3] = s.w;
+      float* o = H + (size_t)b * r2 + 4 * q;              // + the rank-one part removed by the centring of G
+      if (4 * q + 0 < r2) o[0] = s.x + hc[4 * q + 0];
+      if (4 * q + 1 < r2) o[1] = s.y + hc[4 * q + 1];
+      if (4 * q + 2 < r2) o[2] = s.z + hc[4 * q + 2];
+      if (4 * q + 3 < r2) o[3] = s.w + hc[4 * q + 3];
     }
   }
   if (blockIdx.x == 0 && threadIdx.x < 32) {
-    double t = 0.0;
-    for (int k = threadIdx.x; k < nparts; k += 32) t += loss_partial[k];
+    double t = 0.0, gs = 0.0;
+    for (int k = threadIdx.x; k < nparts; k += 32) { t += loss_partial[k]; gs += gsum_partial[k]; }
     t = rt::warp_sum(t);            // xor-butterfly: the same association on every lane and every run
-    if (threadIdx.x == 0) loss_out[0] = t;
+    gs = rt::warp_sum(gs);
+    if (threadIdx.x == 0) {
+      loss_out[0] = t;
+      if (centre_state) centre_state[1] = (float)(gs / valid_count - (double)t_neg);   // mean of p - t: the next centre
+    }
   }
 }
 
@@ -697,7 +745,7 @@ long long* g_v3_prof = nullptr;
 struct V3Layout {
   int TN, r2p, ncb, n_tiles, n_chunks, grid;
   uint32_t OB, QB, smem;
-  size_t off_loss, off_scal, off_abs, off_Opk, off_Qpk, total;
+  size_t off_loss, off_gsum, off_cq, off_hc, off_tcs, off_scal, off_abs, off_Opk, off_Qpk, total;
 };
 V3Layout v3_layout(int B, int n_local, int r2) {
   V3Layout L;
@@ -715,6 +763,10 @@ V3Layout v3_layout(int B, int n_local, int r2) {
   L.smem = 2 * L.OB + 2 * L.QB + (tail < 16 * QCS ? 16 * QCS : tail);
   size_t o = rt::align_up((size_t)L.grid * L.n_chunks * L.r2p * TB * sizeof(float), 256);
   L.off_loss = o; o += rt::align_up((size_t)L.grid * sizeof(double), 256);
+  L.off_gsum = o; o += rt::align_up((size_t)L.grid * sizeof(double), 256);
+  L.off_cq = o; o += rt::align_up((size_t)L.r2p * sizeof(float), 256);
+  L.off_hc = o; o += rt::align_up((size_t)L.r2p * sizeof(float), 256);
+  L.off_tcs = o; o += rt::align_up((size_t)(L.n_tiles > 0 ? L.n_tiles : 1) * L.r2p * sizeof(float), 256);
   L.off_scal = o; o += 256;
   L.off_abs = o; o += 256;
   L.off_Opk = o; o += rt::align_up((size_t)(L.n_tiles > 0 ? L.n_tiles : 1) * L.OB, 256);
@@ -735,19 +787,20 @@ extern "C" size_t rt_score_bce_v3_ws_bytes(int B, int n_local, int r2) { return 
 extern "C" int rt_score_bce_v3_phases(const float* q, const float* O, int B, int r2, int n_begin, int n_local,
                                       int n_total, int b_total, const int32_t* tgt_off, const int32_t* tgt_idx,
                                       float label_smoothing, float o_absmax_hint, double* loss_sum, float* H, float* dO,
-                                      void* ws, void* stream, int phases);
+                                      float* centre_state, void* ws, void* stream, int phases);
 
 extern "C" int rt_score_bce_v3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
                                int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
-                               float o_absmax_hint, double* loss_sum, float* H, float* dO, void* ws, void* stream) {
+                               float o_absmax_hint, double* loss_sum, float* H, float* dO, float* centre_state, void* ws,
+                               void* stream) {
   return rt_score_bce_v3_phases(q, O, B, r2, n_begin, n_local, n_total, b_total, tgt_off, tgt_idx, label_smoothing,
-                                o_absmax_hint, loss_sum, H, dO, ws, stream, 7);
+                                o_absmax_hint, loss_sum, H, dO, centre_state, ws, stream, 7);
 }
 
 extern "C" int rt_score_bce_v3_phases(const float* q, const float* O, int B, int r2, int n_begin, int n_local,
                                       int n_total, int b_total, const int32_t* tgt_off, const int32_t* tgt_idx,
                                       float label_smoothing, float o_absmax_hint, double* loss_sum, float* H, float* dO,
-                                      void* ws, void* stream, int phases) {
+                                      float* centre_state, void* ws, void* stream, int phases) {
   RT_REQUIRE(rt_score_bce_v3_supported(r2), "rt_score_bce_v3: r2=%d out of range (1..%d)", r2, R2P_MAX);
   RT_REQUIRE(B >= 1 && B <= 64 * TB && n_local >= 0, "rt_score_bce_v3: bad sizes B=%d (1..%d) n_local=%d", B, 64 * TB, n_local);
   cudaStream_t s = (cudaStream_t)stream;
@@ -771,6 +824,10 @@ extern "C" int rt_score_bce_v3_phases(const float* q, const float* O, int B, int
   a.inv_count = (float)(1.0 / ((double)b_total * (double)n_total));
   a.H_ws = (float*)ws;
   a.loss_partial = (double*)(base + L.off_loss);
+  a.gsum_partial = (double*)(base + L.off_gsum);
+  a.cq = (const float*)(base + L.off_cq);
+  float* hc = (float*)(base + L.off_hc);
+  float* tile_colsum = (float*)(base + L.off_tcs);
   a.dO = dO;
   a.OB = L.OB; a.QB = L.QB;
   a.prof = g_v3_prof;
@@ -782,10 +839,17 @@ extern "C" int rt_score_bce_v3_phases(const float* q, const float* O, int B, int
     RT_LAUNCH_CHECK();
   }
   prep_q_kernel<<<8 * L.n_chunks, 512, 0, s>>>(q, B, r2, L.ncb, L.n_chunks, absbits, o_absmax_hint, (float*)a.scal,
-                                   (unsigned char*)a.Qpk, L.QB);
+                                   (unsigned char*)a.Qpk, L.QB, centre_state, a.inv_count, (float*)a.cq);
   RT_LAUNCH_CHECK();
-  pack16_kernel<<<L.n_tiles, 256, 0, s>>>(O, n_local, r2, L.TN, L.ncb, a.scal, 1, (unsigned char*)a.Opk, L.OB);
+  pack16_kernel<<<L.n_tiles, 256, 0, s>>>(O, n_local, r2, L.TN, L.ncb, a.scal, 1, (unsigned char*)a.Opk, L.OB,
+                                          centre_state ? tile_colsum : nullptr);
   RT_LAUNCH_CHECK();
+  if (centre_state) {
+    colsum_reduce_kernel<<<rt::cdiv(L.r2p, 128), 128, 0, s>>>(tile_colsum, L.n_tiles, L.r2p, a.scal, a.inv_count, hc);
+    RT_LAUNCH_CHECK();
+  } else {
+    RT_CHECK_CUDA(cudaMemsetAsync(hc, 0, (size_t)L.r2p * sizeof(float), s));
+  }
   }
   if (phases & 2) {
 #define RT_V3_LAUNCH(TN_, PROF_)                                                                                   \
@@ -801,7 +865,8 @@ extern "C" int rt_score_bce_v3_phases(const float* q, const float* O, int B, int
   }
   if (phases & 4) {
   const int cnt = L.n_chunks * (L.r2p / 4) * TB;
-  reduce_H_v3_kernel<<<(cnt + 31) / 32, 256, 0, s>>>(a.H_ws, L.grid, L.n_chunks, L.r2p, B, r2, H, a.loss_partial, loss_sum);
+  reduce_H_v3_kernel<<<(cnt + 31) / 32, 256, 0, s>>>(a.H_ws, L.grid, L.n_chunks, L.r2p, B, r2, H, a.loss_partial, loss_sum,
+                                                     hc, a.gsum_partial, (double)B * (double)n_local, a.t_neg, centre_state);
   RT_LAUNCH_CHECK();
   }
   return 0;

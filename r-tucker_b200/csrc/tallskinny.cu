@@ -55,79 +55,7 @@ constexpr int GT = 64;       // output tile edge
 constexpr int GKC = 32;      // rows per smem chunk
 constexpr int GFLUSH = 8;    // chunks accumulated in fp32 before flushing to fp64
 
-template <bool PRECISE>
-__global__ void __launch_bounds__(256)
-gram_partial_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
-                    int n, int ra, int rb, int tiles_b, int rows_per_split,
-                    double* __restrict__ partial) {
-  __shared__ float As[GKC][GT + 4];
-  __shared__ float Bs[GKC][GT + 4];
-  const int tile = blockIdx.x;
-  const int ta = tile / tiles_b, tb = tile % tiles_b;
-  const int a0 = ta * GT, b0 = tb * GT;
-  const int split = blockIdx.y;
-  const int n0 = split * rows_per_split;
-  const int n1 = min(n, n0 + rows_per_split);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-
-  double acc64[4][4];
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { acc64[i][j] = 0.0; acc[i][j] = 0.0f; }
-
-  int chunk = 0;
-  for (int row = n0; row < n1; row += GKC, ++chunk) {
-    // cooperative load: 32 rows x 64 cols per operand, 8 elements per thread
-#pragma unroll
-    for (int it = 0; it < (GKC * GT) / 256; ++it) {
-      const int e = it * 256 + threadIdx.x;
-      const int rr = e / GT, cc = e % GT;
-      const int gr = row + rr;
-      float va = 0.0f, vb = 0.0f;
-      if (gr < n1) {
-        if (a0 + cc < ra) va = __ldg(A + (int64_t)gr * lda + a0 + cc);
-        if (b0 + cc < rb) vb = __ldg(B + (int64_t)gr * ldb + b0 + cc);
-      }
-      As[rr][cc] = va;
-      Bs[rr][cc] = vb;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < GKC; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float a[4] = {av.x, av.y, av.z, av.w};
-      const float bq[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (PRECISE) acc64[i][j] = fma((double)a[i], (double)bq[j], acc64[i][j]);  // exact products
-          else acc[i][j] = fmaf(a[i], bq[j], acc[i][j]);
-        }
-    }
-    __syncthreads();
-    if (!PRECISE && (chunk % GFLUSH) == GFLUSH - 1) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { acc64[i][j] += (double)acc[i][j]; acc[i][j] = 0.0f; }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gi = a0 + ty * 4 + i, gj = b0 + tx * 4 + j;
-      if (gi < ra && gj < rb)
-        partial[((int64_t)split * ra + gi) * rb + gj] = acc64[i][j] + (double)acc[i][j];
-    }
-}
-
-// ---- exact-fp64 Gram on the fp64 tensor cores (what rt_gram(precise = 1) launches) ----
-// Same tiling and the same two-stage, fixed-order reduction as gram_partial_kernel<true>; the products of two fp32
+// Exact Gram A^T B for A != B (A^T A takes gram_sym.cu): 64 x 64 tiles, two-stage fixed-order reduction; the products of two fp32
 // values are exact in fp64 and accumulated in fp64 by mma.sync m8n8k4 (DMMA).  A CTA owns a 64 x 64 output tile over
 // its row split; warp w owns the 8 x 64 strip of A-columns [8w, 8w + 8): eight 8 x 8 accumulator tiles.
 // Row chunks are staged in shared memory as doubles (pitch 72: the four k-rows of a fragment load fall into
@@ -237,89 +165,6 @@ GramPlan gram_plan(int n, int ra, int rb) {
   return p;
 }
 
-// ------------------------------------------------------------------------------------------
-// Apply:  Y = a0*X0 + sum_k X_k K_k
-// ------------------------------------------------------------------------------------------
-constexpr int AT_M = 128;  // rows per tile
-constexpr int AT_N = 64;   // cols per tile
-constexpr int AT_K = 16;
-constexpr int kMaxTerms = 4;
-
-struct ApplyArgs {
-  const float* X[kMaxTerms];
-  int64_t ldx[kMaxTerms];
-  int rk[kMaxTerms];
-  const double* K[kMaxTerms];
-  int nk;
-};
-
-__global__ void __launch_bounds__(256)
-apply_kernel(float* __restrict__ Y, int64_t ldy, int n, int rc, const float* __restrict__ X0,
-             int64_t ldx0, const double* __restrict__ a0_dev, ApplyArgs args) {
-  __shared__ float Xs[AT_K][AT_M + 4];  // transposed: [k][row]
-  __shared__ float Ks[AT_K][AT_N + 4];
-  const int row0 = blockIdx.x * AT_M;
-  const int col0 = blockIdx.y * AT_N;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // ty: 8 rows each, tx: 4 cols each
-  float acc[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
-
-  for (int t = 0; t < args.nk; ++t) {
-    const float* __restrict__ X = args.X[t];
-    const double* __restrict__ K = args.K[t];
-    const int64_t ldx = args.ldx[t];
-    const int rk = args.rk[t];
-    for (int k0 = 0; k0 < rk; k0 += AT_K) {
-      // X tile: 128 rows x 16 k  -> 8 per thread; lanes run along k (contiguous in memory)
-#pragma unroll
-      for (int it = 0; it < (AT_M * AT_K) / 256; ++it) {
-        const int e = it * 256 + threadIdx.x;
-        const int rr = e / AT_K, kk = e % AT_K;
-        const int gr = row0 + rr, gk = k0 + kk;
-        Xs[kk][rr] = (gr < n && gk < rk) ? __ldg(X + (int64_t)gr * ldx + gk) : 0.0f;
-      }
-#pragma unroll
-      for (int it = 0; it < (AT_K * AT_N) / 256; ++it) {
-        const int e = it * 256 + threadIdx.x;
-        const int kk = e / AT_N, cc = e % AT_N;
-        const int gk = k0 + kk, gc = col0 + cc;
-        Ks[kk][cc] = (gk < rk && gc < rc) ? (float)__ldg(K + (int64_t)gk * rc + gc) : 0.0f;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < AT_K; ++kk) {
-        const float4 x0 = *reinterpret_cast<const float4*>(&Xs[kk][ty * 8]);
-        const float4 x1 = *reinterpret_cast<const float4*>(&Xs[kk][ty * 8 + 4]);
-        const float4 kv = *reinterpret_cast<const float4*>(&Ks[kk][tx * 4]);
-        const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-        const float kb[4] = {kv.x, kv.y, kv.z, kv.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], kb[j], acc[i][j]);
-      }
-      __syncthreads();
-    }
-  }
-  const float a0 = a0_dev ? (float)(*a0_dev) : 1.0f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int gr = row0 + ty * 8 + i;
-    if (gr >= n) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gc = col0 + tx * 4 + j;
-      if (gc >= rc) continue;
-      float v = acc[i][j];
-      if (X0) v = fmaf(a0, X0[(int64_t)gr * ldx0 + gc], v);
-      Y[(int64_t)gr * ldy + gc] = v;
-    }
-  }
-}
-
 }  // namespace
 
 extern "C" int rt_gather_rows(const float* table, int rows, int r, int row_begin, const int32_t* idx,
@@ -390,11 +235,7 @@ extern "C" int rt_gram(const float* A, int64_t lda, const float* B, int64_t ldb,
   if (!precise) return rt_gram_v2(A, lda, B, ldb, n, ra, rb, out, ws, stream);
   GramPlan p = gram_plan(n, ra, rb);
   dim3 grid(p.tiles_a * p.tiles_b, p.nsplit);
-  if (precise)
-    gram_dmma_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, n, ra, rb, p.tiles_b, p.rows_per_split, (double*)ws);
-  else
-    gram_partial_kernel<false><<<grid, 256, 0, s>>>(A, lda, B, ldb, n, ra, rb, p.tiles_b,
-                                                    p.rows_per_split, (double*)ws);
+  gram_dmma_kernel<<<grid, 256, 0, s>>>(A, lda, B, ldb, n, ra, rb, p.tiles_b, p.rows_per_split, (double*)ws);
   RT_LAUNCH_CHECK();
   const int count = ra * rb;
   gram_reduce_kernel<<<rt::cdiv(count, 256), 256, 0, s>>>((const double*)ws, p.nsplit, count, out);
@@ -407,21 +248,8 @@ extern "C" int rt_apply(float* Y, int64_t ldy, int n, int rc, const float* X0, i
                         const int64_t* ldx_host, const int* rk_host, const double* const* K_host,
                         void* stream) {
   RT_REQUIRE(n >= 0 && rc > 0 && ldy >= rc, "rt_apply: bad shape n=%d rc=%d", n, rc);
-  RT_REQUIRE(nk >= 0 && nk <= kMaxTerms, "rt_apply: nk=%d out of range (max %d)", nk, kMaxTerms);
+  RT_REQUIRE(nk >= 0 && nk <= 4, "rt_apply: nk=%d out of range (max 4)", nk);
   RT_REQUIRE(X0 != nullptr || nk > 0, "rt_apply: nothing to compute");
   if (n == 0) return 0;
-  if (true) return rt_apply_v2(Y, ldy, n, rc, X0, ldx0, a0_dev, nk, X_host, ldx_host, rk_host, K_host, stream);
-  ApplyArgs a;
-  a.nk = nk;
-  for (int k = 0; k < kMaxTerms; ++k) {
-    a.X[k] = k < nk ? X_host[k] : nullptr;
-    a.ldx[k] = k < nk ? ldx_host[k] : 0;
-    a.rk[k] = k < nk ? rk_host[k] : 0;
-    a.K[k] = k < nk ? K_host[k] : nullptr;
-    if (k < nk) RT_REQUIRE(a.X[k] != Y, "rt_apply: Y may alias X0 only");
-  }
-  dim3 grid(rt::cdiv(n, AT_M), rt::cdiv(rc, AT_N));
-  apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, ldy, n, rc, X0, ldx0, a0_dev, a);
-  RT_LAUNCH_CHECK();
-  return 0;
+  return rt_apply_v2(Y, ldy, n, rc, X0, ldx0, a0_dev, nk, X_host, ldx_host, rk_host, K_host, stream);
 }

@@ -16,6 +16,7 @@ r-sized objects are replicated; the only exchanges are all-reduces of [B,r] row 
 scalar and r x r Gram matrices.  ``ops`` is injectable so the sharding logic can be exercised on CPU
 (gloo) by the tests with the oracle's arithmetic; the product always uses the CUDA ops.
 """
+import os
 from contextlib import contextmanager
 from dataclasses import dataclass
 from typing import List, Optional
@@ -25,6 +26,8 @@ import torch
 from . import ops as cuda_ops
 
 f32, f64 = torch.float32, torch.float64
+# RT_GRAPH_NCCL=0 keeps entity-sharded runs on eager launches (round 1 saw a captured 2-GPU step hang)
+GRAPHS_WITH_NCCL = os.environ.get("RT_GRAPH_NCCL", "1") == "1"
 
 
 @dataclass
@@ -91,6 +94,21 @@ class StepEngine:
         self.M_next = [torch.empty(r, 2 * r, dtype=f64, device=dev) if keep else None for r in self.rank]
         if self.sym:
             self.M_next[2] = self.M_next[1]
+        # Gram buckets: one flat fp64 buffer per Gram phase, the entity factors' blocks adjacent, so that an
+        # entity-sharded run needs ONE all-reduce per phase (norm, retraction) instead of one per factor
+        sizes = [r * r for r in self.rank[: self.nf]]
+        self._gram_flat = [torch.empty(sum(sizes), dtype=f64, device=dev) for _ in range(2)]
+        self._gram_view = []
+        for flat in self._gram_flat:
+            views, o = [], 0
+            for k, r in enumerate(self.rank[: self.nf]):
+                views.append(flat[o:o + r * r].view(r, r))
+                o += r * r
+            self._gram_view.append(views)
+        self._gram_ent = sizes[0]           # the relation factor's block comes first: [r0*r0 | entity blocks ...]
+        # centre of the fp16 gradient operand of score variant 2 (see rt_score_bce_v3): [1] = mean of p - t measured by
+        # the previous step; p = 0.5 at the xavier / QR initialisation
+        self.score_centre = torch.tensor([0.0, 0.5], dtype=f32, device=dev)
         self.loss_buf = torch.zeros(1, dtype=f64, device=dev)
         self.norm_buf = torch.zeros(1, dtype=f64, device=dev)
         self.has_old = False
@@ -195,7 +213,8 @@ class StepEngine:
             if fold_a:
                 ops.score_bce_fwd_bwd(q, None, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
                                       b_total=B, n_begin=self.n_begin, variant=2, out=(bce_sum, H, dO_raw),
-                                      o_absmax=1.0)     # factors of a point on the manifold are orthonormal
+                                      o_absmax=1.0,     # factors of a point on the manifold are orthonormal
+                                      centre=self.score_centre)
             else:
                 ops.score_bce_fwd_bwd(q, qp, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
                                       b_total=B, n_begin=self.n_begin, variant=min(self.score_variant, 1),
@@ -225,8 +244,8 @@ class StepEngine:
             dV_g[k] = v
         ops.scatter_rows_add(dV_g[1], sub_idx, dsA, self.n_begin)
         # ---- norm of the Riemannian gradient ----
-        grams = [ops.gram(v, v) for v in dV_g]
-        self._allreduce(*[grams[k] for k in self._entity_factor_ids()])
+        grams = [ops.gram(v, v, out=self._gram_view[0][k]) for k, v in enumerate(dV_g)]
+        self._allreduce(self._gram_flat[0][self._gram_ent:])
         norm, alpha = small.norm(dS_g, grams[0], grams[1], grams[2] if not sym else grams[1], self.hyper,
                                  adam=self.adam)
         # ---- momentum: transport the previous direction, then combine ----
@@ -269,8 +288,8 @@ class StepEngine:
         core = self.core.data
         # exact fp64 Gram: it feeds the Cholesky that stands in for the reference's QR of [U | W]
         with self._stage("retract_gram"):
-            grams = [ops.gram(v, v, precise=True) for v in dV]
-        self._allreduce(*[grams[k] for k in self._entity_factor_ids()])
+            grams = [ops.gram(v, v, precise=True, out=self._gram_view[1][k]) for k, v in enumerate(dV)]
+        self._allreduce(self._gram_flat[1][self._gram_ent:])
         with self._stage("small_retract_hosvd"):
             core_new, Z1, Z2, _ = small.retract(core, dS_dir, grams[0], grams[1],
                                                 grams[2] if not sym else grams[1], self.hyper,
@@ -324,7 +343,7 @@ class StepEngine:
             "dV_dir": [c(t) for t in self.dV_dir] if keep else None,
             "core_old": c(self.core_old), "dS_dir_old": c(self.dS_dir_old),
             "M_next": [c(t) for t in self.M_next[: self.nf]] if keep else None,
-            "adam": c(self.adam),
+            "adam": c(self.adam), "score_centre": c(self.score_centre),
         }
 
     def load_state_dict(self, sd):
@@ -344,6 +363,8 @@ class StepEngine:
         self.has_old = bool(sd["has_old"])
         if self.adam is not None and sd.get("adam") is not None:
             self.adam.copy_(sd["adam"])
+        if sd.get("score_centre") is not None:
+            self.score_centre.copy_(sd["score_centre"])
         if sd.get("hyper_vals") is not None:
             self._hyper_vals = None
             self._set_hyper(*sd["hyper_vals"])
@@ -354,8 +375,10 @@ class StepEngine:
     # -------------------------------------------------------------------------------------------
     # CUDA-graph front end: same arithmetic, replayed from two captured graphs (fit, step).
     def _graphs_ok(self):
-        return (self.use_graphs and self.group is None and self.dev.type == "cuda" and self.ops is cuda_ops
-                and getattr(self, "timers", None) is None)
+        # with a process group the captured step contains the NCCL all-reduces: every rank captures and replays the
+        # same two graphs in lockstep (capture_error_mode "thread_local": the NCCL watchdog thread may query events)
+        return (self.use_graphs and (self.group is None or GRAPHS_WITH_NCCL) and self.dev.type == "cuda"
+                and self.ops is cuda_ops and getattr(self, "timers", None) is None)
 
     def fit_auto(self, rel_idx, sub_idx, targets: SparseTargets, label_smoothing, reg, lr_hint=0.0,
                  normalize_grad=1.0):
@@ -383,7 +406,7 @@ class StepEngine:
         g = self._graphs.get(key)
         if g is None:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self.fit(si["rel"], si["sub"], SparseTargets(si["off"], si["idx"]), label_smoothing, reg,
                          lr_hint, normalize_grad)
             self._graphs[key] = g
@@ -404,7 +427,7 @@ class StepEngine:
         g = self._graphs.get(("step",))
         if g is None:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self.step(lr)
             self._graphs[("step",)] = g
         g.replay()

@@ -111,12 +111,13 @@ def score_v3_supported(r2):
     return bool(lib().rt_score_bce_v3_supported(int(r2)))
 
 def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None, b_total=None,
-                      n_begin=0, variant=0, out=None, ws=None, o_absmax=None, phases=7):
+                      n_begin=0, variant=0, out=None, ws=None, o_absmax=None, phases=7, centre=None):
     """Returns (loss_sum[1] f64 -- un-normalised, H [B,r2], dO [n_local,r2]).
     variant 2 (warp-specialised fp16 tcgen05 kernel) computes dO = G^T q: qp must be None; ``o_absmax`` is an
     optional promise max|O| <= o_absmax (1.0 for orthonormal factors) that saves the measuring pass;
-    ``phases`` (variant 2 only) selects packing (1), fused kernel (2), reduction (4) for timing."""
-    require_cuda(q, qp, O, tgt_off, tgt_idx)
+    ``phases`` (variant 2 only) selects packing (1), fused kernel (2), reduction (4) for timing; ``centre`` (variant 2,
+    device float[2], persistent across steps, [1] initialised to 0.5) enables the centred gradient operand."""
+    require_cuda(q, qp, O, tgt_off, tgt_idx, centre)
     if variant == 2:
         if qp is not None and qp is not q:
             raise RTuckerError("score_bce_fwd_bwd(variant=2) computes dO = G^T q: pass qp=None")
@@ -133,7 +134,7 @@ def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None,
         check(lib().rt_score_bce_v3_phases(ptr(_c(q, f32)), ptr(_c(O, f32)), B, r2, n_begin, n_local, n_total,
                                            b_total, ptr(_c(tgt_off, i32)), ptr(_c(tgt_idx, i32)),
                                            float(label_smoothing), float(o_absmax or 0.0), ptr(loss), ptr(H),
-                                           ptr(dO), ptr(ws), stream_ptr(), int(phases)), "rt_score_bce_v3")
+                                           ptr(dO), ptr(centre), ptr(ws), stream_ptr(), int(phases)), "rt_score_bce_v3")
         return loss, H, dO
     B, r2 = q.shape
     n_local = O.shape[0]

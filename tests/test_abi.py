@@ -8,10 +8,20 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "rtucker.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", text)))
+def declared_symbols(headers=("rtucker.h", "rtucker_debug.h")):
+    """Entry points of the drop-in boundary (rtucker.h) and of the debug / self-test header (rtucker_debug.h)."""
+    syms = set()
+    for h in headers:
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        syms |= set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", text))
+    return sorted(syms)
+
+
+def test_debug_entry_points_are_not_in_the_public_header():
+    public = declared_symbols(("rtucker.h",))
+    for s in ("rt_tc_selftest", "rt_mma_probe", "rt_score_v3_set_profile", "rt_score_bce_v3_phases"):
+        assert s not in public and s in declared_symbols(("rtucker_debug.h",))
 
 
 def test_header_declares_the_path():

@@ -532,3 +532,79 @@ def test_apply_multi_jobs_inplace_and_copies(cuda_device):
     for (Ud, Uc, dVc), (ref, U, dV) in zip(outs, refs):
         assert relerr(Ud, ref) < 1e-6, relerr(Ud, ref)
         assert torch.equal(Uc.cpu(), U) and torch.equal(dVc.cpu(), dV)
+
+
+@pytest.mark.parametrize("B,N,r2,scale", [(512, 40943, 200, 3.0), (300, 5000, 64, 30.0), (512, 14951, 100, 12.0),
+                                          (64, 2048, 200, 0.0), (130, 4099, 200, 60.0)])
+def test_score_rank_fused_equals_dense_path(cuda_device, B, N, r2, scale):
+    """The tensor-core ranking (logits by 3xTF32, exact fp32 re-check of the entities near the target's probability,
+    csrc/apply_tc.cu rank mode) must give EXACTLY the counts of the dense path (rt_score_dense + rt_rank_filtered =
+    filter_predictions + metrics on the fp32 probabilities): confident scores that saturate to p == 1, duplicated
+    entity rows (exact ties), an all-equal score matrix (every entity a candidate -> the gated fp32 fallback)."""
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(7 * B + N + r2)
+    q = scale * torch.randn(B, r2, generator=g) / r2 ** 0.5
+    O = torch.randn(N, r2, generator=g)
+    O[11] = O[3]; O[N - 2] = O[3]; O[N // 2] = O[N // 2 + 1]          # exact ties
+    target = torch.randint(0, N, (B,), generator=g).int()
+    target[0], target[1], target[2] = 3, 11, N // 2
+    # half of the targets among the best-scored entities of their query (where saturation and ties live)
+    z = q @ O.T
+    top = z.topk(3, dim=1).indices
+    for b in range(3, B, 2):
+        target[b] = int(top[b, b % 3])
+    off, idx = make_csr(B, N, g, max_per_row=8)
+    for b in range(B):
+        idx[off[b]] = target[b]
+    qd, Od, td, offd, idxd = (x.to(dev) for x in (q, O, target, off, idx))
+    P = ops.score_dense(qd, Od)
+    pt = P[torch.arange(B, device=dev), td.long()].contiguous()
+    assert torch.equal(pt, ops.target_prob(qd, Od, td))
+    eg, ee, eb = ops.rank_filtered(P.clone(), td, offd, idxd)
+    cg, ce, cb, bce = ops.score_rank_fused(qd, Od, td, pt, offd, idxd)
+    assert torch.equal(cg, eg) and torch.equal(ce, ee) and torch.equal(cb, eb), \
+        (int((cg != eg).sum()), int((ce != ee).sum()), int((cb != eb).sum()))
+    t = torch.zeros(B, N)
+    for b in range(B):
+        t[b, idx[off[b]:off[b + 1]].long()] = 1
+    bce_ref = torch.nn.functional.binary_cross_entropy(P.cpu(), t, reduction="sum").double()
+    # saturated negatives (p == 1) cost exactly 100 each in BCELoss; a logit within the two arithmetics' 1e-5 of the
+    # saturation point 24 ln 2 may fall on the other side: 83 per such element (only the scale >= 30 cases have any)
+    assert abs(float(bce.cpu()) - float(bce_ref)) / float(bce_ref) < (1e-4 if scale >= 30 else REL)
+
+
+def test_score_bce_v3_keeps_the_signal_at_initialisation(cuda_device):
+    """At the xavier / QR initialisation every probability is 0.5 +- 1e-4 and the whole gradient signal sits in
+    those deviations; an 11-bit gradient operand rounds them away (measured on real WN18RR: variant 2 did not learn
+    at all).  With the centred operand (centre_state, rt_score_bce_v3) the informative part of H and dO -- what is
+    left after removing the rank-one bulk common to all queries / all entities -- must match fp64 to the kernel's
+    stated tolerance, and the centre must move to the measured mean of p - t."""
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    B, N, r2 = 512, 12000, 200
+    O = torch.linalg.qr(torch.randn(N, r2, generator=g, dtype=torch.float64))[0].float().contiguous()
+    q = (0.02 * torch.randn(B, r2, generator=g)).contiguous()
+    off = torch.arange(0, 2 * B + 1, 2, dtype=torch.int32)
+    idx = torch.randint(0, N, (2 * B,), generator=g).int()
+    ls = 0.1
+    z = q.double() @ O.double().T
+    p = torch.sigmoid(z)
+    t = torch.full((B, N), ls / N, dtype=torch.float64)
+    for b in range(B):
+        t[b, idx[off[b]:off[b + 1]].long()] = 1 - ls + ls / N
+    G = (p - t) / (B * N)
+    H_ref, dO_ref = G @ O.double(), G.T @ q.double()
+    assert float(z.abs().max()) < 0.05                       # the regime of the initialisation
+    centre = torch.tensor([0.0, 0.5], device=dev)
+    _, H, dO = ops.score_bce_fwd_bwd(q.to(dev), None, O.to(dev), off.to(dev), idx.to(dev), ls, variant=2, o_absmax=1.0,
+                                     centre=centre)
+    torch.cuda.synchronize()
+    H, dO = H.double().cpu(), dO.double().cpu()
+    assert relerr(H, H_ref) < 1e-5 and relerr(dO, dO_ref) < 1e-5          # dominated by the exact rank-one bulk
+    dev_H, dev_H_ref = H - H.mean(0), H_ref - H_ref.mean(0)               # the part that differs between queries
+    dev_dO, dev_dO_ref = dO - dO.mean(0), dO_ref - dO_ref.mean(0)         # the part that differs between entities
+    assert relerr(dev_H, dev_H_ref) < 5e-3, relerr(dev_H, dev_H_ref)
+    assert relerr(dev_dO, dev_dO_ref) < 5e-3, relerr(dev_dO, dev_dO_ref)
+    assert abs(float(centre[1].cpu()) - float((p - t).mean())) < 1e-6
