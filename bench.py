@@ -358,11 +358,15 @@ def time_score_kernel(run, dev, variant, steps, large):
     v = variant
     if v == 2 and not _ops.score_v3_supported(r2_):
         v = 1
-    ws_s = torch.empty(int(lib().rt_score_bce_ws_bytes(B_, O_fac.shape[0], r2_, v)) + 16, dtype=torch.uint8, device=dev)
+    if v == 3 and not _ops.score_tc3_supported(B_, O_fac.shape[0], r2_):
+        v = 0
+    ws_bytes = lib().rt_score_bce_tc3_ws_bytes(B_, O_fac.shape[0], r2_) if v == 3 else \
+        lib().rt_score_bce_ws_bytes(B_, O_fac.shape[0], r2_, v)
+    ws_s = torch.empty(int(ws_bytes) + 16, dtype=torch.uint8, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def run_score(phases=7):
-        _ops.score_bce_fwd_bwd(qq, None if v == 2 else qq, O_fac, od, xd, LABEL_SMOOTHING, n_total=w["N"], b_total=B_,
+        _ops.score_bce_fwd_bwd(qq, None if v >= 2 else qq, O_fac, od, xd, LABEL_SMOOTHING, n_total=w["N"], b_total=B_,
                                n_begin=run.n_begin, variant=v, out=outs, ws=ws_s, o_absmax=1.0 if v == 2 else None,
                                phases=phases)
     reps = max(10, steps)
@@ -421,10 +425,12 @@ def rooflines(w, n_local, ms_step, stage_ms, score_timing, eval_ms, peaks):
     k_ms = (score_timing or {}).get("kernel_ms") or (score_timing or {}).get("op_ms") or st.get("score_bce_fwd_bwd")
     ach = flops_b / (k_ms * 1e-3) / 1e12 if k_ms else None
     vnt = (score_timing or {}).get("variant", 0)
-    peak_b = tf_burst if vnt else FFMA_PEAK_TF
+    # variant 3 spends 3 TF32 MMAs (half the bf16 rate) per product: its roofline is bf16 peak / 6
+    peak_b = (tf_burst / 6.0) if vnt == 3 else (tf_burst if vnt else FFMA_PEAK_TF)
     entry_b = {"family": "b: fused 1-N score + BCE + backward (variant %d)" % vnt, "bound": "tensor", "achieved": ach,
                "peak": peak_b, "unit": "TFLOP/s", "frac": ach / peak_b if ach else None,
-               "peak_source": (src + " bf16_tflops (burst: kernel timed alone)") if vnt else "nominal FP32 FFMA (148 SMs x 128 lanes x 2 x 1.965 GHz)",
+               "peak_source": (src + " bf16_tflops / 6 (fp32-accurate products = 3 TF32 MMAs at half the bf16 rate; op timed alone)") if vnt == 3 else
+                              ((src + " bf16_tflops (burst: kernel timed alone)") if vnt else "nominal FP32 FFMA (148 SMs x 128 lanes x 2 x 1.965 GHz)"),
                "algorithmic_flops_per_launch": flops_b, "ms_per_launch": k_ms, "traffic": ncu_traffic("score_v3:wn18rr"),
                "share_of_step": share(["score_bce_fwd_bwd"]), "timing": score_timing}
     if score_timing and score_timing.get("large") and score_timing["large"].get("kernel_ms"):
@@ -491,10 +497,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="wn18rr", choices=list(WORKLOADS))
-    ap.add_argument("--variant", type=int, default=0,
-                    help="fused score kernel: 0 = fp32 FFMA (1e-5 parity; the default: the only variant that trains from the "
-                         "reference's initialisation, profiles/r02_train_wn18rr_head_v*.json), 1 = tcgen05 TF32 (2e-3), "
-                         "2 = warp-specialised tcgen05 with scaled fp16 operands (2e-3)")
+    ap.add_argument("--variant", type=int, default=3,
+                    help="fused score kernel: 3 = tcgen05 3xTF32 at fp32 accuracy (1e-5 parity, the default), 0 = fp32 FFMA "
+                         "(1e-5 parity), 1 = tcgen05 TF32 (2e-3), 2 = warp-specialised tcgen05 with scaled fp16 operands "
+                         "(2e-3; does not train from the reference's initialisation, profiles/r02_train_wn18rr_head_v*.json)")
     ap.add_argument("--cpu-steps", type=int, default=6, help="reference steps timed for cpu_baseline (0 = skip)")
     ap.add_argument("--torch-gpu-steps", type=int, default=4, help="reference-port steps on CUDA tensors (0 = skip)")
     ap.add_argument("--eval-batches", type=int, default=8)
@@ -579,13 +585,15 @@ def main():
     # ---- the other score kernel on the same batches ----
     strict = fast = None
     if not args.no_strict:
-        other = 2 if args.variant == 0 else 0
+        other = 0 if args.variant != 0 else 3
         del run.dev_batches
         run0 = Runner(w, graph, dev, world, rank, group, other, use_graphs, total_steps)
         ms0, tr0 = run0.timed_resident(args.warmup, args.steps)
         rec = {"value": tr0 / (ms0 * 1e-3), "ms_per_step": ms0 / args.steps}
         if other == 0:
             strict = dict(rec, note="score kernel variant 0 (fp32 FFMA, 1e-5 parity path), everything else identical")
+        elif other == 3:
+            fast = dict(rec, note="score kernel variant 3 (3xTF32 tensor-core path at fp32 accuracy), everything else identical")
         else:
             fast = dict(rec, note="score kernel variant 2 (fp16-operand tcgen05, 2e-3 kernel tolerance), everything else identical. "
                                   "NOT the headline: on real WN18RR from the reference's initialisation it does not learn (valid MRR "
@@ -651,7 +659,9 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 (score GEMMs: f16 operands / f32 accumulate; N x r x r passes 3xTF32; N-independent stage f64)" if args.variant == 2 else
                  ("f32 (score GEMMs tf32)" if args.variant == 1 else
-                  "f32 (score GEMMs fp32 FFMA; N x r x r passes 3xTF32 with round-to-nearest partial sums = fp32 accuracy; Grams and N-independent stage f64)"),
+                  ("f32 (score GEMMs and N x r x r passes: 3xTF32 on tcgen05 with round-to-nearest partial sums = fp32 accuracy, "
+                   "1e-5 parity; Grams and N-independent stage f64)" if args.variant == 3 else
+                   "f32 (score GEMMs fp32 FFMA; N x r x r passes 3xTF32 with round-to-nearest partial sums = fp32 accuracy; Grams and N-independent stage f64)")),
         "data": data_label,
         "config": dict(config_dict(w, args), note="entity-sharded over %d GPU(s)" % world),
         "queries_per_s": BATCH * args.steps / (ms * 1e-3),

@@ -51,7 +51,12 @@ struct Job {
   const float* X[MAX_TERMS]; int64_t ldx[MAX_TERMS];
   float* copy[MAX_TERMS]; int64_t ldc[MAX_TERMS];
   int rk[MAX_TERMS]; int blk_end[MAX_TERMS];        // blk_end[t]: first block index after term t
+  int xt[MAX_TERMS];                                // term given transposed: element (row, k) at X + k * ldx + row
   int n, nk, nblk, kblk0, tile0, ntiles;
+  // replication: the job is run `reps` times on shifted operands (row chunks of a long contraction whose partial
+  // results are summed afterwards): rep r uses X_t + r * x_rep[t], Y + r * y_rep, K blocks kblk0 + r * nblk
+  int reps, tiles_per_rep;
+  int64_t x_rep[MAX_TERMS], y_rep;
 };
 struct Args {
   Job job[MAX_JOBS];
@@ -66,9 +71,16 @@ struct Args {
   int32_t* greater; int32_t* equal; int32_t* equal_before;
   int2* cand; int* cand_count; int cand_cap;   // (local entity, query) pairs whose probability must be recomputed exactly
   double* loss_sum;                   // sum of softplus(z) over every valid (entity, query)
+  // ---- score mode (MODE 2): the same logits; the epilogue writes G[e][b] = dBCE/dz for all-negative targets ----
+  float* G; int64_t ldg;              // [n_local][ldg] (ldg = 256 * njobs)
+  float t_neg, inv_count;
+  double* loss_partial;               // [grid]
 };
 struct PackArgs {
-  const double* K[MAX_JOBS * MAX_TERMS]; int rk[MAX_JOBS * MAX_TERMS]; int blk0[MAX_JOBS * MAX_TERMS + 1];
+  const void* K[MAX_JOBS * MAX_TERMS]; int rk[MAX_JOBS * MAX_TERMS]; int blk0[MAX_JOBS * MAX_TERMS + 1];
+  int f32[MAX_JOBS * MAX_TERMS];            // source type of the term: fp64 (0) or fp32 (1), row-major [rows][rc]
+  int rep_blocks[MAX_JOBS * MAX_TERMS];     // blocks per repetition (0: not replicated); rep r reads rows r * rk + k
+  int rows_total[MAX_JOBS * MAX_TERMS];     // rows that exist in the source (beyond: zeros)
   int nterms, rc, rcp; unsigned char* img; uint32_t cs_k, kimg_bytes;
 };
 
@@ -89,16 +101,20 @@ __global__ void pack_K_kernel(PackArgs a) {
   const int blk = blockIdx.x;
   int t = 0;
   while (t + 1 < a.nterms && blk >= a.blk0[t + 1]) ++t;
-  const int kb = blk - a.blk0[t];
-  const double* __restrict__ K = a.K[t];
+  int kb = blk - a.blk0[t], rep = 0;
+  if (a.rep_blocks[t] > 0) { rep = kb / a.rep_blocks[t]; kb -= rep * a.rep_blocks[t]; }
   const int rk = a.rk[t];
+  const int64_t row_base = (int64_t)rep * rk;
   unsigned char* img = a.img + (size_t)blk * a.kimg_bytes;
   const uint32_t half = (KB / 4) * a.cs_k;
   for (int e = threadIdx.x; e < KB * a.rcp; e += blockDim.x) {
     const int kk = e / a.rcp, c = e - kk * a.rcp;
     const int k = kb * KB + kk;
     float v = 0.0f;
-    if (k < rk && c < a.rc) v = (float)K[(int64_t)k * a.rc + c];
+    if (k < rk && c < a.rc && row_base + k < a.rows_total[t]) {
+      const int64_t at = (row_base + k) * a.rc + c;
+      v = a.f32[t] ? __ldg(reinterpret_cast<const float*>(a.K[t]) + at) : (float)reinterpret_cast<const double*>(a.K[t])[at];
+    }
     uint32_t hi, lo;
     split_tf32(v, hi, lo);
     const uint32_t off = (uint32_t)(kk >> 2) * a.cs_k + (uint32_t)(c >> 3) * RS + (uint32_t)(c & 7) * 16u + (uint32_t)(kk & 3) * 4u;
@@ -134,7 +150,7 @@ struct Cursor {
       job = 0;
       while (job + 1 < a.njobs && tile >= a.job[job + 1].tile0) ++job;
       nblk = a.job[job].nblk;
-      kblk0 = a.job[job].kblk0;
+      kblk0 = a.job[job].kblk0 + ((tile - a.job[job].tile0) / a.job[job].tiles_per_rep) * nblk;
     }
   }
   __device__ __forceinline__ void init(const Args& a) { tile = blockIdx.x; blk = 0; job = 0; nblk = 1; kblk0 = 0; set_job(a); }
@@ -229,7 +245,7 @@ apply_tc_kernel(const __grid_constant__ Args a) {
       PROF_BEGIN;
       if (MODE == 1) {
         // ---- filtered-ranking epilogue: acc[c] = logit of (entity row, query column) ----
-        const int e_loc = (tile - J.tile0) * TM + quarter * 32 + lane;       // entity (row) of this thread
+        const int e_loc = (tile - J.tile0) * TM + quarter * 32 + lane;       // entity (row) of this thread (reps == 1)
         const bool rv = e_loc < J.n;
         const int e_glob = a.n_begin + e_loc;
         const int q0 = job * 256 + half * halfcols;                          // first query of this warp's columns
@@ -282,12 +298,50 @@ apply_tc_kernel(const __grid_constant__ Args a) {
           }
         }
         lacc += (double)lsum;
+      } else if (MODE == 2) {
+        // ---- score epilogue: G[e][b] = dBCE/dz and the BCE itself for ALL-NEGATIVE targets (t = t_neg), with the
+        //      reference's fp32 semantics (score_bce.cu: p = 1 / (1 + expf(-z)), log terms clamped at -100, gradient
+        //      scaled by p (1 - p) / max(p (1 - p), 1e-12)); the sparse positives are fixed up afterwards ----
+        const int e_loc = (tile - J.tile0) * TM + quarter * 32 + lane;
+        const bool rv = e_loc < J.n;
+        const int q0 = job * 256 + half * halfcols;
+        float* grow = a.G + (int64_t)e_loc * a.ldg + q0;
+        const float tn = a.t_neg, inv = a.inv_count;
+        float lsum = 0.0f;
+#pragma unroll
+        for (int c4 = 0; c4 < NACC; c4 += 4) {
+          float gv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float z = acc[c4 + u];
+            const float en = __expf(-fabsf(z));
+            const float l1p = en < 1e-3f ? en * (1.0f - 0.5f * en) : __logf(1.0f + en);     // log(1 + e^-|z|)
+            const float r = __frcp_rn(1.0f + en);
+            float p, lp, lq;
+            if (z >= 0.0f) {                         // p in [0.5, 1]: 1 - p is exact, p == 1 from z = 24 ln 2 on
+              p = r; lp = -l1p;
+              lq = (z >= 16.635532f) ? -100.0f : __logf(1.0f - p);
+            } else {
+              p = en * r; lq = -l1p;
+              lp = fmaxf(z - l1p, -100.0f);
+            }
+            const float pq = (1.0f - p) * p;
+            float g = (p - tn) * inv;
+            if (pq < 1e-12f) g *= pq * 1e12f;
+            const bool on = rv && (q0 + c4 + u) < a.B;
+            if (on) lsum -= tn * lp + (1.0f - tn) * lq;
+            gv[u] = on ? g : 0.0f;
+          }
+          if (rv) *reinterpret_cast<float4*>(grow + c4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+        }
+        lacc += (double)lsum;
       } else {
-      const int row0 = (tile - J.tile0) * TM;
+      const int lt = tile - J.tile0, rep = lt / J.tiles_per_rep;
+      const int row0 = (lt - rep * J.tiles_per_rep) * TM;
       const int row = quarter * 32 + lane;
       if (row0 + row < J.n) {
         const float a0 = J.a0 ? (float)(*J.a0) : 1.0f;
-        float* y = J.Y + (int64_t)(row0 + row) * J.ldy + half * halfcols;
+        float* y = J.Y + (int64_t)rep * J.y_rep + (int64_t)(row0 + row) * J.ldy + half * halfcols;
         const float* x0 = J.X0 ? J.X0 + (int64_t)(row0 + row) * J.ldx0 + half * halfcols : nullptr;
         const int cmax = min(halfcols, a.rc - half * halfcols);     // valid columns of this half
         const bool vec = ((J.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(J.Y) & 15) == 0) &&
@@ -325,14 +379,20 @@ apply_tc_kernel(const __grid_constant__ Args a) {
       for (int o = 16; o > 0; o >>= 1) lacc += __shfl_xor_sync(0xffffffffu, lacc, o);
       if (lane == 0 && lacc != 0.0) atomicAdd(a.loss_sum, lacc);
     }
+    if (MODE == 2) {                                  // one slot per epilogue warp: summed later in a fixed order
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lacc += __shfl_xor_sync(0xffffffffu, lacc, o);
+      if (lane == 0) a.loss_partial[blockIdx.x * kEpiWarps + warp] = lacc;
+    }
     if (tid == 0) { PROF_PRINT("epilogue (acc_full, store)"); }
   } else if (warp < kEpiWarps + kProdWarps) {
     // ================= producers: X block -> hi / lo operand images (+ optional raw copy) =================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
     const int ptid = tid - kEpiWarps * 32;             // 0 .. kProdWarps*32-1
-    const int ch = ptid & 3, r0 = ptid >> 2;           // this thread: 16-byte chunk `ch` of rows r0, r0+RSTEP, ...
-    constexpr int RSTEP = kProdWarps * 8;              // rows between two items of a thread
-    const uint32_t sm_off = (uint32_t)ch * CS_X + (uint32_t)(r0 >> 3) * RS + (uint32_t)(r0 & 7) * 16u;
+    // thread -> (16-byte chunk ch of the block's 4, rows r0, r0 + rstep, ...).  Row-major terms: 4 lanes cover the 64
+    // contiguous bytes of a row; transposed terms (element (row, k) at X + k * ld + row): a warp per chunk, lanes along
+    // the rows, so that the loads coalesce either way
+    constexpr int RSTEP_N = kProdWarps * 8, RSTEP_T = 32;
     // blocks this CTA will produce
     int todo = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -342,14 +402,15 @@ apply_tc_kernel(const __grid_constant__ Args a) {
     }
     // ---- load side: a (tile, term, k-block) walk whose per-term state lives in registers ----
     int l_tile = blockIdx.x - gridDim.x, l_job = 0, l_t = 0, l_nk = 0, l_kb = 0, l_nkb = 0;
-    int l_k = 0, l_rk = 0, l_nitems = 0, l_left = todo;
-    bool l_fast = false;
+    int l_k = 0, l_rk = 0, l_nitems = 0, l_left = todo, l_rep = 0, l_trow = 0, l_rows = 0;
+    bool l_fast = false, l_xt = false;
     const float* l_p = nullptr; float* l_q = nullptr;
-    int64_t l_pstep = 0, l_qstep = 0;
-    int l_row = 0;
+    int64_t l_pstep = 0, l_qstep = 0, l_kstep = 0, l_ld = 0;
+    uint32_t l_smoff = 0, l_smstep = 0;
     float4 xf[PF][XPT];
     float* cq[PF]; int64_t cqstep[PF]; int cni[PF];    // raw-copy destination of the block held in slot u (cni < 0: slow path)
-    auto load_next = [&](float4 (&x)[XPT], float*& q, int64_t& qstep, int& ni_copy) {
+    uint32_t csm[PF], csmstep[PF];                     // shared-memory offset of the thread's first item and item stride
+    auto load_next = [&](float4 (&x)[XPT], float*& q, int64_t& qstep, int& ni_copy, uint32_t& smo, uint32_t& sms) {
       if (l_kb == l_nkb) {                             // next term, or next tile
         if (++l_t >= l_nk) {
           l_tile += gridDim.x;
@@ -357,27 +418,42 @@ apply_tc_kernel(const __grid_constant__ Args a) {
           while (l_job + 1 < a.njobs && l_tile >= a.job[l_job + 1].tile0) ++l_job;
           const Job& J = a.job[l_job];
           l_nk = J.nk; l_t = 0;
-          l_row = (l_tile - J.tile0) * TM + r0;
-          const int left = min(TM, J.n - (l_tile - J.tile0) * TM) - r0;
-          l_nitems = left <= 0 ? 0 : (left + RSTEP - 1) / RSTEP;
+          const int lt = l_tile - J.tile0;
+          l_rep = lt / J.tiles_per_rep;
+          l_trow = (lt - l_rep * J.tiles_per_rep) * TM;
+          l_rows = min(TM, J.n - l_trow);
         }
         const Job& J = a.job[l_job];
-        const float* X = J.X[l_t];
-        const int64_t ld = J.ldx[l_t];
+        l_xt = J.xt[l_t] != 0;
+        const int ch = l_xt ? (ptid >> 5) : (ptid & 3), r0 = l_xt ? (ptid & 31) : (ptid >> 2);
+        const int rstep = l_xt ? RSTEP_T : RSTEP_N;
+        l_smoff = (uint32_t)ch * CS_X + (uint32_t)(r0 >> 3) * RS + (uint32_t)(r0 & 7) * 16u;
+        l_smstep = (uint32_t)(rstep / 8) * RS;
+        const int left = l_rows - r0;
+        l_nitems = left <= 0 ? 0 : (left + rstep - 1) / rstep;
+        const float* X = J.X[l_t] + (int64_t)l_rep * J.x_rep[l_t];
+        l_ld = J.ldx[l_t];
         l_rk = J.rk[l_t];
         l_kb = 0; l_nkb = J.blk_end[l_t] - (l_t ? J.blk_end[l_t - 1] : 0);
         l_k = 4 * ch;
-        l_p = X + (int64_t)l_row * ld + l_k;
-        l_pstep = (int64_t)RSTEP * ld;
-        l_fast = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((l_rk & 3) == 0);
+        const int row = l_trow + r0;
+        if (l_xt) {
+          l_p = X + (int64_t)l_k * l_ld + row;
+          l_pstep = rstep; l_kstep = (int64_t)KB * l_ld;
+          l_fast = false;
+        } else {
+          l_p = X + (int64_t)row * l_ld + l_k;
+          l_pstep = (int64_t)rstep * l_ld; l_kstep = KB;
+          l_fast = ((l_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((l_rk & 3) == 0);
+        }
         l_q = nullptr; l_qstep = 0;
-        if (J.copy[l_t]) {
-          l_q = J.copy[l_t] + (int64_t)l_row * J.ldc[l_t] + l_k;
-          l_qstep = (int64_t)RSTEP * J.ldc[l_t];
+        if (J.copy[l_t] && !l_xt) {
+          l_q = J.copy[l_t] + (int64_t)row * J.ldc[l_t] + l_k;
+          l_qstep = (int64_t)rstep * J.ldc[l_t];
           l_fast = l_fast && ((J.ldc[l_t] & 3) == 0) && ((reinterpret_cast<uintptr_t>(J.copy[l_t]) & 15) == 0);
         }
       }
-      q = l_q; qstep = l_qstep;
+      q = l_q; qstep = l_qstep; smo = l_smoff; sms = l_smstep;
       if (l_fast) {
         const int ni = (l_k < l_rk) ? l_nitems : 0;
         ni_copy = ni;
@@ -387,28 +463,29 @@ apply_tc_kernel(const __grid_constant__ Args a) {
           x[i] = i < nl ? __ldg(reinterpret_cast<const float4*>(l_p + i * l_pstep)) : make_float4(0.f, 0.f, 0.f, 0.f);
       } else {
         ni_copy = -1 - (l_nitems + 16 * max(0, min(4, l_rk - l_k)));
+        const int64_t ks = l_xt ? l_ld : 1;            // distance between consecutive k of one row
 #pragma unroll
         for (int i = 0; i < XPT; ++i) {
           const float* p = l_p + i * l_pstep;
           const bool on = i < l_nitems && !DBG(0);
-          x[i].x = (on && l_k + 0 < l_rk) ? __ldg(p + 0) : 0.f;
-          x[i].y = (on && l_k + 1 < l_rk) ? __ldg(p + 1) : 0.f;
-          x[i].z = (on && l_k + 2 < l_rk) ? __ldg(p + 2) : 0.f;
-          x[i].w = (on && l_k + 3 < l_rk) ? __ldg(p + 3) : 0.f;
+          x[i].x = (on && l_k + 0 < l_rk) ? __ldg(p) : 0.f;
+          x[i].y = (on && l_k + 1 < l_rk) ? __ldg(p + ks) : 0.f;
+          x[i].z = (on && l_k + 2 < l_rk) ? __ldg(p + 2 * ks) : 0.f;
+          x[i].w = (on && l_k + 3 < l_rk) ? __ldg(p + 3 * ks) : 0.f;
         }
       }
-      ++l_kb; l_k += KB; l_p += KB; if (l_q) l_q += KB;
+      ++l_kb; l_k += KB; l_p += l_kstep; if (l_q) l_q += KB;
       --l_left;
     };
     PROF_DECL;
     int ps = 0; uint32_t pphase = 0;                   // stage / parity of the produce side
     bool wrapped = false;
-    auto produce = [&](const float4 (&x)[XPT], float* q, int64_t qstep, int ni_copy) {
+    auto produce = [&](const float4 (&x)[XPT], float* q, int64_t qstep, int ni_copy, uint32_t smo, uint32_t sms) {
       PROF_BEGIN;
       if (wrapped) mbar_wait(&bar_empty[ps], pphase ^ 1u);
       PROF_END(pw0);
       PROF_BEGIN;
-      unsigned char* st = smem + (size_t)ps * a.stage_bytes + sm_off;
+      unsigned char* st = smem + (size_t)ps * a.stage_bytes + smo;
 #pragma unroll
       for (int i = 0; i < XPT; ++i) {
         const float4 v = x[i];
@@ -418,8 +495,8 @@ apply_tc_kernel(const __grid_constant__ Args a) {
         split_tf32_fast(v.x, h.x, l.x); split_tf32_fast(v.y, h.y, l.y);
         split_tf32_fast(v.z, h.z, l.z); split_tf32_fast(v.w, h.w, l.w);
         }
-        *reinterpret_cast<uint4*>(st + i * (RSTEP / 8) * RS) = h;
-        *reinterpret_cast<uint4*>(st + X_HALF + i * (RSTEP / 8) * RS) = l;
+        *reinterpret_cast<uint4*>(st + i * sms) = h;
+        *reinterpret_cast<uint4*>(st + X_HALF + i * sms) = l;
       }
       if (q) {                                         // raw copy of the block (the data is in registers by now)
         if (ni_copy >= 0) {
@@ -447,14 +524,14 @@ apply_tc_kernel(const __grid_constant__ Args a) {
     };
 #pragma unroll
     for (int u = 0; u < PF; ++u)
-      if (l_left > 0) load_next(xf[u], cq[u], cqstep[u], cni[u]);
+      if (l_left > 0) load_next(xf[u], cq[u], cqstep[u], cni[u], csm[u], csmstep[u]);
     while (todo > 0) {
 #pragma unroll
       for (int u = 0; u < PF; ++u) {
         if (todo > 0) {
-          produce(xf[u], cq[u], cqstep[u], cni[u]);
+          produce(xf[u], cq[u], cqstep[u], cni[u], csm[u], csmstep[u]);
           --todo;
-          if (l_left > 0) load_next(xf[u], cq[u], cqstep[u], cni[u]);
+          if (l_left > 0) load_next(xf[u], cq[u], cqstep[u], cni[u], csm[u], csmstep[u]);
         }
       }
     }
@@ -741,6 +818,7 @@ int rank_tc(const float* q, const float* O, int B, int r2, int n_begin, int n_lo
     J.n = n_local; J.nk = 1; J.X[0] = O; J.ldx[0] = r2; J.rk[0] = r2;
     for (int t = 0; t < MAX_TERMS; ++t) J.blk_end[t] = L.nblk;
     J.nblk = L.nblk; J.kblk0 = j * L.nblk; J.tile0 = j * tiles_per_job; J.ntiles = tiles_per_job;
+    J.reps = 1; J.tiles_per_rep = tiles_per_job;
   }
   a.ntiles = L.njobs * tiles_per_job;
   a.thr = thr; a.target = target; a.B = B; a.n_begin = n_begin;
@@ -788,37 +866,58 @@ extern "C" size_t rt_apply_multi_ws_bytes(int njobs, const rt_apply_job* jobs, i
   return blocks * p.kimg_bytes + 256;
 }
 
-extern "C" int rt_apply_multi(int njobs, const rt_apply_job* jobs, int rc, void* ws, void* stream) {
-  RT_REQUIRE(njobs >= 1 && njobs <= MAX_JOBS, "rt_apply_multi: 1..%d jobs per launch, got %d", MAX_JOBS, njobs);
-  RT_REQUIRE(ws != nullptr, "rt_apply_multi: workspace is NULL");
+namespace {
+// internal job description: rt_apply_job plus what the score kernel needs (fp32 right factors, transposed and
+// replicated terms)
+struct TermSpec { const float* X; int64_t ldx; int rk; const void* K; int k_f32; int xt; float* copy; int64_t ldc;
+                  int64_t x_rep; int rows_total; };
+struct JobSpec { float* Y; int64_t ldy; int n; const float* X0; int64_t ldx0; const double* a0; int nk; TermSpec t[MAX_TERMS];
+                 int reps; int64_t y_rep; };
+
+size_t run_apply_ws_bytes(int njobs, const JobSpec* jobs, int rc) {
   const Plan p = make_plan(rc);
-  cudaStream_t s = (cudaStream_t)stream;
+  size_t blocks = 0;
+  for (int j = 0; j < njobs; ++j)
+    for (int t = 0; t < jobs[j].nk; ++t) blocks += (size_t)std::max(jobs[j].reps, 1) * rt::cdiv(jobs[j].t[t].rk, KB);
+  return blocks * p.kimg_bytes + 256;
+}
+
+int run_apply(int njobs, const JobSpec* jobs, int rc, void* ws, cudaStream_t s) {
+  const Plan p = make_plan(rc);
   Args a{};
   PackArgs pk{};
   a.rc = rc; a.rcp = p.rcp; a.nstages = p.nstages; a.cs_k = p.cs_k; a.kimg_bytes = p.kimg_bytes;
   a.stage_bytes = p.stage_bytes; a.Kimg = (const unsigned char*)ws;
   int tiles = 0, blocks = 0, nj = 0, nterms = 0;
   for (int j = 0; j < njobs; ++j) {
-    const rt_apply_job& in = jobs[j];
-    RT_REQUIRE(rt_apply_tc_supported(rc, in.nk, in.rk), "rt_apply_multi: unsupported shape rc=%d nk=%d", rc, in.nk);
+    const JobSpec& in = jobs[j];
     if (in.n == 0) continue;
+    const int reps = std::max(in.reps, 1);
+    RT_REQUIRE(reps == 1 || in.nk == 1, "run_apply: replicated jobs have one term");
     Job& J = a.job[nj++];
-    J.Y = in.Y; J.ldy = in.ldy; J.X0 = in.X0; J.ldx0 = in.ldx0; J.a0 = in.a0_dev; J.n = in.n; J.nk = in.nk;
-    J.kblk0 = blocks; J.tile0 = tiles; J.ntiles = rt::cdiv(in.n, TM);
+    J.Y = in.Y; J.ldy = in.ldy; J.X0 = in.X0; J.ldx0 = in.ldx0; J.a0 = in.a0; J.n = in.n; J.nk = in.nk;
+    J.reps = reps; J.tiles_per_rep = rt::cdiv(in.n, TM); J.y_rep = in.y_rep;
+    J.kblk0 = blocks; J.tile0 = tiles; J.ntiles = reps * J.tiles_per_rep;
     int b = 0;
     for (int t = 0; t < MAX_TERMS; ++t) {
       const bool on = t < in.nk;
-      J.X[t] = on ? in.X[t] : nullptr; J.ldx[t] = on ? in.ldx[t] : 0; J.rk[t] = on ? in.rk[t] : 0;
-      J.copy[t] = on ? in.copy_out[t] : nullptr; J.ldc[t] = on ? in.ldcopy[t] : 0;
+      const TermSpec& T = in.t[t];
+      J.X[t] = on ? T.X : nullptr; J.ldx[t] = on ? T.ldx : 0; J.rk[t] = on ? T.rk : 0;
+      J.copy[t] = on ? T.copy : nullptr; J.ldc[t] = on ? T.ldc : 0;
+      J.xt[t] = on ? T.xt : 0; J.x_rep[t] = on ? T.x_rep : 0;
       if (on) {
-        RT_REQUIRE(in.copy_out[t] != in.Y || in.copy_out[t] == nullptr, "rt_apply_multi: copy_out may not alias Y");
-        pk.K[nterms] = in.K[t]; pk.rk[nterms] = in.rk[t]; pk.blk0[nterms] = blocks + b; ++nterms;
-        b += rt::cdiv(in.rk[t], KB);
+        RT_REQUIRE(T.copy != in.Y || T.copy == nullptr, "rt_apply_multi: copy_out may not alias Y");
+        const int nb = rt::cdiv(T.rk, KB);
+        pk.K[nterms] = T.K; pk.rk[nterms] = T.rk; pk.blk0[nterms] = blocks + b; pk.f32[nterms] = T.k_f32;
+        pk.rep_blocks[nterms] = reps > 1 ? nb : 0;
+        pk.rows_total[nterms] = T.rows_total > 0 ? T.rows_total : T.rk * reps;
+        ++nterms;
+        b += nb;
       }
       J.blk_end[t] = b;
     }
     J.nblk = b;
-    blocks += b;
+    blocks += b * reps;
     tiles += J.ntiles;
   }
   if (nj == 0) return 0;
@@ -840,6 +939,173 @@ extern "C" int rt_apply_multi(int njobs, const rt_apply_job* jobs, int rc, void*
   }
   RT_LAUNCH_CHECK();
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Score mode: fused 1-N score + BCE + backward at fp32 accuracy on the tensor cores (variant 3).
+//   1. logits Z = O Q^T by the 3xTF32 kernel (rows = entities, 256 queries per job); its epilogue turns them into
+//      the BCE and G = dBCE/dZ for all-negative targets with the reference's fp32 semantics and stores G[e][b];
+//   2. the few positives (CSR targets) are recomputed exactly and patched into G and the loss;
+//   3. dO = G Q        -- the same kernel as a plain factor update (X = G, right factor = the query rows);
+//   4. H  = G^T O      -- the same kernel on transposed operand blocks, the contraction over the entities cut into
+//                          chunks (replicated job) whose partial results are summed in a fixed order.
+// The logit / probability matrices never exist; G (B x N fp32, 84 MB at WN18RR size) is staged between the three
+// launches and stays resident in the 126 MB L2.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void score_fix_positives_kernel(const float* __restrict__ q, const float* __restrict__ O, int B, int r2,
+                                           int n_begin, int n_local, const int32_t* __restrict__ off,
+                                           const int32_t* __restrict__ idx, float t_pos, float t_neg, float inv_count,
+                                           float* __restrict__ G, int64_t ldg, double* __restrict__ delta) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  double dl = 0.0;
+  for (int i = __ldg(off + b) + lane; i < __ldg(off + b + 1); i += 32) {
+    const int fl = __ldg(idx + i) - n_begin;
+    if (fl < 0 || fl >= n_local) continue;
+    const float z = exact_logit(q + (int64_t)b * r2, O + (int64_t)fl * r2, r2);
+    const float p = sigmoid_ref(z);
+    const float lp = fmaxf(logf(p), -100.0f), lq = fmaxf(log1pf(-p), -100.0f);
+    const float pq = (1.0f - p) * p;
+    G[(int64_t)fl * ldg + b] = (p - t_pos) / fmaxf(pq, 1e-12f) * inv_count * pq;
+    dl += -(double)(t_pos - t_neg) * ((double)lp - (double)lq);     // the kernel charged the negative-target term
+  }
+  dl = rt::warp_sum(dl);
+  if (lane == 0) delta[b] = dl;
+}
+
+__global__ void score_finish_kernel(const float* __restrict__ Hpart, int reps, int count, float* __restrict__ H,
+                                    const double* __restrict__ loss_slots, int nslots, const double* __restrict__ delta,
+                                    int B, double* __restrict__ loss_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    float s = 0.0f;
+    for (int r = 0; r < reps; ++r) s += Hpart[(size_t)r * count + i];      // fixed order
+    H[i] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < nslots; ++k) t += loss_slots[k];
+    for (int b = 0; b < B; ++b) t += delta[b];
+    loss_out[0] = t;
+  }
+}
+
+struct ScoreLayout { size_t G, kq, kws, hpart, slots, delta, total; int njobs, Bp, nblk, chunk, reps, grid; };
+ScoreLayout score_layout(int B, int n_local, int r2) {
+  ScoreLayout L;
+  const Plan p256 = make_plan(256);
+  L.njobs = rt::cdiv(B, 256); L.Bp = 256 * L.njobs; L.nblk = rt::cdiv(r2, KB);
+  // H = G^T O: chunks of the entity range so that (query tiles) x (chunks) fills the SMs about once
+  const int qtiles = rt::cdiv(B, TM);
+  int reps = std::max(1, rt::sm_count() / qtiles);
+  int chunk = rt::cdiv(rt::cdiv(n_local, reps), KB) * KB;
+  if (chunk < 256) chunk = 256;
+  L.chunk = chunk; L.reps = rt::cdiv(n_local, chunk);
+  L.grid = std::min(rt::sm_count(), L.njobs * rt::cdiv(n_local, TM));
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t at = o; o += rt::align_up(bytes, 256); return at; };
+  L.G = take(sizeof(float) * (size_t)L.reps * L.chunk * L.Bp);
+  L.kq = take((size_t)L.njobs * L.nblk * p256.kimg_bytes);
+  JobSpec j2{}; j2.n = n_local; j2.nk = 1; j2.t[0].rk = B; j2.reps = 1;
+  JobSpec j3{}; j3.n = B; j3.nk = 1; j3.t[0].rk = L.chunk; j3.reps = L.reps;
+  L.kws = take(std::max(run_apply_ws_bytes(1, &j2, r2), run_apply_ws_bytes(1, &j3, r2)));
+  L.hpart = take(sizeof(float) * (size_t)L.reps * B * r2);
+  L.slots = take(sizeof(double) * (size_t)rt::sm_count() * kEpiWarps);
+  L.delta = take(sizeof(double) * (size_t)B);
+  L.total = o;
+  return L;
+}
+}  // namespace
+
+extern "C" int rt_score_bce_tc3_supported(int B, int n_local, int r2) {
+  return (B >= 1 && B <= 256 * MAX_JOBS && r2 >= 64 && r2 <= RCP_MAX && n_local >= 1024 && make_plan(256).nstages >= 3 &&
+          make_plan(r2).nstages >= 3) ? 1 : 0;
+}
+extern "C" size_t rt_score_bce_tc3_ws_bytes(int B, int n_local, int r2) { return score_layout(B, n_local, r2).total; }
+
+extern "C" int rt_score_bce_tc3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
+                                int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
+                                double* loss_sum, float* H, float* dO, void* ws, void* stream) {
+  RT_REQUIRE(rt_score_bce_tc3_supported(B, n_local, r2), "rt_score_bce_tc3: unsupported shape B=%d n_local=%d r2=%d", B, n_local, r2);
+  RT_REQUIRE(ws != nullptr, "rt_score_bce_tc3: workspace is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  const ScoreLayout L = score_layout(B, n_local, r2);
+  const Plan p = make_plan(256);
+  char* base = (char*)ws;
+  float* G = (float*)(base + L.G);
+  const float t_neg = label_smoothing / (float)n_total, t_pos = (1.0f - label_smoothing) + t_neg;
+  const float inv_count = (float)(1.0 / ((double)b_total * (double)n_total));
+  // rows [n_local, reps * chunk) of G are contraction padding of step 4
+  const size_t pad_rows = (size_t)L.reps * L.chunk - n_local;
+  if (pad_rows) RT_CHECK_CUDA(cudaMemsetAsync(G + (size_t)n_local * L.Bp, 0, pad_rows * L.Bp * sizeof(float), s));
+  // ---- 1. logits -> loss, G ----
+  rank_pack_q_kernel<<<L.njobs * L.nblk, 256, 0, s>>>(q, B, r2, L.nblk, p.rcp, (unsigned char*)(base + L.kq), p.cs_k, p.kimg_bytes);
+  RT_LAUNCH_CHECK();
+  {
+    Args a{};
+    a.rc = 256; a.rcp = p.rcp; a.nstages = p.nstages; a.cs_k = p.cs_k; a.kimg_bytes = p.kimg_bytes;
+    a.stage_bytes = p.stage_bytes; a.Kimg = (const unsigned char*)(base + L.kq);
+    a.njobs = L.njobs;
+    const int tiles_per_job = rt::cdiv(n_local, TM);
+    for (int j = 0; j < L.njobs; ++j) {
+      Job& J = a.job[j];
+      J.n = n_local; J.nk = 1; J.X[0] = O; J.ldx[0] = r2; J.rk[0] = r2;
+      for (int t = 0; t < MAX_TERMS; ++t) J.blk_end[t] = L.nblk;
+      J.nblk = L.nblk; J.kblk0 = j * L.nblk; J.tile0 = j * tiles_per_job; J.ntiles = tiles_per_job;
+      J.reps = 1; J.tiles_per_rep = tiles_per_job;
+    }
+    a.ntiles = L.njobs * tiles_per_job;
+    a.B = B; a.n_begin = n_begin; a.G = G; a.ldg = L.Bp; a.t_neg = t_neg; a.inv_count = inv_count;
+    a.loss_partial = (double*)(base + L.slots);
+    RT_CHECK_CUDA(cudaMemsetAsync(a.loss_partial, 0, sizeof(double) * (size_t)rt::sm_count() * kEpiWarps, s));
+    RT_CHECK_CUDA(rt::ensure_dyn_smem((const void*)apply_tc_kernel<16, 2>, SMEM_LIMIT));
+    apply_tc_kernel<16, 2><<<L.grid, kThreads, p.smem, s>>>(a);
+    RT_LAUNCH_CHECK();
+  }
+  // ---- 2. positives ----
+  score_fix_positives_kernel<<<rt::cdiv(B, 8), 256, 0, s>>>(q, O, B, r2, n_begin, n_local, tgt_off, tgt_idx, t_pos, t_neg,
+                                                            inv_count, G, L.Bp, (double*)(base + L.delta));
+  RT_LAUNCH_CHECK();
+  // ---- 3. dO = G Q ----
+  {
+    JobSpec j{};
+    j.Y = dO; j.ldy = r2; j.n = n_local; j.nk = 1; j.reps = 1;
+    j.t[0].X = G; j.t[0].ldx = L.Bp; j.t[0].rk = B; j.t[0].K = q; j.t[0].k_f32 = 1; j.t[0].rows_total = B;
+    int rc = run_apply(1, &j, r2, base + L.kws, s);
+    if (rc) return rc;
+  }
+  // ---- 4. H = G^T O in entity chunks ----
+  {
+    JobSpec j{};
+    float* Hpart = (float*)(base + L.hpart);
+    j.Y = Hpart; j.ldy = r2; j.n = B; j.nk = 1; j.reps = L.reps; j.y_rep = (int64_t)B * r2;
+    j.t[0].X = G; j.t[0].ldx = L.Bp; j.t[0].xt = 1; j.t[0].rk = L.chunk; j.t[0].x_rep = (int64_t)L.chunk * L.Bp;
+    j.t[0].K = O; j.t[0].k_f32 = 1; j.t[0].rows_total = n_local;
+    int rc = run_apply(1, &j, r2, base + L.kws, s);
+    if (rc) return rc;
+    score_finish_kernel<<<rt::cdiv(B * r2, 256), 256, 0, s>>>(Hpart, L.reps, B * r2, H, (const double*)(base + L.slots),
+                                                              rt::sm_count() * kEpiWarps, (const double*)(base + L.delta), B,
+                                                              loss_sum);
+    RT_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int rt_apply_multi(int njobs, const rt_apply_job* jobs, int rc, void* ws, void* stream) {
+  RT_REQUIRE(njobs >= 1 && njobs <= MAX_JOBS, "rt_apply_multi: 1..%d jobs per launch, got %d", MAX_JOBS, njobs);
+  RT_REQUIRE(ws != nullptr, "rt_apply_multi: workspace is NULL");
+  JobSpec js[MAX_JOBS] = {};
+  for (int j = 0; j < njobs; ++j) {
+    const rt_apply_job& in = jobs[j];
+    RT_REQUIRE(rt_apply_tc_supported(rc, in.nk, in.rk), "rt_apply_multi: unsupported shape rc=%d nk=%d", rc, in.nk);
+    JobSpec& o = js[j];
+    o.Y = in.Y; o.ldy = in.ldy; o.n = in.n; o.X0 = in.X0; o.ldx0 = in.ldx0; o.a0 = in.a0_dev; o.nk = in.nk; o.reps = 1;
+    for (int t = 0; t < in.nk; ++t) {
+      o.t[t].X = in.X[t]; o.t[t].ldx = in.ldx[t]; o.t[t].rk = in.rk[t]; o.t[t].K = in.K[t]; o.t[t].k_f32 = 0;
+      o.t[t].copy = in.copy_out[t]; o.t[t].ldc = in.ldcopy[t]; o.t[t].rows_total = in.rk[t];
+    }
+  }
+  return run_apply(njobs, js, rc, ws, (cudaStream_t)stream);
 }
 
 extern "C" int rt_apply_tc(float* Y, int64_t ldy, int n, int rc, const float* X0, int64_t ldx0, const double* a0_dev,

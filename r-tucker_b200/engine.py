@@ -207,17 +207,25 @@ class StepEngine:
         H = torch.empty(B, r2, dtype=core.dtype, device=self.dev)
         # variant 2 (warp-specialised fp16 tcgen05 kernel) returns dO = G^T q; the right factor A_O is folded into
         # the projection apply below (dO_raw lands in the not-yet-used direction buffer)
-        fold_a = self.score_variant == 2 and getattr(ops, "HAS_SCORE_V3", False) and ops.score_v3_supported(r2)
+        # variant 3 = the same at fp32 accuracy (3xTF32 tensor-core kernels); it falls back to variant 0 on shapes the
+        # tensor-core path does not take (thin ranks, short shards)
+        variant = self.score_variant
+        if variant == 3 and not (getattr(ops, "HAS_SCORE_V3", False) and ops.score_tc3_supported(B, O.shape[0], r2)):
+            variant = 0
+        fold_a = variant == 3 or (variant == 2 and getattr(ops, "HAS_SCORE_V3", False) and ops.score_v3_supported(r2))
         dO_raw = self.dV_new[k_obj] if fold_a else None
         with self._stage("score_bce_fwd_bwd"):
-            if fold_a:
+            if fold_a and variant == 3:
+                ops.score_bce_fwd_bwd(q, None, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
+                                      b_total=B, n_begin=self.n_begin, variant=3, out=(bce_sum, H, dO_raw))
+            elif fold_a:
                 ops.score_bce_fwd_bwd(q, None, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
                                       b_total=B, n_begin=self.n_begin, variant=2, out=(bce_sum, H, dO_raw),
                                       o_absmax=1.0,     # factors of a point on the manifold are orthonormal
                                       centre=self.score_centre)
             else:
                 ops.score_bce_fwd_bwd(q, qp, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
-                                      b_total=B, n_begin=self.n_begin, variant=min(self.score_variant, 1),
+                                      b_total=B, n_begin=self.n_begin, variant=min(variant, 1),
                                       out=(bce_sum, H, dOp))
         self._allreduce(H, bce_sum)
         with self._stage("query_bwd"):

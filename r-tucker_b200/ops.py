@@ -110,6 +110,10 @@ HAS_SCORE_V3 = True   # this ops module implements variant 2 (the CPU stand-in o
 def score_v3_supported(r2):
     return bool(lib().rt_score_bce_v3_supported(int(r2)))
 
+
+def score_tc3_supported(B, n_local, r2):
+    return bool(lib().rt_score_bce_tc3_supported(int(B), int(n_local), int(r2)))
+
 def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None, b_total=None,
                       n_begin=0, variant=0, out=None, ws=None, o_absmax=None, phases=7, centre=None):
     """Returns (loss_sum[1] f64 -- un-normalised, H [B,r2], dO [n_local,r2]).
@@ -118,6 +122,23 @@ def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None,
     ``phases`` (variant 2 only) selects packing (1), fused kernel (2), reduction (4) for timing; ``centre`` (variant 2,
     device float[2], persistent across steps, [1] initialised to 0.5) enables the centred gradient operand."""
     require_cuda(q, qp, O, tgt_off, tgt_idx, centre)
+    if variant == 3:
+        if qp is not None and qp is not q:
+            raise RTuckerError("score_bce_fwd_bwd(variant=3) computes dO = G^T q: pass qp=None")
+        B, r2 = q.shape
+        n_local = O.shape[0]
+        n_total = n_local if n_total is None else n_total
+        b_total = B if b_total is None else b_total
+        dev = q.device
+        if out is None:
+            out = (torch.empty(1, dtype=f64, device=dev), torch.empty(B, r2, dtype=f32, device=dev),
+                   torch.empty(n_local, r2, dtype=f32, device=dev))
+        loss, H, dO = out
+        ws = ws if ws is not None else _ws(lib().rt_score_bce_tc3_ws_bytes(B, n_local, r2), dev)
+        check(lib().rt_score_bce_tc3(ptr(_c(q, f32)), ptr(_c(O, f32)), B, r2, n_begin, n_local, n_total, b_total,
+                                     ptr(_c(tgt_off, i32)), ptr(_c(tgt_idx, i32)), float(label_smoothing), ptr(loss),
+                                     ptr(H), ptr(dO), ptr(ws), stream_ptr()), "rt_score_bce_tc3")
+        return loss, H, dO
     if variant == 2:
         if qp is not None and qp is not q:
             raise RTuckerError("score_bce_fwd_bwd(variant=2) computes dO = G^T q: pass qp=None")

@@ -608,3 +608,66 @@ def test_score_bce_v3_keeps_the_signal_at_initialisation(cuda_device):
     assert relerr(dev_H, dev_H_ref) < 5e-3, relerr(dev_H, dev_H_ref)
     assert relerr(dev_dO, dev_dO_ref) < 5e-3, relerr(dev_dO, dev_dO_ref)
     assert abs(float(centre[1].cpu()) - float((p - t).mean())) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# variant 3: the fused score + BCE + backward at fp32 accuracy on the tensor cores (csrc/apply_tc.cu, score mode):
+# the SAME 1e-5 bounds as the fp32 FFMA kernel (variant 0)
+@pytest.mark.parametrize("B,N,r2,ls,scale", [
+    (512, 40943, 200, 0.1, 3.0), (100, 1777, 200, 0.1, 1.0), (512, 4099, 100, 0.0, 1.0),
+    (300, 2500, 64, 0.1, 40.0),     # saturating logits: log clamp at -100 and zero gradient
+    (512, 14541, 72, 0.1, 8.0), (700, 3001, 130, 0.1, 2.0),
+])
+def test_score_bce_tc3(cuda_device, B, N, r2, ls, scale):
+    import analytic as A
+    from rtucker_b200 import ops
+    dev = cuda_device
+    assert ops.score_tc3_supported(B, N, r2)
+    g = torch.Generator().manual_seed(B + N + r2)
+    q = scale * torch.randn(B, r2, generator=g) / r2 ** 0.5
+    O = torch.randn(N, r2, generator=g)
+    off, idx = make_csr(B, N, g, max_per_row=6, dense_row=1)
+    z = (q.double() @ O.double().T).float()
+    t = A.dense_targets(B, N, off.long(), idx, ls, torch.float32)
+    _, loss_el, gsum = A.bce_sigmoid_terms(z, t)
+    loss_ref = loss_el.double().sum()
+    G = gsum.double() / (B * N)
+    H_ref, dO_ref = G @ O.double(), G.T @ q.double()
+    loss, H, dO = ops.score_bce_fwd_bwd(q.to(dev), None, O.to(dev), off.to(dev), idx.to(dev), ls, variant=3)
+    # saturating case: an element whose logit sits within 1e-6 of the p == 1 point may land on the other side of the
+    # clamp (100 instead of 16.6): a few such elements in 750 k
+    assert abs(float(loss.cpu()) - float(loss_ref)) / abs(float(loss_ref)) < (1e-4 if scale >= 40 else REL)
+    assert relerr(H, H_ref) < REL, relerr(H, H_ref)
+    assert relerr(dO, dO_ref) < REL, relerr(dO, dO_ref)
+    loss2, H2, dO2 = ops.score_bce_fwd_bwd(q.to(dev), None, O.to(dev), off.to(dev), idx.to(dev), ls, variant=3)
+    assert torch.equal(H, H2) and torch.equal(dO, dO2) and torch.equal(loss, loss2)      # deterministic
+
+
+def test_score_bce_tc3_at_initialisation_and_sharded(cuda_device):
+    """The regime that broke the 11-bit kernels (all p = 0.5 +- 1e-4): the informative part of H and dO, after removing
+    the rank-one bulk, to 1e-4; and an entity shard with n_begin != 0 against the whole."""
+    from rtucker_b200 import ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    B, N, r2, ls = 512, 12000, 200, 0.1
+    O = torch.linalg.qr(torch.randn(N, r2, generator=g, dtype=torch.float64))[0].float().contiguous()
+    q = (0.02 * torch.randn(B, r2, generator=g)).contiguous()
+    off = torch.arange(0, 2 * B + 1, 2, dtype=torch.int32)
+    idx = torch.randint(0, N, (2 * B,), generator=g).int()
+    z = q.double() @ O.double().T
+    p = torch.sigmoid(z)
+    t = torch.full((B, N), ls / N, dtype=torch.float64)
+    for b in range(B):
+        t[b, idx[off[b]:off[b + 1]].long()] = 1 - ls + ls / N
+    G = (p - t) / (B * N)
+    H_ref, dO_ref = G @ O.double(), G.T @ q.double()
+    _, H, dO = ops.score_bce_fwd_bwd(q.to(dev), None, O.to(dev), off.to(dev), idx.to(dev), ls, variant=3)
+    H, dO = H.double().cpu(), dO.double().cpu()
+    assert relerr(H - H.mean(0), H_ref - H_ref.mean(0)) < 1e-4
+    assert relerr(dO - dO.mean(0), dO_ref - dO_ref.mean(0)) < 1e-4
+    lo, hi = 3000, 9100
+    l_s, H_s, dO_s = ops.score_bce_fwd_bwd(q.to(dev), None, O[lo:hi].contiguous().to(dev), off.to(dev), idx.to(dev), ls,
+                                           n_total=N, b_total=B, n_begin=lo, variant=3)
+    G_s = G[:, lo:hi]
+    assert relerr(H_s, G_s @ O[lo:hi].double()) < REL
+    assert relerr(dO_s, G_s.T @ q.double()) < REL
