@@ -144,13 +144,13 @@ int rt_score_bce_v3(const float* q, const float* O, int B, int r2, int n_begin, 
 
 /* Variant 3: the same operation at fp32 accuracy on the tensor cores (apply_tc.cu, score mode): logits by 3xTF32 with
  * round-to-nearest partial sums, loss and gradient with the fp32 semantics of variant 0, the two backward contractions
- * by the 3xTF32 factor-update kernel.  Returns dO = G^T q like variant 2.  The gradient matrix G (B x n_local fp32) is
+ * by the 3xTF32 factor-update kernel.  Like variant 0: dO = G^T qp (qp = q when NULL).  The gradient matrix G (B x n_local fp32) is
  * staged in the workspace between the launches (it fits the 126 MB L2 at WN18RR size); the logit / probability /
  * target matrices never exist. */
 int rt_score_bce_tc3_supported(int B, int n_local, int r2);
 size_t rt_score_bce_tc3_ws_bytes(int B, int n_local, int r2);
-int rt_score_bce_tc3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
-                     int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
+int rt_score_bce_tc3(const float* q, const float* qp, const float* O, int B, int r2, int n_begin, int n_local,
+                     int n_total, int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
                      double* loss_sum, float* H, float* dO, void* ws, void* stream);
 
 /* ---- (c) tall-skinny passes over the N x r factors ----------------------------------- */

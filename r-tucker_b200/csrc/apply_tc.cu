@@ -33,7 +33,10 @@ constexpr int kThreads = 512;       // 16 warps = 4 warpgroups: epilogue (2), pr
 constexpr int kRegsEpi = 168, kRegsOther = 88;                  // setmaxnreg: 256 * 168 + 256 * 88 = 64 K registers
 constexpr int TM = 128;             // rows per tile
 constexpr int KB = 16;              // contraction elements per staged block (2 MMA k-steps)
-constexpr int GB = 2;               // blocks per partial sum held in tensor memory
+constexpr int GB = 2;               // blocks per partial sum held in tensor memory (factor updates)
+constexpr int GB_LOGITS = 7;        // rank / score mode: a 200-wide contraction is two partial sums, so that a whole tile can
+                                    // sit in the two accumulators while the (long) epilogue of the previous tile runs; the
+                                    // truncation bias of 112-element partial sums is ~6e-7, inside the logit margins
 constexpr int PF = 3;               // X blocks in flight per producer thread (registers)
 constexpr int XPT = TM * (KB / 4) / (kProdWarps * 32);          // float4 per producer thread and block
 constexpr int MAX_STAGES = 6;
@@ -60,7 +63,7 @@ struct Job {
 };
 struct Args {
   Job job[MAX_JOBS];
-  int njobs, ntiles, rc, rcp, nstages;
+  int njobs, ntiles, rc, rcp, nstages, gb;
   const unsigned char* Kimg;          // [total blocks][hi | lo][KB/4 chunks][cs_k bytes]
   uint32_t cs_k, kimg_bytes, stage_bytes;
   int debug;                          // profiling build only (RT_APPLY_DEBUG): 1 no X loads, 2 no K loads, 4 no MMAs, 8 ld.cg
@@ -165,6 +168,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // HC8 = 8-column groups of the accumulator owned by one epilogue warp (rcp / 16): 13 for r = 200, 16 = any rcp <= 256
 template <int HC8, int MODE = 0>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -207,7 +214,7 @@ apply_tc_kernel(const __grid_constant__ Args a) {
       int job = 0;
       while (job + 1 < a.njobs && tile >= a.job[job + 1].tile0) ++job;
       const Job& J = a.job[job];
-      const int ngroups = (J.nblk + GB - 1) / GB;
+      const int ngroups = (J.nblk + a.gb - 1) / a.gb;
       for (int grp = 0; grp < ngroups; ++grp, ++g) {
         const int ab = g & 1;
         PROF_BEGIN;
@@ -314,17 +321,19 @@ apply_tc_kernel(const __grid_constant__ Args a) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float z = acc[c4 + u];
-            const float en = __expf(-fabsf(z));
-            const float l1p = en < 1e-3f ? en * (1.0f - 0.5f * en) : __logf(1.0f + en);     // log(1 + e^-|z|)
-            const float r = __frcp_rn(1.0f + en);
-            float p, lp, lq;
-            if (z >= 0.0f) {                         // p in [0.5, 1]: 1 - p is exact, p == 1 from z = 24 ln 2 on
-              p = r; lp = -l1p;
-              lq = (z >= 16.635532f) ? -100.0f : __logf(1.0f - p);
-            } else {
-              p = en * r; lq = -l1p;
-              lp = fmaxf(z - l1p, -100.0f);
+            // three special-function operations per element (ex2, lg2, rcp): the epilogue is bound by them
+            const float en = ex2_fast(-1.4426950408889634f * fabsf(z));                      // e^-|z|
+            const float sden = 1.0f + en;
+            float p, lq;
+            if (z >= 0.0f) {          // p in [0.5, 1]: the fp32 quotient (1 - p is then exact; p == 1 from z = 24 ln 2 on)
+              p = __frcp_rn(sden);
+              lq = (z >= 16.635532f) ? -100.0f : 0.6931471805599453f * lg2_fast(1.0f - p);
+            } else {                  // log(1 - p) = -log(1 + e^z)
+              p = en * rcp_fast(sden);
+              lq = -(en < 1e-3f ? en * (1.0f - 0.5f * en) : 0.6931471805599453f * lg2_fast(sden));
             }
+            // log p = log(1 - p) + z (exact identity; its term carries the weight t_neg = ls / N ~ 1e-6 of the loss)
+            const float lp = fmaxf(lq + z, -100.0f);
             const float pq = (1.0f - p) * p;
             float g = (p - tn) * inv;
             if (pq < 1e-12f) g *= pq * 1e12f;
@@ -547,8 +556,8 @@ apply_tc_kernel(const __grid_constant__ Args a) {
       PROF_DECL;
       int s = 0; uint32_t phase = 0;
       for (; c.valid(a); c.next(a)) {
-        const bool group_start = (c.blk % GB) == 0;
-        const bool group_end = c.blk == c.nblk - 1 || ((c.blk + 1) % GB) == 0;
+        const bool group_start = (c.blk % a.gb) == 0;
+        const bool group_end = c.blk == c.nblk - 1 || ((c.blk + 1) % a.gb) == 0;
         const int ab = g & 1;
         PROF_BEGIN;
         if (group_start && g >= 2) mbar_wait(&bar_acc_empty[ab], (uint32_t)((g >> 1) - 1) & 1u);
@@ -809,7 +818,7 @@ int rank_tc(const float* q, const float* O, int B, int r2, int n_begin, int n_lo
                                                        p.kimg_bytes);
   RT_LAUNCH_CHECK();
   Args a{};
-  a.rc = 256; a.rcp = p.rcp; a.nstages = p.nstages; a.cs_k = p.cs_k; a.kimg_bytes = p.kimg_bytes;
+  a.rc = 256; a.rcp = p.rcp; a.nstages = p.nstages; a.cs_k = p.cs_k; a.kimg_bytes = p.kimg_bytes; a.gb = GB_LOGITS;
   a.stage_bytes = p.stage_bytes; a.Kimg = (const unsigned char*)(base + L.kimg);
   a.njobs = L.njobs;
   const int tiles_per_job = rt::cdiv(n_local, TM);
@@ -886,7 +895,7 @@ int run_apply(int njobs, const JobSpec* jobs, int rc, void* ws, cudaStream_t s) 
   const Plan p = make_plan(rc);
   Args a{};
   PackArgs pk{};
-  a.rc = rc; a.rcp = p.rcp; a.nstages = p.nstages; a.cs_k = p.cs_k; a.kimg_bytes = p.kimg_bytes;
+  a.rc = rc; a.rcp = p.rcp; a.nstages = p.nstages; a.cs_k = p.cs_k; a.kimg_bytes = p.kimg_bytes; a.gb = GB;
   a.stage_bytes = p.stage_bytes; a.Kimg = (const unsigned char*)ws;
   int tiles = 0, blocks = 0, nj = 0, nterms = 0;
   for (int j = 0; j < njobs; ++j) {
@@ -982,11 +991,12 @@ __global__ void score_finish_kernel(const float* __restrict__ Hpart, int reps, i
     for (int r = 0; r < reps; ++r) s += Hpart[(size_t)r * count + i];      // fixed order
     H[i] = s;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x < 32) {       // lane-strided partial sums + butterfly: the same association every run
     double t = 0.0;
-    for (int k = 0; k < nslots; ++k) t += loss_slots[k];
-    for (int b = 0; b < B; ++b) t += delta[b];
-    loss_out[0] = t;
+    for (int k = threadIdx.x; k < nslots; k += 32) t += loss_slots[k];
+    for (int b = threadIdx.x; b < B; b += 32) t += delta[b];
+    t = rt::warp_sum(t);
+    if (threadIdx.x == 0) loss_out[0] = t;
   }
 }
 
@@ -1023,9 +1033,9 @@ extern "C" int rt_score_bce_tc3_supported(int B, int n_local, int r2) {
 }
 extern "C" size_t rt_score_bce_tc3_ws_bytes(int B, int n_local, int r2) { return score_layout(B, n_local, r2).total; }
 
-extern "C" int rt_score_bce_tc3(const float* q, const float* O, int B, int r2, int n_begin, int n_local, int n_total,
-                                int b_total, const int32_t* tgt_off, const int32_t* tgt_idx, float label_smoothing,
-                                double* loss_sum, float* H, float* dO, void* ws, void* stream) {
+extern "C" int rt_score_bce_tc3(const float* q, const float* qp, const float* O, int B, int r2, int n_begin, int n_local,
+                                int n_total, int b_total, const int32_t* tgt_off, const int32_t* tgt_idx,
+                                float label_smoothing, double* loss_sum, float* H, float* dO, void* ws, void* stream) {
   RT_REQUIRE(rt_score_bce_tc3_supported(B, n_local, r2), "rt_score_bce_tc3: unsupported shape B=%d n_local=%d r2=%d", B, n_local, r2);
   RT_REQUIRE(ws != nullptr, "rt_score_bce_tc3: workspace is NULL");
   cudaStream_t s = (cudaStream_t)stream;
@@ -1043,7 +1053,7 @@ extern "C" int rt_score_bce_tc3(const float* q, const float* O, int B, int r2, i
   RT_LAUNCH_CHECK();
   {
     Args a{};
-    a.rc = 256; a.rcp = p.rcp; a.nstages = p.nstages; a.cs_k = p.cs_k; a.kimg_bytes = p.kimg_bytes;
+    a.rc = 256; a.rcp = p.rcp; a.nstages = p.nstages; a.cs_k = p.cs_k; a.kimg_bytes = p.kimg_bytes; a.gb = GB_LOGITS;
     a.stage_bytes = p.stage_bytes; a.Kimg = (const unsigned char*)(base + L.kq);
     a.njobs = L.njobs;
     const int tiles_per_job = rt::cdiv(n_local, TM);
@@ -1066,11 +1076,11 @@ extern "C" int rt_score_bce_tc3(const float* q, const float* O, int B, int r2, i
   score_fix_positives_kernel<<<rt::cdiv(B, 8), 256, 0, s>>>(q, O, B, r2, n_begin, n_local, tgt_off, tgt_idx, t_pos, t_neg,
                                                             inv_count, G, L.Bp, (double*)(base + L.delta));
   RT_LAUNCH_CHECK();
-  // ---- 3. dO = G Q ----
+  // ---- 3. dO = G Q'  (Q' = qp = q A_O when the caller folds the right factor of the projection in, else q) ----
   {
     JobSpec j{};
     j.Y = dO; j.ldy = r2; j.n = n_local; j.nk = 1; j.reps = 1;
-    j.t[0].X = G; j.t[0].ldx = L.Bp; j.t[0].rk = B; j.t[0].K = q; j.t[0].k_f32 = 1; j.t[0].rows_total = B;
+    j.t[0].X = G; j.t[0].ldx = L.Bp; j.t[0].rk = B; j.t[0].K = qp ? qp : q; j.t[0].k_f32 = 1; j.t[0].rows_total = B;
     int rc = run_apply(1, &j, r2, base + L.kws, s);
     if (rc) return rc;
   }

@@ -212,20 +212,20 @@ class StepEngine:
         variant = self.score_variant
         if variant == 3 and not (getattr(ops, "HAS_SCORE_V3", False) and ops.score_tc3_supported(B, O.shape[0], r2)):
             variant = 0
-        fold_a = variant == 3 or (variant == 2 and getattr(ops, "HAS_SCORE_V3", False) and ops.score_v3_supported(r2))
+        # variant 2 returns dO = G^T q and leaves the right factor A_O to the projection apply ("fold"): measured on real
+        # WN18RR this is what keeps it from learning -- rounding G^T q to fp32 BEFORE the ill-conditioned A_O loses the
+        # components along the weak directions of the core; variants 0 and 3 contract with qp = q A_O directly
+        fold_a = variant == 2 and getattr(ops, "HAS_SCORE_V3", False) and ops.score_v3_supported(r2)
         dO_raw = self.dV_new[k_obj] if fold_a else None
         with self._stage("score_bce_fwd_bwd"):
-            if fold_a and variant == 3:
-                ops.score_bce_fwd_bwd(q, None, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
-                                      b_total=B, n_begin=self.n_begin, variant=3, out=(bce_sum, H, dO_raw))
-            elif fold_a:
+            if fold_a:
                 ops.score_bce_fwd_bwd(q, None, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
                                       b_total=B, n_begin=self.n_begin, variant=2, out=(bce_sum, H, dO_raw),
                                       o_absmax=1.0,     # factors of a point on the manifold are orthonormal
                                       centre=self.score_centre)
             else:
                 ops.score_bce_fwd_bwd(q, qp, O, targets.off, targets.idx, label_smoothing, n_total=self.n_total,
-                                      b_total=B, n_begin=self.n_begin, variant=min(variant, 1),
+                                      b_total=B, n_begin=self.n_begin, variant=variant if variant == 3 else min(variant, 1),
                                       out=(bce_sum, H, dOp))
         self._allreduce(H, bce_sum)
         with self._stage("query_bwd"):

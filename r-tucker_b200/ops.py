@@ -123,8 +123,6 @@ def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None,
     device float[2], persistent across steps, [1] initialised to 0.5) enables the centred gradient operand."""
     require_cuda(q, qp, O, tgt_off, tgt_idx, centre)
     if variant == 3:
-        if qp is not None and qp is not q:
-            raise RTuckerError("score_bce_fwd_bwd(variant=3) computes dO = G^T q: pass qp=None")
         B, r2 = q.shape
         n_local = O.shape[0]
         n_total = n_local if n_total is None else n_total
@@ -135,7 +133,7 @@ def score_bce_fwd_bwd(q, qp, O, tgt_off, tgt_idx, label_smoothing, n_total=None,
                    torch.empty(n_local, r2, dtype=f32, device=dev))
         loss, H, dO = out
         ws = ws if ws is not None else _ws(lib().rt_score_bce_tc3_ws_bytes(B, n_local, r2), dev)
-        check(lib().rt_score_bce_tc3(ptr(_c(q, f32)), ptr(_c(O, f32)), B, r2, n_begin, n_local, n_total, b_total,
+        check(lib().rt_score_bce_tc3(ptr(_c(q, f32)), ptr(qp), ptr(_c(O, f32)), B, r2, n_begin, n_local, n_total, b_total,
                                      ptr(_c(tgt_off, i32)), ptr(_c(tgt_idx, i32)), float(label_smoothing), ptr(loss),
                                      ptr(H), ptr(dO), ptr(ws), stream_ptr()), "rt_score_bce_tc3")
         return loss, H, dO
