@@ -31,6 +31,7 @@ using namespace rt::tc;
 constexpr int kEpiWarps = 8, kProdWarps = 4, kMmaWarp = 12, kLoadWarp = 13;
 constexpr int kThreads = 512;       // 16 warps = 4 warpgroups: epilogue (2), producers (1), MMA + loader + 2 idle (1)
 constexpr int kRegsEpi = 168, kRegsOther = 88;                  // setmaxnreg: 256 * 168 + 256 * 88 = 64 K registers
+constexpr int kRegsEpiLogits = 176, kRegsOtherLogits = 80;      // rank / score mode: 128 logits + counters per thread
 constexpr int TM = 128;             // rows per tile
 constexpr int KB = 16;              // contraction elements per staged block (2 MMA k-steps)
 constexpr int GB = 2;               // blocks per partial sum held in tensor memory (factor updates)
@@ -196,19 +197,33 @@ apply_tc_kernel(const __grid_constant__ Args a) {
 
   if (warp < kEpiWarps) {
     // ================= epilogue: partial sums -> fp32 running sum (round to nearest) -> Y =================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" :: "n"(kRegsEpi));
+    if (MODE == 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" :: "n"(kRegsEpi));
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" :: "n"(kRegsEpiLogits));
     const int quarter = warp & 3, half = warp >> 2;
     constexpr int NACC = HC8 * 8;
     float acc[NACC];
 #pragma unroll
     for (int j = 0; j < NACC; ++j) acc[j] = 0.0f;
     PROF_DECL;
-    int cnt[MAX_JOBS][4];                            // rank mode: "greater" counts of columns lane, lane + 32, ... per job
+    // rank mode: "greater" counts of this thread's row(s), one 4-bit counter per column (16 columns per word)
+    uint32_t cntw[HC8];
+    int cnt_job = -1, cnt_tiles = 0;
     double lacc = 0.0;
 #pragma unroll
-    for (int jj = 0; jj < MAX_JOBS; ++jj)
+    for (int u = 0; u < HC8; ++u) cntw[u] = 0u;
+    // sum the counters over the lanes and add them to greater[] (job = query block the counters belong to)
+    auto flush_counts = [&](int job_of) {
+      if (MODE != 1 || job_of < 0) return;
+      const int q0 = job_of * 256 + (warp >> 2) * halfcols;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) cnt[jj][u] = 0;
+      for (int c = 0; c < HC8 * 8; ++c) {
+        const int v = (int)((cntw[c >> 3] >> ((c & 7) * 4)) & 15u);
+        const int tot = __reduce_add_sync(0xffffffffu, v);
+        if (lane == (c & 31) && tot && c < halfcols && q0 + c < a.B) atomicAdd(a.greater + q0 + c, tot);
+      }
+#pragma unroll
+      for (int u = 0; u < HC8; ++u) cntw[u] = 0u;
+    };
     int g = 0;                                       // finished partial sums so far (accumulator = g & 1)
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       int job = 0;
@@ -252,6 +267,8 @@ apply_tc_kernel(const __grid_constant__ Args a) {
       PROF_BEGIN;
       if (MODE == 1) {
         // ---- filtered-ranking epilogue: acc[c] = logit of (entity row, query column) ----
+        if (job != cnt_job || cnt_tiles == 15) { flush_counts(cnt_job); cnt_job = job; cnt_tiles = 0; }
+        ++cnt_tiles;
         const int e_loc = (tile - J.tile0) * TM + quarter * 32 + lane;       // entity (row) of this thread (reps == 1)
         const bool rv = e_loc < J.n;
         const int e_glob = a.n_begin + e_loc;
@@ -261,47 +278,58 @@ apply_tc_kernel(const __grid_constant__ Args a) {
         const float* hi_p = a.thr + Bp + q0;
         const float* eq_p = a.thr + 2 * Bp + q0;
         float lsum = 0.0f;
+        // does any query of these columns have a saturated target (p_t == 1)?  (eqlo finite: rare, warp-uniform)
+        bool any_eq = false;
 #pragma unroll
-        for (int c = 0; c < NACC; ++c) {
-          const int b = q0 + c;
-          const float z = acc[c];
-          const float lo = __ldg(lo_p + c), hi = __ldg(hi_p + c), eqlo = __ldg(eq_p + c);   // uniform over the warp
-          const bool on = rv && b < a.B;
-          const unsigned gm = __ballot_sync(0xffffffffu, on && z > hi);
-          const bool eqd = on && z > eqlo;                                   // certainly p == 1 == p_target
-          const bool cd = on && !eqd && z >= lo && z <= hi;
-          const unsigned em = __ballot_sync(0xffffffffu, eqd);
-          const unsigned cm = __ballot_sync(0xffffffffu, cd);
-          if (lane == (c & 31)) {
+        for (int c4 = 0; c4 < NACC; c4 += 4) {
+          const float4 e4 = __ldg(reinterpret_cast<const float4*>(eq_p + c4));
+          any_eq |= (e4.x < INFINITY) | (e4.y < INFINITY) | (e4.z < INFINITY) | (e4.w < INFINITY);
+        }
 #pragma unroll
-            for (int jj = 0; jj < MAX_JOBS; ++jj)
-              if (jj == job) cnt[jj][c >> 5] += __popc(gm);
-          }
-          if (em) {
-            const int t = __ldg(a.target + b);
-            const unsigned em2 = __ballot_sync(0xffffffffu, eqd && e_glob != t);
-            const unsigned bm = __ballot_sync(0xffffffffu, eqd && e_glob < t);
-            if (lane == 0) {
-              if (em2) atomicAdd(a.equal + b, __popc(em2));
-              if (bm) atomicAdd(a.equal_before + b, __popc(bm));
+        for (int c4 = 0; c4 < NACC; c4 += 4) {
+          const float4 lo4 = __ldg(reinterpret_cast<const float4*>(lo_p + c4));       // uniform over the warp
+          const float4 hi4 = __ldg(reinterpret_cast<const float4*>(hi_p + c4));
+          const float los[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, his[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int c = c4 + u;
+            const int b = q0 + c;
+            const float z = acc[c];
+            const bool on = rv && b < a.B;
+            bool eqd = false;
+            if (any_eq) {                                                      // certainly p == 1 == p_target
+              eqd = on && z > __ldg(eq_p + c);
+              const unsigned em = __ballot_sync(0xffffffffu, eqd);
+              if (em) {
+                const int t = __ldg(a.target + b);
+                const unsigned em2 = __ballot_sync(0xffffffffu, eqd && e_glob != t);
+                const unsigned bm = __ballot_sync(0xffffffffu, eqd && e_glob < t);
+                if (lane == 0) {
+                  if (em2) atomicAdd(a.equal + b, __popc(em2));
+                  if (bm) atomicAdd(a.equal_before + b, __popc(bm));
+                }
+              }
             }
-          }
-          if (cm) {
-            if (cd) {
+            // "greater" as a 4-bit counter per column in this thread's registers: no warp collective in the hot loop;
+            // the cross-lane sums happen once per job (or every 15 tiles), see flush_counts
+            const bool gt = on && z > his[u];
+            const bool cd = on && !eqd && z >= los[u] && z <= his[u];
+            cntw[c >> 3] += (gt ? 1u : 0u) << ((c & 7) * 4);
+            if (cd) {                                                          // rare: recomputed exactly afterwards
               const int pos = atomicAdd(a.cand_count, 1);
               if (pos < a.cand_cap) a.cand[pos] = make_int2(e_loc, b);
             }
-          }
-          if (on) {
-            // -log(1 - p) with the reference's fp32 semantics: p = 1 / (1 + expf(-z)) is exactly 1 as soon as
-            // expf(-z) <= 2^-24, i.e. z >= 24 ln 2, and BCELoss clamps log(1 - p) = -inf at -100; below that it is
-            // softplus(z)
-            // softplus(z); for z >= 0 through the fp32 probability itself -- 1 - p is quantised to multiples of 2^-24
-            // there and log(1 - p) inherits it (up to 0.35 per element near saturation: 2e-4 of the batch's BCE)
-            const float en = __expf(-fabsf(z));
-            const float p32 = __frcp_rn(1.0f + en);
-            const float sp = z >= 0.0f ? -__logf(1.0f - p32) : __logf(1.0f + en);
-            lsum += (z >= 16.635532f) ? 100.0f : sp;
+            if (on) {
+              // -log(1 - p) with the reference's fp32 semantics: for z >= 0 through the fp32 probability itself (1 - p
+              // is quantised to multiples of 2^-24 there: up to 0.35 per element near saturation, 2e-4 of a batch's
+              // BCE), p == 1 from z = 24 ln 2 on (BCELoss clamps log(1 - p) at -100); for z < 0 log(1 + e^z)
+              const float en = ex2_fast(-1.4426950408889634f * fabsf(z));
+              const float sden = 1.0f + en;
+              float sp;
+              if (z >= 0.0f) sp = (z >= 16.635532f) ? 100.0f : -0.6931471805599453f * lg2_fast(1.0f - __frcp_rn(sden));
+              else sp = en < 1e-3f ? en * (1.0f - 0.5f * en) : 0.6931471805599453f * lg2_fast(sden);
+              lsum += sp;
+            }
           }
         }
         lacc += (double)lsum;
@@ -377,13 +405,7 @@ apply_tc_kernel(const __grid_constant__ Args a) {
       PROF_END(pw1);
     }
     if (MODE == 1) {
-#pragma unroll
-      for (int jj = 0; jj < MAX_JOBS; ++jj)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int b = jj * 256 + half * halfcols + u * 32 + lane;
-          if (jj < a.njobs && u * 32 < halfcols && b < a.B && cnt[jj][u]) atomicAdd(a.greater + b, cnt[jj][u]);
-        }
+      flush_counts(cnt_job);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lacc += __shfl_xor_sync(0xffffffffu, lacc, o);
       if (lane == 0 && lacc != 0.0) atomicAdd(a.loss_sum, lacc);
@@ -396,7 +418,8 @@ apply_tc_kernel(const __grid_constant__ Args a) {
     if (tid == 0) { PROF_PRINT("epilogue (acc_full, store)"); }
   } else if (warp < kEpiWarps + kProdWarps) {
     // ================= producers: X block -> hi / lo operand images (+ optional raw copy) =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
+    if (MODE == 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOtherLogits));
     const int ptid = tid - kEpiWarps * 32;             // 0 .. kProdWarps*32-1
     // thread -> (16-byte chunk ch of the block's 4, rows r0, r0 + rstep, ...).  Row-major terms: 4 lanes cover the 64
     // contiguous bytes of a row; transposed terms (element (row, k) at X + k * ld + row): a warp per chunk, lanes along
@@ -547,7 +570,8 @@ apply_tc_kernel(const __grid_constant__ Args a) {
     if (ptid == 0) { PROF_PRINT("producer (empty, produce)"); }
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
+    if (MODE == 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOtherLogits));
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32(TM, a.rcp, false, false);
       Cursor c;
@@ -587,7 +611,8 @@ apply_tc_kernel(const __grid_constant__ Args a) {
     __syncwarp();
   } else if (warp == kLoadWarp) {
     // ================= K image loader =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
+    if (MODE == 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOtherLogits));
     if (lane == 0) {
       Cursor c;
       c.init(a);
@@ -609,7 +634,8 @@ apply_tc_kernel(const __grid_constant__ Args a) {
     }
     __syncwarp();
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));     // idle warps of the last warpgroup
+    if (MODE == 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOther));
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kRegsOtherLogits));     // idle warps of the last warpgroup
   }
   fence_before_sync();
   __syncthreads();
@@ -830,6 +856,9 @@ int rank_tc(const float* q, const float* O, int B, int r2, int n_begin, int n_lo
     J.reps = 1; J.tiles_per_rep = tiles_per_job;
   }
   a.ntiles = L.njobs * tiles_per_job;
+#ifdef RT_APPLY_PROF
+  a.debug = getenv("RT_APPLY_DEBUG") ? atoi(getenv("RT_APPLY_DEBUG")) : 0;
+#endif
   a.thr = thr; a.target = target; a.B = B; a.n_begin = n_begin;
   a.greater = greater; a.equal = equal; a.equal_before = equal_before;
   a.cand = (int2*)(base + L.cand); a.cand_count = scal; a.cand_cap = L.cap; a.loss_sum = loss;
