@@ -100,13 +100,17 @@ __global__ void reduce_splits_kernel(const float* __restrict__ partial, int nspl
 }
 
 // ---- backward (1): d_core[k=(a,i), j] = sum_b r[b,a] s[b,i] H[b,j] ----------------------------
+// grid.z splits the batch (few k x j tiles at small ranks: 128 CTAs walked all 512 rows, 98 us); the partial sums are
+// added in split order by reduce_splits_kernel
 __global__ void __launch_bounds__(256)
 query_bwd_core_kernel(const float* __restrict__ r_rows, const float* __restrict__ s_rows,
-                      const float* __restrict__ H, int B, int r0, int r1, int r2,
+                      const float* __restrict__ H, int B, int r0, int r1, int r2, int b_per_split,
                       float* __restrict__ d_core) {
   __shared__ Smem As, Bs;
   const int k0 = blockIdx.x * T, j0 = blockIdx.y * T;
   const int K = r0 * r1;
+  const int bbeg = blockIdx.z * b_per_split, bend = min(B, bbeg + b_per_split);
+  d_core += (int64_t)blockIdx.z * K * r2;
   float acc[4][4];
   zero_acc(acc);
   auto la = [&](int rr, int b) -> float {  // A[row=k, kdim=b]
@@ -119,7 +123,7 @@ query_bwd_core_kernel(const float* __restrict__ r_rows, const float* __restrict_
     const int j = j0 + cc;
     return (j < r2) ? __ldg(H + (int64_t)b * r2 + j) : 0.0f;
   };
-  tile_mainloop<false, true>(0, B, la, lb, acc, As, Bs);
+  tile_mainloop<false, true>(bbeg, bend, la, lb, acc, As, Bs);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -198,6 +202,7 @@ struct QueryPlan {
   int ksplit, k_per_split;  // forward split-K
   int asplit, a_per_split;  // backward split over the relation rank
   int itiles;
+  int bsplit, b_per_split;  // core-gradient split over the batch
 };
 
 QueryPlan query_plan(int B, int r0, int r1, int r2) {
@@ -217,6 +222,12 @@ QueryPlan query_plan(int B, int r0, int r1, int r2) {
   if (as < 1) as = 1;
   p.a_per_split = rt::cdiv(r0, as);
   p.asplit = rt::cdiv(r0, p.a_per_split);
+  const int tiles3 = rt::cdiv(K, T) * rt::cdiv(r2, T);
+  int bs = rt::cdiv(2 * 148, tiles3);
+  if (bs > rt::cdiv(B, 4 * KC)) bs = rt::cdiv(B, 4 * KC);
+  if (bs < 1) bs = 1;
+  p.b_per_split = rt::cdiv(rt::cdiv(B, bs), KC) * KC;
+  p.bsplit = rt::cdiv(B, p.b_per_split);
   return p;
 }
 
@@ -226,7 +237,7 @@ extern "C" size_t rt_query_ws_bytes(int B, int r0, int r1, int r2) {
   if (B <= 0) return 16;
   QueryPlan p = query_plan(B, r0, r1, r2);
   size_t fwd = (size_t)p.ksplit * B * r2;
-  size_t bwd = (size_t)p.asplit * B * r1 + (size_t)p.itiles * B * r0;
+  size_t bwd = (size_t)p.asplit * B * r1 + (size_t)p.itiles * B * r0 + (p.bsplit > 1 ? (size_t)p.bsplit * r0 * r1 * r2 : 0);
   return sizeof(float) * (fwd > bwd ? fwd : bwd);
 }
 
@@ -254,13 +265,20 @@ extern "C" int rt_query_bwd(const float* core, const float* r_rows, const float*
   RT_REQUIRE(ws != nullptr, "rt_query_bwd: workspace is NULL");
   cudaStream_t s = (cudaStream_t)stream;
   QueryPlan p = query_plan(B, r0, r1, r2);
-  {
-    dim3 grid(rt::cdiv(r0 * r1, T), rt::cdiv(r2, T));
-    query_bwd_core_kernel<<<grid, 256, 0, s>>>(r_rows, s_rows, H, B, r0, r1, r2, d_core);
-    RT_LAUNCH_CHECK();
-  }
   float* ds_partial = (float*)ws;
   float* dr_partial = ds_partial + (size_t)p.asplit * B * r1;
+  {
+    float* core_partial = dr_partial + (size_t)p.itiles * B * r0;
+    dim3 grid(rt::cdiv(r0 * r1, T), rt::cdiv(r2, T), p.bsplit);
+    query_bwd_core_kernel<<<grid, 256, 0, s>>>(r_rows, s_rows, H, B, r0, r1, r2, p.b_per_split,
+                                               p.bsplit > 1 ? core_partial : d_core);
+    RT_LAUNCH_CHECK();
+    if (p.bsplit > 1) {
+      const int64_t cc = (int64_t)r0 * r1 * r2;
+      reduce_splits_kernel<<<(int)((cc + 255) / 256), 256, 0, s>>>(core_partial, p.bsplit, cc, d_core);
+      RT_LAUNCH_CHECK();
+    }
+  }
   {
     dim3 grid(rt::cdiv(B, T), p.itiles, p.asplit);
     query_bwd_rows_kernel<<<grid, 256, 0, s>>>(core, r_rows, s_rows, H, B, r0, r1, r2,
