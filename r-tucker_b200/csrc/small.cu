@@ -387,12 +387,17 @@ struct Ctx {
   int spd(const SpdBatch& b, int count, int nmax) {
     flush();
     if (err) return 1;
-    const size_t smem = ((size_t)nmax * (nmax + 1) / 2 + (size_t)SPD_NB * nmax) * sizeof(double);
+    size_t smem = ((size_t)nmax * (nmax + 1) / 2 + (size_t)SPD_NB * nmax) * sizeof(double);
     if (smem > 227 * 1024 || nmax > 256) {
       rt::set_error("small stage: rank %d exceeds the in-shared-memory Cholesky limit (232)", nmax); return 2; }
+    // tensor-core phases need one more [8][n] block; the largest ranks keep the plain fp64 path
+    static const bool dmma_off = getenv("RT_SPD_DMMA") && atoi(getenv("RT_SPD_DMMA")) == 0;
+    SpdBatch bb = b;
+    bb.dmma = (!dmma_off && smem + (size_t)SPD_NB * nmax * sizeof(double) <= 227 * 1024) ? 1 : 0;
+    if (bb.dmma) smem += (size_t)SPD_NB * nmax * sizeof(double);
     if (cudaFuncSetAttribute(spd_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       rt::set_error("small stage: cannot raise shared memory to %zu", smem); return 1; }
-    spd_blocked_kernel<<<count, SPD_THREADS, smem, s>>>(b); ++rt::g_launches;
+    spd_blocked_kernel<<<count, SPD_THREADS, smem, s>>>(bb); ++rt::g_launches;
     return 0;
   }
 };

@@ -290,9 +290,17 @@ struct SpdProblem {
   double* Ginv;      // [n][n] (may be NULL)
   int n;
 };
-struct SpdBatch { SpdProblem p[3]; };
+struct SpdBatch { SpdProblem p[3]; int dmma; };   // dmma: O(n^3) phases on the fp64 tensor cores (needs 8 n more doubles of smem)
 
 __device__ __forceinline__ int pk(int i, int j) { return i * (i + 1) / 2 + j; }
+__device__ __forceinline__ void spd_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// sum of 8 interleaved partial accumulators in a fixed order
+__device__ __forceinline__ double spd_sum8(const double (&c)[8][2], int e) {
+  return ((c[0][e] + c[1][e]) + (c[2][e] + c[3][e])) + ((c[4][e] + c[5][e]) + (c[6][e] + c[7][e]));
+}
 
 // Blocked variant (what the small stage launches): same contract and the same zero-pivot semantics as
 // spd_factor_kernel below, but ~10x fewer block barriers.  Two threads per matrix row.
@@ -359,9 +367,45 @@ spd_blocked_kernel(SpdBatch batch) {
 #define SPD_LAP(v) do {} while (0)
 #endif
   // ---------------- Cholesky ----------------
+  // The plain fp64 pipe of this part runs at ~3 TFLOP/s per GPU (20 GFLOP/s per SM, tools/dmma_probe.cu) against 36 on the
+  // fp64 tensor cores: the three n^3 / 3 phases (left-looking update, inverse, L^-T L^-1) took ~130 us each on the one SM
+  // a problem owns.  With batch.dmma they run as 8 x 8 x 4 DMMAs on fragments read from the packed triangle; a tile's
+  // contraction is spread over 8 interleaved accumulators (a dependent DMMA waits hundreds of cycles) summed in a
+  // fixed order.
+  const bool use_dmma = batch.dmma != 0;
+  const int warp = tid >> 5, lane = tid & 31, fg = lane >> 2, ft = lane & 3;
+  constexpr int NW = SPD_THREADS / 32;
+  double* accS = stage + SPD_NB * n;              // [SPD_NB][n] tile results of the inverse (dmma only)
   for (int kb = 0; kb < n; kb += SPD_NB) {
     const int nbk = min(SPD_NB, n - kb);
-    {
+    if (use_dmma) {
+      // T[row][c] = sum_{k < kb} L[row][k] L[kb + c][k] for rows >= kb: A = L rows, B[k][c] = L[kb + c][k]
+      if (kb > 0) {
+        const int ntile = (n - kb + 7) >> 3, nsteps = kb >> 2;
+        const int brow = kb + fg;
+        const bool bv = brow < n;
+        const double* Lb = Lp + pk(bv ? brow : 0, 0) + ft;
+        for (int tile = warp; tile < ntile; tile += NW) {
+          const int arow = kb + 8 * tile + fg;
+          const bool av = arow < n;
+          const double* La = Lp + pk(av ? arow : 0, 0) + ft;
+          double c[8][2];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { c[u][0] = 0.0; c[u][1] = 0.0; }
+          for (int s0 = 0; s0 < nsteps; s0 += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (s0 + u < nsteps) spd_dmma(c[u][0], c[u][1], av ? La[4 * (s0 + u)] : 0.0, bv ? Lb[4 * (s0 + u)] : 0.0);
+          }
+          // result element: row 8 tile + fg (the SAME row this lane fetched), columns 2 ft, 2 ft + 1
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = 2 * ft + e;
+            if (av && col < nbk && kb + col <= arow) Lp[pk(arow, kb + col)] -= spd_sum8(c, e);
+          }
+        }
+      }
+    } else {
       double acc[SPD_NB];
 #pragma unroll
       for (int c = 0; c < SPD_NB; ++c) acc[c] = 0.0;
@@ -501,17 +545,45 @@ spd_blocked_kernel(SpdBatch batch) {
     double acc[SPD_NB];
 #pragma unroll
     for (int r = 0; r < SPD_NB; ++r) acc[r] = 0.0;
-    if (j < n && j < ib) {
-      for (int k = j + sub; k < ib; k += SPD_TPR) {
-        const double xk = Lp[pk(k, j)];                  // X[k][j], rows above this block are already inverted
+    if (use_dmma) {
+      // T[r][j] = sum_{k = j}^{ib - 1} L[ib + r][k] X[k][j]: A = the staged rows, B[k][j] = X[k][j] (0 above the diagonal);
+      // a warp per tile of 8 columns, the contraction starts at the tile's first column
+      const int ntile = ib >> 3;
+      for (int tile = warp; tile < ntile; tile += NW) {
+        const int j0 = 8 * tile, jc = j0 + fg;            // B column of this lane
+        const int nsteps = (ib - j0) >> 2;
+        double c[8][2];
 #pragma unroll
-        for (int r = 0; r < SPD_NB; ++r) acc[r] = fma(stage[r * n + k], xk, acc[r]);   // rows r >= nbi are stale: unused
+        for (int u = 0; u < 8; ++u) { c[u][0] = 0.0; c[u][1] = 0.0; }
+        for (int s0 = 0; s0 < nsteps; s0 += 8) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (s0 + u < nsteps) {
+              const int k = j0 + 4 * (s0 + u) + ft;
+              spd_dmma(c[u][0], c[u][1], stage[fg * n + k], k >= jc ? Lp[pk(k, jc)] : 0.0);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) accS[fg * n + j0 + 2 * ft + e] = spd_sum8(c, e);
       }
-    }
+      __syncthreads();
+      if (j < n && j < ib) {
 #pragma unroll
-    for (int r = 0; r < SPD_NB; ++r) {
+        for (int r = 0; r < SPD_NB; ++r) acc[r] = accS[r * n + j];
+      }
+    } else {
+      if (j < n && j < ib) {
+        for (int k = j + sub; k < ib; k += SPD_TPR) {
+          const double xk = Lp[pk(k, j)];                  // X[k][j], rows above this block are already inverted
 #pragma unroll
-      for (int o = 1; o < SPD_TPR; o <<= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+          for (int r = 0; r < SPD_NB; ++r) acc[r] = fma(stage[r * n + k], xk, acc[r]);   // rows r >= nbi are stale: unused
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < SPD_NB; ++r) {
+#pragma unroll
+        for (int o = 1; o < SPD_TPR; o <<= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+      }
     }
     if (j < n && j < ib + nbi && sub == 0) {
       double xs[SPD_NB];
@@ -548,7 +620,42 @@ spd_blocked_kernel(SpdBatch batch) {
     }
   }
   SPD_LAP(t_b);
-  if (P.Ginv) {
+  if (P.Ginv && use_dmma) {
+    // Ginv = X^T X by 8 x 8 tiles of the lower half: G[i][j] = sum_{k >= i} X[k][i] X[k][j]; A[i][k] = X[k][i],
+    // B[k][j] = X[k][j], both 0 above the diagonal of X (only the first k-steps of a tile need the mask)
+    __syncthreads();
+    const int T8 = (n + 7) >> 3;
+    const double sc = s_scale[3];
+    for (int u0 = warp; u0 < T8 * (T8 + 1) / 2; u0 += NW) {
+      int it = (int)((sqrtf(8.0f * u0 + 1.0f) - 1.0f) * 0.5f);
+      while (it * (it + 1) / 2 > u0) --it;
+      while ((it + 1) * (it + 2) / 2 <= u0) ++it;
+      const int jt = u0 - it * (it + 1) / 2;
+      const int i0 = 8 * it, ic = i0 + fg, jc = 8 * jt + fg;
+      const int nsteps = (n - i0 + 3) >> 2;
+      double c[8][2];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { c[u][0] = 0.0; c[u][1] = 0.0; }
+      for (int s0 = 0; s0 < nsteps; s0 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (s0 + u < nsteps) {
+            const int k = i0 + 4 * (s0 + u) + ft;
+            const bool kv = k < n;
+            spd_dmma(c[u][0], c[u][1], (kv && ic < n && k >= ic) ? Lp[pk(k, ic)] : 0.0, (kv && jc < n && k >= jc) ? Lp[pk(k, jc)] : 0.0);
+          }
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = i0 + fg, j = 8 * jt + 2 * ft + e;
+        if (i < n && j <= i) {
+          const double v = spd_sum8(c, e) * sc;
+          P.Ginv[(int64_t)i * n + j] = v;
+          P.Ginv[(int64_t)j * n + i] = v;
+        }
+      }
+    }
+  } else if (P.Ginv) {
     // Ginv = X^T X, lower half computed (four independent accumulators per element), mirrored on store
     for (int e = tid; e < n * (n + 1) / 2; e += nt) {
       int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
