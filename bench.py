@@ -490,6 +490,15 @@ def rooflines(w, n_local, ms_step, stage_ms, score_timing, eval_ms, peaks):
     return out
 
 
+_T0 = time.time()
+
+
+def progress(msg):
+    """Phase marker on stderr (RT_BENCH_LOG=1): where a multi-GPU run is when it stops answering."""
+    if os.environ.get("RT_BENCH_LOG", "0") == "1":
+        print(f"[bench +{time.time() - _T0:6.1f}s rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -546,6 +555,7 @@ def main():
     total_steps = args.warmup + args.steps
     run = Runner(w, graph, dev, world, rank, group, args.variant, use_graphs, 2 * total_steps)
 
+    progress("runner built; device-resident timing")
     # ---- device-resident timing (CUDA graphs replay fit + step; inputs already in HBM) ----
     clocks = ClockSampler()
     clocks.start()
@@ -555,6 +565,7 @@ def main():
     value = n_tr / (ms * 1e-3)
     eng = run.opt._engine
 
+    progress(f"resident done: {ms / args.steps:.3f} ms/step; stage profile")
     # ---- per-stage profile pass: same steps launched eagerly with CUDA-event brackets around every stage
     #      (the graph path cannot be bracketed); also counts the kernels of one step ----
     prof_steps = min(args.steps, 10)
@@ -569,19 +580,23 @@ def main():
     eng.timers = None
     launches = launches_per_step * args.steps if launches_eager <= 2 * args.steps else launches_eager
 
+    progress("stage profile done; e2e")
     # ---- end to end: host batches in, loss out, every step ----
     ms_e2e, tr_e2e, h2d, d2h = run.timed_e2e(total_steps, args.steps)
     clock_info = clocks.stop()
     e2e_value = tr_e2e / (ms_e2e * 1e-3)
 
+    progress("e2e done; eval")
     # ---- filtered evaluation ----
     eval_qps = eval_ms = None
     if args.eval_batches > 0:
         eval_qps, eval_ms = run.eval_qps(args.eval_batches, w.get("eval"))
 
+    progress("eval done; score kernel timing")
     score_timing = time_score_kernel(run, dev, args.variant, args.steps,
                                      large=(world == 1 and args.workload != "synthetic-1m" and not args.no_large_kernel))
 
+    progress("score timing done; other variant")
     # ---- the other score kernel on the same batches ----
     strict = fast = None
     if not args.no_strict:
@@ -602,6 +617,7 @@ def main():
         del run0
         torch.cuda.empty_cache()
 
+    progress("other variant done; c5")
     # ---- BASELINE configs[4]: synthetic 1M entities, rank (200,200,200), on the same ranks ----
     c5 = None
     if not args.no_c5 and args.workload != "synthetic-1m":
@@ -620,11 +636,18 @@ def main():
         except RuntimeError as exc:
             c5 = {"error": str(exc)[:200]}
 
+    progress("c5 done; teardown")
     if world > 1:
+        # No destroy_process_group(): with CUDA graphs that captured NCCL kernels still alive it never returned (measured:
+        # both ranks reached this line after 25 s and sat in the destructor until the driver's limit).  Every rank
+        # synchronises, passes one last barrier and leaves through os._exit once its output is flushed.
+        torch.cuda.synchronize()
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
     if rank != 0:
-        return
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(peaks_path)) if os.path.isfile(peaks_path) else {}
@@ -685,6 +708,10 @@ def main():
         "clocks": clock_info,
     }
     print(json.dumps(line))
+    if world > 1:          # see the teardown note above: leave without running the communicator's destructor
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
