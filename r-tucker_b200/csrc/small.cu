@@ -198,6 +198,8 @@ struct Ctx {
       }
     }
     rec.op.units = tiles * g.ksplit;
+    g.thin = (m <= kThinM && K1 == 1 && K2 <= kThinK && batch == 1 && g.ksplit == 1 && n >= 4 * kThinCols) ? 1 : 0;
+    if (g.thin) rec.op.units = cdiv(n, kThinCols);
     auto ext = [](int64_t a, int64_t b, int64_t c, int64_t d) { return (size_t)(a + b + c + d + 1); };
     const size_t ea = ext((int64_t)(m - 1) * a_m, (int64_t)(K1 - 1) * a_k1, (int64_t)(K2 - 1) * a_k2, (int64_t)(batch - 1) * a_b);
     const size_t eb = ext((int64_t)(n - 1) * b_n, (int64_t)(K1 - 1) * b_k1, (int64_t)(K2 - 1) * b_k2, (int64_t)(batch - 1) * b_b);
@@ -388,12 +390,13 @@ struct Ctx {
     flush();
     if (err) return 1;
     size_t smem = ((size_t)nmax * (nmax + 1) / 2 + (size_t)SPD_NB * nmax) * sizeof(double);
-    if (smem > 227 * 1024 || nmax > 256) {
-      rt::set_error("small stage: rank %d exceeds the in-shared-memory Cholesky limit (232)", nmax); return 2; }
+    const size_t smem_limit = 227 * 1024 - 3072;      // the kernel also has ~2.7 KB of static shared memory
+    if (smem > smem_limit || nmax > 256) {
+      rt::set_error("small stage: rank %d exceeds the in-shared-memory Cholesky limit (230)", nmax); return 2; }
     // tensor-core phases need one more [8][n] block; the largest ranks keep the plain fp64 path
     static const bool dmma_off = getenv("RT_SPD_DMMA") && atoi(getenv("RT_SPD_DMMA")) == 0;
     SpdBatch bb = b;
-    bb.dmma = (!dmma_off && smem + (size_t)SPD_NB * nmax * sizeof(double) <= 227 * 1024) ? 1 : 0;
+    bb.dmma = (!dmma_off && smem + (size_t)SPD_NB * nmax * sizeof(double) <= smem_limit) ? 1 : 0;
     if (bb.dmma) smem += (size_t)SPD_NB * nmax * sizeof(double);
     if (cudaFuncSetAttribute(spd_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       rt::set_error("small stage: cannot raise shared memory to %zu", smem); return 1; }
@@ -589,18 +592,21 @@ extern "C" int rt_small_project(const float* core, const float* core_old, const 
   c.unfold_gram<float>(2, U1, d, Cf, d[2], KCf[2], d[2], 1.0, 0.0);
   c.unfold_gram<float>(2, U2, d, Cf, d[2], KCf[2] + (int64_t)d[2] * d[2], d[2], 1.0, 0.0);
   // KC_1: V1 = D x2 W2a + Ta x2 W2b ; V2 = Ta x2 W2a     (reuse U1/U2 storage after KC_2)
-  float* V1 = U1; float* V2 = U2;
+  // Every intermediate has its own buffer (T0, T1, T7 and both halves are idle during the projection): the levels come
+  // from byte-range hazards, so REUSING U1 / U2 / Ta / D here serialised the three KC chains behind each other
+  // (16 levels); with private buffers the KC_0 chain starts at level 0 and KC_1 right after the first mode products.
+  float* V1 = c.Tf(0); float* V2 = c.Tf(0) + c.L.c;
   c.mode_prod<float>(2, Wa[2], st_o[2], st_i[2], d[2], d[2], D, d, V1, 1.0, 0.0);
   c.mode_prod<float>(2, Wb[2], st_o[2], st_i[2], d[2], d[2], Ta, d, V1, 1.0, 1.0);
   c.mode_prod<float>(2, Wa[2], st_o[2], st_i[2], d[2], d[2], Ta, d, V2, 1.0, 0.0);
   c.unfold_gram<float>(1, V1, d, Cf, d[1], KCf[1], d[1], 1.0, 0.0);
   c.unfold_gram<float>(1, V2, d, Cf, d[1], KCf[1] + (int64_t)d[1] * d[1], d[1], 1.0, 0.0);
   // KC_0: Ea = Co x1 W1a, Eb = Co x1 W1b, F = Xo x1 W1a + Eb ; Z1 = F x2 W2a + Ea x2 W2b ; Z2 = Ea x2 W2a
-  float* Ea = Ta; float* F = D;
+  float* Ea = c.Tf(1); float* F = c.Tf(1) + c.L.c;
   c.mode_prod<float>(1, Wa[1], st_o[1], st_i[1], d[1], d[1], Co, d, Ea, 1.0, 0.0);
   c.mode_prod<float>(1, Wa[1], st_o[1], st_i[1], d[1], d[1], Xo, d, F, 1.0, 0.0);
   c.mode_prod<float>(1, Wb[1], st_o[1], st_i[1], d[1], d[1], Co, d, F, 1.0, 1.0);
-  float* Z1 = U1; float* Z2 = U2;
+  float* Z1 = c.Tf(7); float* Z2 = c.Tf(7) + c.L.c;
   c.mode_prod<float>(2, Wa[2], st_o[2], st_i[2], d[2], d[2], F, d, Z1, 1.0, 0.0);
   c.mode_prod<float>(2, Wb[2], st_o[2], st_i[2], d[2], d[2], Ea, d, Z1, 1.0, 1.0);
   c.mode_prod<float>(2, Wa[2], st_o[2], st_i[2], d[2], d[2], Ea, d, Z2, 1.0, 0.0);

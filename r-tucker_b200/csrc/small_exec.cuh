@@ -48,6 +48,7 @@ struct GemmPart {
   int64_t a_m, a_k1, a_k2, b_k1, b_k2, b_n, c_m, c_n, a_b, b_b, c_b;
   double alpha, beta;
   int ta, tb, tc, m, n, K1, K2, batch, ksplit, steps_per_split, tiles_m, tiles_n;
+  int thin, pad_;   // thin: m <= 16, K <= 32 (a mode product along a small rank): one output COLUMN per thread (thin_unit)
 };
 struct EwPart {
   const void* x; const void* y; void* z;
@@ -62,7 +63,7 @@ struct Op {
 };
 // A program travels to the device as a kernel PARAMETER (by value: captured as is by CUDA graphs, no staging
 // buffer to keep alive); CUDA >= 12.1 allows 32764 bytes of parameters.
-constexpr int kMaxOps = 150;
+constexpr int kMaxOps = 146;
 struct Program {
   int nops;
   unsigned int* bar;
@@ -191,6 +192,41 @@ __device__ __noinline__ void gemm_unit(const GemmPart& op, int unit, double* red
         if (op.beta != 0.0) v += op.beta * ld_as_f64(op.C, ci, op.tc);
         st_from_f64(op.C, ci, op.tc, v);
       }
+    }
+  }
+  __syncthreads();
+}
+
+// Thin GEMM unit: C[m, n] with m <= 16 rows and K <= 32 (the mode product along the relation rank, r0 = 10: out[a', x] =
+// sum_a W[a', a] X[a, x] over 40 000 columns x).  As 32 x 32 DMMA tiles this was 1 250 units of three k-steps whose
+// fixed cost (operand fetch, cross-warp reduction) is ~6 us each: 20-25 us per product, ten products per step.  Here a
+// thread owns one column: K coalesced loads, m x K fp64 FMAs against the small matrix in shared memory, m coalesced stores.
+constexpr int kThinM = 16, kThinK = 32, kThinCols = kExecThreads;
+__device__ __forceinline__ void thin_unit(const GemmPart& op, int unit, double* As) {
+  const int tid = threadIdx.x;
+  const int K = op.K2;
+  for (int e = tid; e < op.m * K; e += kExecThreads) {
+    const int mm = e / K, k = e - mm * K;
+    As[e] = ld_as_f64(op.A, (int64_t)mm * op.a_m + (int64_t)k * op.a_k2, op.ta);
+  }
+  __syncthreads();
+  const int col = unit * kThinCols + tid;
+  if (col < op.n) {
+    double b[kThinK];
+#pragma unroll
+    for (int k = 0; k < kThinK; ++k) b[k] = k < K ? ld_as_f64(op.B, (int64_t)k * op.b_k2 + (int64_t)col * op.b_n, op.tb) : 0.0;
+    const double alpha = op.alpha * (op.alpha_dev ? __ldcg(op.alpha_dev) : 1.0);
+    for (int mm = 0; mm < op.m; ++mm) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < kThinK; k += 2) {
+        if (k < K) s0 = fma(As[mm * K + k], b[k], s0);
+        if (k + 1 < K) s1 = fma(As[mm * K + k + 1], b[k + 1], s1);
+      }
+      const int64_t ci = (int64_t)mm * op.c_m + (int64_t)col * op.c_n;
+      double v = alpha * (s0 + s1);
+      if (op.beta != 0.0) v += op.beta * ld_as_f64(op.C, ci, op.tc);
+      st_from_f64(op.C, ci, op.tc, v);
     }
   }
   __syncthreads();
@@ -376,7 +412,8 @@ small_exec_kernel(const __grid_constant__ Program prog) {
       const int lu = u - ub;
       switch (op.kind) {
         case OP_GEMM:
-          if (op.g.ta == DT_F64 && op.g.tb == DT_F64) gemm_unit<double, double>(op.g, lu, xsm);
+          if (op.g.thin) thin_unit(op.g, lu, xsm);
+          else if (op.g.ta == DT_F64 && op.g.tb == DT_F64) gemm_unit<double, double>(op.g, lu, xsm);
           else if (op.g.ta == DT_F32 && op.g.tb == DT_F32) gemm_unit<float, float>(op.g, lu, xsm);
           else if (op.g.ta == DT_F32) gemm_unit<float, double>(op.g, lu, xsm);
           else gemm_unit<double, float>(op.g, lu, xsm);

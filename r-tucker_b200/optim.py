@@ -39,7 +39,7 @@ class _RiemannianBase(Optimizer):
     adam = None            # (beta1, beta2, eps, step_velocity) for the Adam subclasses
 
     def __init__(self, params, rank, max_lr, momentum_beta: Optional[float] = None, group=None,
-                 n_total=None, n_begin=0, score_variant=0, ops=None, use_graphs=False):
+                 n_total=None, n_begin=0, score_variant=3, ops=None, use_graphs=False):
         self.rank = rank
         self.max_lr = max_lr
         self.lr = max_lr

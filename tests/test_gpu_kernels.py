@@ -671,3 +671,25 @@ def test_score_bce_tc3_at_initialisation_and_sharded(cuda_device):
     G_s = G[:, lo:hi]
     assert relerr(H_s, G_s @ O[lo:hi].double()) < REL
     assert relerr(dO_s, G_s.T @ q.double()) < REL
+
+
+@pytest.mark.parametrize("rank", [(10, 200, 200), (7, 37, 50), (3, 5, 9), (16, 64, 220), (4, 30, 228)])
+def test_small_prepare_gram_inverses(cuda_device, rank):
+    """rt_small_prepare: A_i = (C_(i) C_(i)^T)^-1 by the blocked Cholesky / inverse / L^-T L^-1 kernel (its n^3 phases run
+    as DMMAs on the packed triangle up to rank 223, the plain fp64 path above -- 228 here; odd sizes exercise the masked
+    edge tiles) against numpy's fp64 inverse.  Reference use: the gauge of TuckerRiemannian.grad
+    (call site src/model/asymmetric/optim.py:89)."""
+    from rtucker_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    core = torch.randn(rank, generator=g, dtype=torch.float64).float()
+    small = ops.SmallStage(rank, 16, False, cuda_device)
+    small.prepare(core.to(cuda_device))
+    C = core.double().numpy()
+    for mode in range(3):
+        unf = np.moveaxis(C, mode, 0).reshape(rank[mode], -1)
+        G = unf @ unf.T
+        ref = np.linalg.inv(G)
+        got = small.ainv(mode).double().cpu().numpy()
+        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        assert err < 1e-9 * max(np.linalg.cond(G), 1.0), (mode, err)
+        assert np.linalg.norm(got @ G - np.eye(rank[mode])) < 1e-9 * np.linalg.cond(G)
