@@ -239,8 +239,16 @@ __device__ __forceinline__ void reduce_unit(const GemmPart& op, int unit) {
   for (int mI = 0; mI < kReduceChunk / kExecThreads; ++mI) {
     const int64_t e = (int64_t)unit * kReduceChunk + threadIdx.x + kExecThreads * mI;
     if (e >= total) continue;
+    // 16 loads in flight per thread (a 63-way split summed 4 at a time was 16 dependent L2 round trips), fixed order
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int zz = 0;
+    for (; zz + 16 <= op.ksplit; zz += 16) {
+      double v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = __ldcg(op.partial + (int64_t)(zz + u) * total + e);
+#pragma unroll
+      for (int u = 0; u < 16; u += 4) { s0 += v[u]; s1 += v[u + 1]; s2 += v[u + 2]; s3 += v[u + 3]; }
+    }
     for (; zz + 4 <= op.ksplit; zz += 4) {
       s0 += __ldcg(op.partial + (int64_t)zz * total + e);
       s1 += __ldcg(op.partial + (int64_t)(zz + 1) * total + e);
