@@ -470,7 +470,11 @@ def rooflines(w, n_local, ms_step, stage_ms, score_timing, eval_ms, peaks):
     out.append({"family": "c-small: N-independent fp64 stage (Gram inverses, projection cores, HOSVD subspaces)",
                 "bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None,
                 "ms_per_step": sum(st.get(k, 0.0) for k in sm_keys), "share_of_step": share(sm_keys),
-                "note": "replicated on every rank; persistent DMMA executor + purification kernel, a few dozen grid-barrier rounds"})
+                "note": "replicated on every rank; persistent DMMA executor + purification kernel: ~47 dependency levels and "
+                        "~85 purification / Newton-Schulz rounds per step, each a grid barrier + one wave of 32 x 32 DMMA tiles. "
+                        "Measured fp64 ceilings of this part (tools/dmma_probe.cu): DMMA 36.4 TFLOP/s, plain DFMA 2.9 TFLOP/s; the "
+                        "stage's GEMM units run at 18-19 TFLOP/s inside their k-loops (L2 operand bandwidth 31.5 B/clk/SM = the "
+                        "DMMA rate for 32 x 32 tiles)"})
     # (a) query contraction
     flops_a = 8.0 * BATCH * r0 * r1 * r2
     ms_a = st.get("query_fwd", 0.0) + st.get("query_bwd", 0.0)
@@ -483,9 +487,15 @@ def rooflines(w, n_local, ms_step, stage_ms, score_timing, eval_ms, peaks):
     if eval_ms:
         flops_d = 2.0 * BATCH * n_local * r2
         ach_d = flops_d / (eval_ms * 1e-3) / 1e12
-        out.append({"family": "d: fused score + filtered rank (evaluation batch of 512)", "bound": "fp32-ffma",
-                    "achieved": ach_d, "peak": FFMA_PEAK_TF, "unit": "TFLOP/s", "frac": ach_d / FFMA_PEAK_TF,
-                    "peak_source": "nominal FP32 FFMA (ranks need fp32-accurate scores)", "algorithmic_flops_per_batch": flops_d,
+        tc_eval = r2 >= 64 and n_local >= 1024          # rt_score_rank_fused takes the tensor-core path for these shapes
+        peak_d = tf_burst / 6.0 if tc_eval else FFMA_PEAK_TF
+        out.append({"family": "d: fused score + filtered rank (evaluation batch of 512)",
+                    "bound": "tensor" if tc_eval else "fp32-ffma",
+                    "achieved": ach_d, "peak": peak_d, "unit": "TFLOP/s", "frac": ach_d / peak_d,
+                    "peak_source": (src + " bf16_tflops / 6 (fp32-accurate logits = 3 TF32 MMAs at half the bf16 rate; exact fp32 "
+                                    "re-check of the band around the target)") if tc_eval
+                                   else "nominal FP32 FFMA (ranks need fp32-accurate scores)",
+                    "algorithmic_flops_per_batch": flops_d,
                     "ms_per_batch": eval_ms, "share_of_step": None})
     return out
 
@@ -569,6 +579,8 @@ def main():
     # ---- per-stage profile pass: same steps launched eagerly with CUDA-event brackets around every stage
     #      (the graph path cannot be bracketed); also counts the kernels of one step ----
     prof_steps = min(args.steps, 10)
+    for i in range(2):                       # two untimed eager steps: the first eager launches after graph replay stall
+        run.one_step(*run.dev_batches[i])
     eng.timers = {}
     l0 = lib().rt_launch_count()
     run.barrier()
@@ -699,7 +711,7 @@ def main():
         "roofline": roofline,
         "roofline_all": roof_all,
         "stage_ms": stage_ms,
-        "stage_ms_note": "mean ms per stage over %d EAGERLY launched steps (CUDA events on the launching stream): stages made "
+        "stage_ms_note": "median ms per stage over %d EAGERLY launched steps (CUDA events on the launching stream): stages made "
                          "of several launches include host launch gaps, so the sum exceeds ms_per_step, which is "
                          "measured on the CUDA-graph path; shares in roofline_all are shares of this sum" % prof_steps,
         "cpu_baseline": cpu,

@@ -28,6 +28,7 @@
 // entity-sharded run, which keeps the replicated cores identical.
 #include "common.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace rt {
 
@@ -57,6 +58,7 @@ struct SubBatch {
   int count;
   unsigned int* bar;    // grid barrier counter (zeroed by the host before the launch)
   double* scratch;      // [gridDim][2 * kSubMaxProblems] per-CTA partials of phase 0
+  int debug;            // RT_SUB_PRINT=1: print the iteration counts of every problem
 };
 
 enum SubState { S_TC2 = 0, S_COPY = 1, S_NSG = 2, S_NSZ = 3, S_DONE = 4 };
@@ -385,6 +387,7 @@ subspace_kernel(SubBatch batch) {
             if (ns_last[pi]) {
               state[pi] = S_DONE;
               if (blockIdx.x == 0 && P.info) { P.info[0] = iters[pi]; P.info[1] = ns_iters[pi]; }
+              if (blockIdx.x == 0 && batch.debug) printf("subspace problem %d (n=%d r=%d): purification %d rounds, Newton-Schulz %d x 2 rounds\n", pi, P.n, P.r, iters[pi], ns_iters[pi]);
             } else {
               zcur[pi] ^= 1;
               state[pi] = S_NSG;
@@ -434,6 +437,7 @@ int subspace_batch(int count, const double* const* N, const int* n, const int* r
   b.count = count;
   b.bar = (unsigned int*)shared_ws;
   b.scratch = (double*)((char*)shared_ws + 256);
+  { static const int dbg = getenv("RT_SUB_PRINT") ? atoi(getenv("RT_SUB_PRINT")) : 0; b.debug = dbg; }
   for (int i = 0; i < count; ++i) {
     RT_REQUIRE(n[i] >= 1 && n[i] <= 512 && r[i] >= 1 && r[i] <= n[i], "subspace_batch: n=%d r=%d out of range", n[i], r[i]);
     SubLayout L = sub_layout(n[i], r[i]);

@@ -134,9 +134,14 @@ class StepEngine:
         self.timers.setdefault(name, []).append((e0, e1))
 
     def stage_ms(self):
-        """Mean milliseconds per call of every bracketed stage (synchronises)."""
+        """Median milliseconds per call of every bracketed stage (synchronises).  The median, not the mean: eagerly
+        launched stages pick up one-off host stalls (allocator, lazy module loading) that are not kernel time."""
         torch.cuda.synchronize()
-        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in (self.timers or {}).items()}
+        out = {}
+        for k, v in (self.timers or {}).items():
+            ms = sorted(a.elapsed_time(b) for a, b in v)
+            out[k] = ms[len(ms) // 2] if len(ms) % 2 else 0.5 * (ms[len(ms) // 2 - 1] + ms[len(ms) // 2])
+        return out
 
     def _set_hyper(self, lr, reg, beta, normalize):
         vals = (float(lr), float(reg), float(beta or 0.0), float(normalize or 0.0))
