@@ -716,12 +716,7 @@ int eig_batch(int count, const double* const* A, const int* n, double* const* w,
     total_items += L.npairs * L.npairs + (L.np / EP) * L.npairs;
   }
   const size_t smem = (size_t)kEigWarps * (3 * EP * ELD + 4 * EB) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    RT_CHECK_CUDA(cudaFuncSetAttribute(eig_block_jacobi_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  RT_CHECK_CUDA(ensure_dyn_smem((const void*)eig_block_jacobi_kernel, smem));   // cached per (kernel, device)
   // one warp per phase-B tile if possible (latency matters more than occupancy), capped at 1 CTA / SM
   // (launch bounds) so the cooperative grid is co-resident
   int grid = total_items;
