@@ -167,8 +167,9 @@ struct Ctx {
   void gemm_any(const void* A, int ta, const void* B, int tb, void* C, int tc, int m, int n, int K1, int K2,
                 int64_t a_m, int64_t a_k1, int64_t a_k2, int64_t b_k1, int64_t b_k2, int64_t b_n, int64_t c_m,
                 int64_t c_n, int batch, int64_t a_b, int64_t b_b, int64_t c_b, double alpha, double beta,
-                const double* alpha_dev = nullptr) {
+                const double* alpha_dev = nullptr, bool sym = false) {
     if (err || m <= 0 || n <= 0) return;
+    if (m != n || batch != 1) sym = false;
     Rec rec{};
     GemmPart& g = rec.op.g;
     rec.op.kind = OP_GEMM;
@@ -178,7 +179,8 @@ struct Ctx {
     g.batch = batch; g.a_b = a_b; g.b_b = b_b; g.c_b = c_b;
     g.alpha = alpha; g.beta = beta; g.alpha_dev = alpha_dev;
     g.tiles_m = cdiv(m, XT); g.tiles_n = cdiv(n, XT);
-    const int tiles = batch * g.tiles_m * g.tiles_n;
+    g.sym = sym ? 1 : 0;
+    const int tiles = sym ? g.tiles_n * (g.tiles_n + 1) / 2 : batch * g.tiles_m * g.tiles_n;
     const int S = K1 * cdiv(K2, 4);
     g.ksplit = 1; g.steps_per_split = S > 0 ? S : 1; g.partial = nullptr;
     if (tiles < 120 && S >= 32) {
@@ -199,7 +201,7 @@ struct Ctx {
     }
     rec.op.units = tiles * g.ksplit;
     g.thin = (m <= kThinM && K1 == 1 && K2 <= kThinK && batch == 1 && g.ksplit == 1 && n >= 4 * kThinCols) ? 1 : 0;
-    if (g.thin) rec.op.units = cdiv(n, kThinCols);
+    if (g.thin) { rec.op.units = cdiv(n, kThinCols); g.sym = 0; }
     auto ext = [](int64_t a, int64_t b, int64_t c, int64_t d) { return (size_t)(a + b + c + d + 1); };
     const size_t ea = ext((int64_t)(m - 1) * a_m, (int64_t)(K1 - 1) * a_k1, (int64_t)(K2 - 1) * a_k2, (int64_t)(batch - 1) * a_b);
     const size_t eb = ext((int64_t)(n - 1) * b_n, (int64_t)(K1 - 1) * b_k1, (int64_t)(K2 - 1) * b_k2, (int64_t)(batch - 1) * b_b);
@@ -229,7 +231,7 @@ struct Ctx {
   template <typename T>
   void gemm(const GemmT<T>& g) {
     gemm_any(g.A, DT<T>::v, g.B, DT<T>::v, g.C, DT<T>::v, g.m, g.n, g.K1, g.K2, g.a_m, g.a_k1, g.a_k2, g.b_k1, g.b_k2,
-             g.b_n, g.c_m, g.c_n, g.batch, g.a_b, g.b_b, g.c_b, g.alpha, g.beta);
+             g.b_n, g.c_m, g.c_n, g.batch, g.a_b, g.b_b, g.c_b, g.alpha, g.beta, nullptr, g.sym != 0);
   }
 
   // Y = alpha * (X x_mode M) + beta * Y.  M is (mo x mi) with strides (sm_o, sm_i);
@@ -265,6 +267,7 @@ struct Ctx {
     GemmT<T> g{};
     g.alpha = alpha; g.beta = beta; g.batch = 1;
     g.A = X; g.B = Y; g.C = out; g.m = dx[mode]; g.n = my; g.c_m = ldo; g.c_n = 1;
+    g.sym = (X == Y && my == dx[mode]) ? 1 : 0;      // X_(mode) X_(mode)^T: symmetric, half the tiles
     if (mode == 0) {
       const int64_t rest = (int64_t)dx[1] * dx[2];
       g.K1 = 1; g.K2 = (int)rest;

@@ -48,7 +48,7 @@ struct GemmPart {
   int64_t a_m, a_k1, a_k2, b_k1, b_k2, b_n, c_m, c_n, a_b, b_b, c_b;
   double alpha, beta;
   int ta, tb, tc, m, n, K1, K2, batch, ksplit, steps_per_split, tiles_m, tiles_n;
-  int thin, pad_;   // thin: m <= 16, K <= 32 (a mode product along a small rank): one output COLUMN per thread (thin_unit)
+  int thin, sym;    // sym: C = C^T (A = B, a Gram): only tiles with tn >= tm are computed, each is stored twice.  thin: m <= 16, K <= 32 (a mode product along a small rank): one output COLUMN per thread (thin_unit)
 };
 struct EwPart {
   const void* x; const void* y; void* z;
@@ -109,9 +109,20 @@ __device__ __noinline__ void gemm_unit(const GemmPart& op, int unit, double* red
   const int g = lane >> 2, t = lane & 3;
   int rem = unit;
   const int z = rem % op.ksplit; rem /= op.ksplit;
-  const int tn = rem % op.tiles_n; rem /= op.tiles_n;
-  const int tm = rem % op.tiles_m;
-  const int b = rem / op.tiles_m;
+  int tn, tm, b;
+  if (op.sym) {                          // upper triangle of tiles, row by row: tm <= tn
+    const int T = op.tiles_n, ntri = T * (T + 1) / 2;
+    int tt = rem % ntri;
+    b = rem / ntri;
+    tm = 0;
+    while (tt >= T - tm) { tt -= T - tm; ++tm; }
+    tn = tm + tt;
+  } else {
+    tn = rem % op.tiles_n; rem /= op.tiles_n;
+    tm = rem % op.tiles_m;
+    b = rem / op.tiles_m;
+  }
+  const bool mirror = op.sym && tm != tn;
   const TA* A = reinterpret_cast<const TA*>(op.A) + (int64_t)b * op.a_b;
   const TB* B = reinterpret_cast<const TB*>(op.B) + (int64_t)b * op.b_b;
   const int i0 = tm * XT, j0 = tn * XT;
@@ -186,11 +197,13 @@ __device__ __noinline__ void gemm_unit(const GemmPart& op, int unit, double* red
     if (mm < op.m && nn < op.n) {
       if (op.ksplit > 1) {
         op.partial[(((int64_t)z * op.batch + b) * op.m + mm) * op.n + nn] = sum;
+        if (mirror) op.partial[(((int64_t)z * op.batch + b) * op.m + nn) * op.n + mm] = sum;
       } else {
         const int64_t ci = (int64_t)b * op.c_b + (int64_t)mm * op.c_m + (int64_t)nn * op.c_n;
         double v = alpha * sum;
         if (op.beta != 0.0) v += op.beta * ld_as_f64(op.C, ci, op.tc);
         st_from_f64(op.C, ci, op.tc, v);
+        if (mirror) st_from_f64(op.C, (int64_t)b * op.c_b + (int64_t)nn * op.c_m + (int64_t)mm * op.c_n, op.tc, v);
       }
     }
   }

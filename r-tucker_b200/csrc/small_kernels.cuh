@@ -20,6 +20,7 @@ struct GemmT {
   double alpha, beta;
   int ksplit, k_per_split;  // split over the flattened K (batch == 1 only)
   T* partial;               // [ksplit][m][n] when ksplit > 1
+  int sym;                  // C is symmetric (A = B with equal strides): compute the upper triangle of tiles only
 };
 using Gemm = GemmT<double>;
 
