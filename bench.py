@@ -431,7 +431,7 @@ def rooflines(w, n_local, ms_step, stage_ms, score_timing, eval_ms, peaks):
                "peak": peak_b, "unit": "TFLOP/s", "frac": ach / peak_b if ach else None,
                "peak_source": (src + " bf16_tflops / 6 (fp32-accurate products = 3 TF32 MMAs at half the bf16 rate; op timed alone)") if vnt == 3 else
                               ((src + " bf16_tflops (burst: kernel timed alone)") if vnt else "nominal FP32 FFMA (148 SMs x 128 lanes x 2 x 1.965 GHz)"),
-               "algorithmic_flops_per_launch": flops_b, "ms_per_launch": k_ms, "traffic": ncu_traffic("score_v3:wn18rr"),
+               "algorithmic_flops_per_launch": flops_b, "ms_per_launch": k_ms, "traffic": ncu_traffic("score_v3:wn18rr" if vnt == 2 else "score_variant%d:wn18rr" % vnt),
                "share_of_step": share(["score_bce_fwd_bwd"]), "timing": score_timing}
     if score_timing and score_timing.get("large") and score_timing["large"].get("kernel_ms"):
         lg = score_timing["large"]
