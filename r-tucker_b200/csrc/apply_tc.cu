@@ -69,7 +69,8 @@ struct Args {
   uint32_t cs_k, kimg_bytes, stage_bytes;
   int debug;                          // profiling build only (RT_APPLY_DEBUG): 1 no X loads, 2 no K loads, 4 no MMAs, 8 ld.cg
   // ---- rank mode (MODE 1): rows = entities of the shard, columns of job j = queries [256 j, 256 j + 256) ----
-  const float* thr;                   // [3][Bp]: lo, hi, eqlo logit thresholds per query (Bp = 256 * njobs)
+  const float* thr;                   // [4][Bp]: lo0, hi0, eqlo0, slope per query (Bp = 256 * njobs), see rank_thresholds_kernel
+  const float* onorms;                // [n_local] upper bounds of the entity row norms
   const int32_t* target;              // [B] global id of the target entity
   int B, n_begin;
   int32_t* greater; int32_t* equal; int32_t* equal_before;
@@ -145,6 +146,132 @@ __global__ void pack_K_kernel(PackArgs a) {
 #define PROF_PRINT(role)
 #endif
 
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// ---- filtered-ranking epilogue of 8 columns (queries) of one thread's row (entity) --------------------------------
+// NOT inlined: the epilogue of a tile is 128 columns per thread, and as one unrolled block it was ~30 000 instructions
+// (0.5 MB) executed once per tile -- ncu showed the epilogue warps stalled on instruction fetch (stall_no_inst at every
+// reconvergence point), 110 k cycles per tile against 10 k of tensor work.  As a function called 16 times the code
+// stays resident.
+struct RankChunkCtx {
+  const float* lo; const float* hi; const float* eq; const float* slope;   // thresholds of query 0 of this warp's columns
+  float onorm;                                            // upper bound of ||O_j|| of this thread's entity
+  const int32_t* target; int32_t* equal; int32_t* equal_before;
+  int2* cand; int* cand_count;
+  int cand_cap, B, q0, e_loc, e_glob;
+  bool rv, any_eq;
+};
+struct RankChunkOut { uint32_t counts; float lsum; };
+__device__ __noinline__ RankChunkOut rank_chunk8(const RankChunkCtx& cx, int c0, float z0, float z1, float z2, float z3, float z4,
+                                                 float z5, float z6, float z7) {
+  const int lane = threadIdx.x & 31;
+  // hot fields of the context in registers; the rare paths (saturated targets, candidates) read theirs from memory
+  const int cB = cx.B, q0 = cx.q0;
+  const bool rv = cx.rv, any_eq = cx.any_eq;
+  const float zs[8] = {z0, z1, z2, z3, z4, z5, z6, z7};
+  const float* lop = cx.lo + c0;
+  const float* hip = cx.hi + c0;
+  const float* slp = cx.slope + c0;
+  const float onorm = cx.onorm;
+  RankChunkOut out;
+  out.counts = 0u; out.lsum = 0.0f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    // thresholds of 4 columns at a time (all 8 at once spilled 340 bytes in this function)
+    float4 lo4, hi4, sl4;
+    if ((u & 3) == 0) {
+      lo4 = __ldg(reinterpret_cast<const float4*>(lop + u)); hi4 = __ldg(reinterpret_cast<const float4*>(hip + u));
+      sl4 = __ldg(reinterpret_cast<const float4*>(slp + u));
+    }
+    const float lo0 = (u & 3) == 0 ? lo4.x : (u & 3) == 1 ? lo4.y : (u & 3) == 2 ? lo4.z : lo4.w;
+    const float hi0 = (u & 3) == 0 ? hi4.x : (u & 3) == 1 ? hi4.y : (u & 3) == 2 ? hi4.z : hi4.w;
+    const float sl0 = (u & 3) == 0 ? sl4.x : (u & 3) == 1 ? sl4.y : (u & 3) == 2 ? sl4.z : sl4.w;
+    const float m = sl0 * onorm, lo_u = lo0 - m, hi_u = hi0 + m;
+    const int c = c0 + u;
+    const int b = q0 + c;
+    const float z = zs[u];
+    const bool on = rv && b < cB;
+    bool eqd = false;
+    if (any_eq) {                                                   // certainly p == 1 == p_target (rare, warp-uniform)
+      eqd = on && z > __ldg(cx.eq + c) + m;
+      const unsigned em = __ballot_sync(0xffffffffu, eqd);
+      if (em) {
+        const int t = __ldg(cx.target + b);
+        const unsigned em2 = __ballot_sync(0xffffffffu, eqd && cx.e_glob != t);
+        const unsigned bm = __ballot_sync(0xffffffffu, eqd && cx.e_glob < t);
+        if (lane == 0) {
+          if (em2) atomicAdd(cx.equal + b, __popc(em2));
+          if (bm) atomicAdd(cx.equal_before + b, __popc(bm));
+        }
+      }
+    }
+    // "greater" as a 4-bit counter per column in this thread's registers: no warp collective in the hot loop;
+    // the cross-lane sums happen once per job (or every 15 tiles), see flush_counts
+    const bool gt = on && z > hi_u;
+    const bool cd = on && !eqd && z >= lo_u && z <= hi_u;
+    out.counts += (gt ? 1u : 0u) << (u * 4);
+    if (cd) {                                                          // rare: recomputed exactly afterwards
+      const int pos = atomicAdd(cx.cand_count, 1);
+      if (pos < cx.cand_cap) cx.cand[pos] = make_int2(cx.e_loc, b);
+    }
+    if (on) {
+      // -log(1 - p) with the reference's fp32 semantics: for z >= 0 through the fp32 probability itself (1 - p
+      // is quantised to multiples of 2^-24 there: up to 0.35 per element near saturation, 2e-4 of a batch's
+      // BCE), p == 1 from z = 24 ln 2 on (BCELoss clamps log(1 - p) at -100); for z < 0 log(1 + e^z)
+      const float en = ex2_fast(-1.4426950408889634f * fabsf(z));
+      const float sden = 1.0f + en;
+      const bool pos = z >= 0.0f;                                      // branch-free: both signs share every warp
+      const float lg = 0.6931471805599453f * lg2_fast(pos ? 1.0f - __frcp_rn(sden) : sden);
+      float sp = pos ? -lg : lg;
+      sp = (!pos && en < 1e-3f) ? en * (1.0f - 0.5f * en) : sp;
+      sp = (pos && z >= 16.635532f) ? 100.0f : sp;
+      out.lsum += sp;
+    }
+  }
+  return out;
+}
+
+// ---- score epilogue of 8 columns (queries) of one thread's row (entity): G[e][b] = dBCE/dz and the BCE itself for
+//      ALL-NEGATIVE targets (t = t_neg), with the reference's fp32 semantics (score_bce.cu: p = 1 / (1 + expf(-z)), log
+//      terms clamped at -100, gradient scaled by p (1 - p) / max(p (1 - p), 1e-12)); the sparse positives are fixed up
+//      afterwards.  Not inlined for the same reason as rank_chunk8 (instruction footprint of 128 unrolled columns). ----
+__device__ __noinline__ float score_chunk8(float* __restrict__ gdst, bool rv, int ncols, float tn, float inv, float z0, float z1,
+                                           float z2, float z3, float z4, float z5, float z6, float z7) {
+  const float zs[8] = {z0, z1, z2, z3, z4, z5, z6, z7};
+  float gv[8];
+  float lsum = 0.0f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float z = zs[u];
+    // three special-function operations per element (ex2, rcp, lg2), BRANCH-FREE (the two signs of z share every warp:
+    // as if / else both sides ran for every element)
+    const float en = ex2_fast(-1.4426950408889634f * fabsf(z));                      // e^-|z|
+    const float sden = 1.0f + en;
+    const float rq = __frcp_rn(sden);                                                 // 1 / (1 + e^-|z|)
+    const bool pos = z >= 0.0f;
+    // z >= 0: p in [0.5, 1] is the fp32 quotient, 1 - p is exact, log(1 - p) from it (p == 1 from z = 24 ln 2 on);
+    // z <  0: p = e^z / (1 + e^z), log(1 - p) = -log(1 + e^z) (series for tiny e^z)
+    const float p = pos ? rq : en * rq;
+    const float lg = 0.6931471805599453f * lg2_fast(pos ? 1.0f - rq : sden);
+    float lq = pos ? lg : -lg;
+    lq = (!pos && en < 1e-3f) ? -(en * (1.0f - 0.5f * en)) : lq;
+    lq = (pos && z >= 16.635532f) ? -100.0f : lq;
+    // log p = log(1 - p) + z (exact identity; its term carries the weight t_neg = ls / N ~ 1e-6 of the loss)
+    const float lp = fmaxf(lq + z, -100.0f);
+    const float pq = (1.0f - p) * p;
+    float g = (p - tn) * inv;
+    if (pq < 1e-12f) g *= pq * 1e12f;
+    const bool on = rv && u < ncols;
+    if (on) lsum -= tn * lp + (1.0f - tn) * lq;
+    gv[u] = on ? g : 0.0f;
+  }
+  if (rv) {
+    *reinterpret_cast<float4*>(gdst) = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    *reinterpret_cast<float4*>(gdst + 4) = make_float4(gv[4], gv[5], gv[6], gv[7]);
+  }
+  return lsum;
+}
+
 // position in this CTA's flattened sequence of (tile, block) pairs
 struct Cursor {
   int tile, job, blk, nblk, kblk0;
@@ -169,8 +296,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "r"(taddr) : "memory");
 }
 
-__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // HC8 = 8-column groups of the accumulator owned by one epilogue warp (rcp / 16): 13 for r = 200, 16 = any rcp <= 256
@@ -285,52 +410,17 @@ apply_tc_kernel(const __grid_constant__ Args a) {
           const float4 e4 = __ldg(reinterpret_cast<const float4*>(eq_p + c4));
           any_eq |= (e4.x < INFINITY) | (e4.y < INFINITY) | (e4.z < INFINITY) | (e4.w < INFINITY);
         }
+        RankChunkCtx cx;
+        cx.lo = lo_p; cx.hi = hi_p; cx.eq = eq_p; cx.slope = a.thr + 3 * Bp + q0; cx.onorm = rv ? __ldg(a.onorms + e_loc) : 0.0f;
+        cx.target = a.target; cx.equal = a.equal; cx.equal_before = a.equal_before;
+        cx.cand = a.cand; cx.cand_count = a.cand_count; cx.cand_cap = a.cand_cap; cx.B = a.B; cx.q0 = q0; cx.e_loc = e_loc;
+        cx.e_glob = e_glob; cx.rv = rv; cx.any_eq = any_eq;
 #pragma unroll
-        for (int c4 = 0; c4 < NACC; c4 += 4) {
-          const float4 lo4 = __ldg(reinterpret_cast<const float4*>(lo_p + c4));       // uniform over the warp
-          const float4 hi4 = __ldg(reinterpret_cast<const float4*>(hi_p + c4));
-          const float los[4] = {lo4.x, lo4.y, lo4.z, lo4.w}, his[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c4 + u;
-            const int b = q0 + c;
-            const float z = acc[c];
-            const bool on = rv && b < a.B;
-            bool eqd = false;
-            if (any_eq) {                                                      // certainly p == 1 == p_target
-              eqd = on && z > __ldg(eq_p + c);
-              const unsigned em = __ballot_sync(0xffffffffu, eqd);
-              if (em) {
-                const int t = __ldg(a.target + b);
-                const unsigned em2 = __ballot_sync(0xffffffffu, eqd && e_glob != t);
-                const unsigned bm = __ballot_sync(0xffffffffu, eqd && e_glob < t);
-                if (lane == 0) {
-                  if (em2) atomicAdd(a.equal + b, __popc(em2));
-                  if (bm) atomicAdd(a.equal_before + b, __popc(bm));
-                }
-              }
-            }
-            // "greater" as a 4-bit counter per column in this thread's registers: no warp collective in the hot loop;
-            // the cross-lane sums happen once per job (or every 15 tiles), see flush_counts
-            const bool gt = on && z > his[u];
-            const bool cd = on && !eqd && z >= los[u] && z <= his[u];
-            cntw[c >> 3] += (gt ? 1u : 0u) << ((c & 7) * 4);
-            if (cd) {                                                          // rare: recomputed exactly afterwards
-              const int pos = atomicAdd(a.cand_count, 1);
-              if (pos < a.cand_cap) a.cand[pos] = make_int2(e_loc, b);
-            }
-            if (on) {
-              // -log(1 - p) with the reference's fp32 semantics: for z >= 0 through the fp32 probability itself (1 - p
-              // is quantised to multiples of 2^-24 there: up to 0.35 per element near saturation, 2e-4 of a batch's
-              // BCE), p == 1 from z = 24 ln 2 on (BCELoss clamps log(1 - p) at -100); for z < 0 log(1 + e^z)
-              const float en = ex2_fast(-1.4426950408889634f * fabsf(z));
-              const float sden = 1.0f + en;
-              float sp;
-              if (z >= 0.0f) sp = (z >= 16.635532f) ? 100.0f : -0.6931471805599453f * lg2_fast(1.0f - __frcp_rn(sden));
-              else sp = en < 1e-3f ? en * (1.0f - 0.5f * en) : 0.6931471805599453f * lg2_fast(sden);
-              lsum += sp;
-            }
-          }
+        for (int c8 = 0; c8 < HC8; ++c8) {
+          const RankChunkOut o = rank_chunk8(cx, c8 * 8, acc[c8 * 8], acc[c8 * 8 + 1], acc[c8 * 8 + 2], acc[c8 * 8 + 3],
+                                             acc[c8 * 8 + 4], acc[c8 * 8 + 5], acc[c8 * 8 + 6], acc[c8 * 8 + 7]);
+          cntw[c8] += o.counts;
+          lsum += o.lsum;
         }
         lacc += (double)lsum;
       } else if (MODE == 2) {
@@ -344,33 +434,9 @@ apply_tc_kernel(const __grid_constant__ Args a) {
         const float tn = a.t_neg, inv = a.inv_count;
         float lsum = 0.0f;
 #pragma unroll
-        for (int c4 = 0; c4 < NACC; c4 += 4) {
-          float gv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float z = acc[c4 + u];
-            // three special-function operations per element (ex2, lg2, rcp): the epilogue is bound by them
-            const float en = ex2_fast(-1.4426950408889634f * fabsf(z));                      // e^-|z|
-            const float sden = 1.0f + en;
-            float p, lq;
-            if (z >= 0.0f) {          // p in [0.5, 1]: the fp32 quotient (1 - p is then exact; p == 1 from z = 24 ln 2 on)
-              p = __frcp_rn(sden);
-              lq = (z >= 16.635532f) ? -100.0f : 0.6931471805599453f * lg2_fast(1.0f - p);
-            } else {                  // log(1 - p) = -log(1 + e^z)
-              p = en * rcp_fast(sden);
-              lq = -(en < 1e-3f ? en * (1.0f - 0.5f * en) : 0.6931471805599453f * lg2_fast(sden));
-            }
-            // log p = log(1 - p) + z (exact identity; its term carries the weight t_neg = ls / N ~ 1e-6 of the loss)
-            const float lp = fmaxf(lq + z, -100.0f);
-            const float pq = (1.0f - p) * p;
-            float g = (p - tn) * inv;
-            if (pq < 1e-12f) g *= pq * 1e12f;
-            const bool on = rv && (q0 + c4 + u) < a.B;
-            if (on) lsum -= tn * lp + (1.0f - tn) * lq;
-            gv[u] = on ? g : 0.0f;
-          }
-          if (rv) *reinterpret_cast<float4*>(grow + c4) = make_float4(gv[0], gv[1], gv[2], gv[3]);
-        }
+        for (int c8 = 0; c8 < HC8; ++c8)
+          lsum += score_chunk8(grow + c8 * 8, rv, a.B - (q0 + c8 * 8), tn, inv, acc[c8 * 8], acc[c8 * 8 + 1], acc[c8 * 8 + 2],
+                               acc[c8 * 8 + 3], acc[c8 * 8 + 4], acc[c8 * 8 + 5], acc[c8 * 8 + 6], acc[c8 * 8 + 7]);
         lacc += (double)lsum;
       } else {
       const int lt = tile - J.tile0, rep = lt / J.tiles_per_rep;
@@ -693,7 +759,8 @@ __device__ __forceinline__ float exact_logit(const float* __restrict__ q, const 
 __device__ __forceinline__ float sigmoid_ref(float z) { return 1.0f / (1.0f + expf(-z)); }
 
 // max_j ||O_j||^2 over the shard (bounds the error of a logit); out is a float bit pattern updated with atomicMax
-__global__ void rank_rownorm_kernel(const float* __restrict__ O, int n_local, int r2, unsigned int* out) {
+__global__ void rank_rownorm_kernel(const float* __restrict__ O, int n_local, int r2, unsigned int* out,
+                                    float* __restrict__ norms) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   float best = 0.0f;
@@ -702,22 +769,30 @@ __global__ void rank_rownorm_kernel(const float* __restrict__ O, int n_local, in
     for (int k = lane; k < r2; k += 32) { const float v = __ldg(O + (int64_t)j * r2 + k); s = fmaf(v, v, s); }
     s = rt::warp_sum(s);
     best = fmaxf(best, s);
+    // an UPPER bound of ||O_j|| (the fp32 sum of squares is off by at most r2 * 2^-24 relative)
+    if (lane == 0) norms[j] = sqrtf(s) * (1.0f + 1e-4f) + 1e-30f;
   }
   if (lane == 0) atomicMax(out, __float_as_uint(best));
 }
 
-// thresholds thr[3][Bp] (lo, hi, eqlo) of every query from p_target; queries >= B get an empty band
+// thresholds thr[4][Bp] of every query from p_target: (lo0, hi0, eqlo0, slope).  The band of entity j is
+// [lo0 - slope * ||O_j||, hi0 + slope * ||O_j||] (eqlo0 + slope * ||O_j|| for the saturated-target test): the error
+// bound of a logit is proportional to ||q_b|| ||O_j|| with the entity's OWN norm -- with the shard maximum the band
+// of every entity was as wide as the heaviest row needs (rows 8x heavier than average after a few hundred steps: the
+// candidate list filled up and the evaluation batch went from 0.9 to 4 ms).  Queries >= B get an empty band.
 __global__ void rank_thresholds_kernel(const float* __restrict__ q, const float* __restrict__ p_target, int B, int Bp,
-                                       int r2, const unsigned int* __restrict__ onorm2, float* __restrict__ thr) {
+                                       int r2, float* __restrict__ thr) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= Bp) return;
-  float lo = INFINITY, hi = INFINITY, eqlo = INFINITY;
+  float lo = INFINITY, hi = INFINITY, eqlo = INFINITY, slope = 0.0f;
   if (b < B) {
     float s = 0.0f;
     for (int k = lane; k < r2; k += 32) { const float v = __ldg(q + (int64_t)b * r2 + k); s = fmaf(v, v, s); }
     s = rt::warp_sum(s);
-    // |z_fp32 - z_tensor| <= (r2 * 2^-24 + 1e-6) * ||q|| ||o||  (fp32 recurrence + 3xTF32); factor 2 of safety
-    const double margin = 2.0 * ((double)r2 * 5.96e-8 + 1e-6) * sqrt((double)s) * sqrt((double)__uint_as_float(*onorm2)) + 1e-6;
+    // |z_fp32 - z_tensor| <= (r2 * 2^-24 + 1e-6) * ||q|| ||o||  (fp32 recurrence + 3xTF32); factor 2 of safety, and
+    // 1e-3 relative for the fp32 evaluation of lo0 - slope * norm in the epilogue
+    slope = (float)(2.0 * ((double)r2 * 5.96e-8 + 1e-6) * sqrt((double)s) * 1.001) + 1e-30f;
+    const double margin = 2e-6;                      // absolute part of the old margin (+ the conversions to fp32)
     const float pt = __ldg(p_target + b);
     if (pt >= 1.0f) {                 // saturated target: nothing is greater; z > 18 certainly gives p == 1
       lo = 15.0f; hi = INFINITY; eqlo = (float)(18.5 + margin);
@@ -729,9 +804,10 @@ __global__ void rank_thresholds_kernel(const float* __restrict__ q, const float*
       lo = plo > 0.0 ? (float)(log(plo / (1.0 - plo)) - margin - 1e-6) : -INFINITY;
       hi = phi < 1.0 ? (float)(log(phi / (1.0 - phi)) + margin + 1e-6) : 19.0f;
       lo = nextafterf(lo, -INFINITY); hi = nextafterf(hi, INFINITY);
+      lo -= 4e-7f * fabsf(lo); hi += 4e-7f * fabsf(hi);        // rounding of lo0 - m, hi0 + m in the epilogue
     }
   }
-  if (lane == 0) { thr[b] = lo; thr[Bp + b] = hi; thr[2 * Bp + b] = eqlo; }
+  if (lane == 0) { thr[b] = lo; thr[Bp + b] = hi; thr[2 * Bp + b] = eqlo; thr[3 * Bp + b] = slope; }
 }
 
 // K images of the query chunks: job j, block kb: element (c, kk) = q[256 j + c][kb * KB + kk]
@@ -815,7 +891,7 @@ __global__ void rank_reset_if_overflow_kernel(int B, int32_t* greater, int32_t* 
   }
 }
 
-struct RankLayout { size_t scal, thr, kimg, cand, total; int cap, nblk, njobs, Bp; };
+struct RankLayout { size_t scal, thr, norms, kimg, cand, total; int cap, nblk, njobs, Bp; };
 RankLayout rank_layout(int B, int n_local, int r2) {
   RankLayout L;
   const Plan p = make_plan(256);
@@ -825,7 +901,8 @@ RankLayout rank_layout(int B, int n_local, int r2) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t at = o; o += rt::align_up(bytes, 256); return at; };
   L.scal = take(256);                                 // [0] cand_count, [1] overflow, [2] max ||O_j||^2, [4..5] loss (double)
-  L.thr = take(sizeof(float) * 3 * L.Bp);
+  L.thr = take(sizeof(float) * 4 * L.Bp);
+  L.norms = take(sizeof(float) * (size_t)(n_local > 0 ? n_local : 1));
   L.kimg = take((size_t)L.njobs * L.nblk * p.kimg_bytes);
   L.cand = take(sizeof(int2) * (size_t)L.cap);
   L.total = o;
@@ -851,9 +928,10 @@ int rank_tc(const float* q, const float* O, int B, int r2, int n_begin, int n_lo
   double* loss = (double*)(base + L.scal + 16);
   float* thr = (float*)(base + L.thr);
   RT_CHECK_CUDA(cudaMemsetAsync(scal, 0, 256, s));
-  rank_rownorm_kernel<<<rt::sm_count() * 4, 256, 0, s>>>(O, n_local, r2, (unsigned int*)(scal + 2));
+  float* onorms = (float*)(base + L.norms);
+  rank_rownorm_kernel<<<rt::sm_count() * 4, 256, 0, s>>>(O, n_local, r2, (unsigned int*)(scal + 2), onorms);
   RT_LAUNCH_CHECK();
-  rank_thresholds_kernel<<<rt::cdiv(L.Bp, 8), 256, 0, s>>>(q, p_target, B, L.Bp, r2, (const unsigned int*)(scal + 2), thr);
+  rank_thresholds_kernel<<<rt::cdiv(L.Bp, 8), 256, 0, s>>>(q, p_target, B, L.Bp, r2, thr);
   RT_LAUNCH_CHECK();
   rank_pack_q_kernel<<<L.njobs * L.nblk, 256, 0, s>>>(q, B, r2, L.nblk, p.rcp, (unsigned char*)(base + L.kimg), p.cs_k,
                                                        p.kimg_bytes);
@@ -874,7 +952,7 @@ int rank_tc(const float* q, const float* O, int B, int r2, int n_begin, int n_lo
 #ifdef RT_APPLY_PROF
   a.debug = getenv("RT_APPLY_DEBUG") ? atoi(getenv("RT_APPLY_DEBUG")) : 0;
 #endif
-  a.thr = thr; a.target = target; a.B = B; a.n_begin = n_begin;
+  a.thr = thr; a.onorms = onorms; a.target = target; a.B = B; a.n_begin = n_begin;
   a.greater = greater; a.equal = equal; a.equal_before = equal_before;
   a.cand = (int2*)(base + L.cand); a.cand_count = scal; a.cand_cap = L.cap; a.loss_sum = loss;
   const int grid = a.ntiles < rt::sm_count() ? a.ntiles : rt::sm_count();
