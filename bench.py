@@ -410,7 +410,7 @@ def time_score_kernel(run, dev, variant, steps, large):
     return out
 
 
-def rooflines(w, n_local, ms_step, stage_ms, score_timing, eval_ms, peaks):
+def rooflines(w, n_local, ms_step, stage_ms, score_timing, eval_ms, peaks, small_flops=None):
     """One entry per kernel family, each with its share of the step."""
     r0, r1, r2 = w["rank"]
     hbm = float(peaks.get("hbm_gbs", 6650.0))
@@ -467,14 +467,22 @@ def rooflines(w, n_local, ms_step, stage_ms, score_timing, eval_ms, peaks):
                     "floor_ms": t_floor_ms, "frac_of_floor": t_floor_ms / ms_c if ms_c > 0 else None}})
     # (c-small) N-independent stage
     sm_keys = ["small_prepare", "small_grad", "small_project", "small_retract_hosvd"]
+    # fp64 tensor-core ceiling measured on this part (tools/dmma_probe.cu, profiles/r02_dmma_probe.txt): DMMA m8n8k4 from
+    # registers 36.4 TFLOP/s; the plain fp64 pipe delivers 2.9
+    DMMA_PEAK_TF = 36.4
+    ms_small = sum(st.get(k, 0.0) for k in sm_keys)
+    ach_s = small_flops / (ms_small * 1e-3) / 1e12 if (small_flops and ms_small > 0) else None
     out.append({"family": "c-small: N-independent fp64 stage (Gram inverses, projection cores, HOSVD subspaces)",
-                "bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None,
-                "ms_per_step": sum(st.get(k, 0.0) for k in sm_keys), "share_of_step": share(sm_keys),
-                "note": "replicated on every rank; persistent DMMA executor + purification kernel: ~47 dependency levels and "
-                        "~85 purification / Newton-Schulz rounds per step, each a grid barrier + one wave of 32 x 32 DMMA tiles. "
-                        "Measured fp64 ceilings of this part (tools/dmma_probe.cu): DMMA 36.4 TFLOP/s, plain DFMA 2.9 TFLOP/s; the "
-                        "stage's GEMM units run at 18-19 TFLOP/s inside their k-loops (L2 operand bandwidth 31.5 B/clk/SM = the "
-                        "DMMA rate for 32 x 32 tiles)"})
+                "bound": "fp64-tensor", "achieved": ach_s, "peak": DMMA_PEAK_TF, "unit": "TFLOP/s",
+                "frac": ach_s / DMMA_PEAK_TF if ach_s else None, "traffic": None,
+                "peak_source": "DMMA m8n8k4 throughput measured on this B200 (tools/dmma_probe.cu; nominal fp64 tensor 40 TFLOP/s)",
+                "algorithmic_flops_per_step": small_flops, "ms_per_step": ms_small, "share_of_step": share(sm_keys),
+                "note": "achieved = fp64 flops of the executor's GEMM operations (2 m n K, half for a symmetric Gram, counted when "
+                        "they are recorded) over the time of the WHOLE stage, which also contains the purification / Newton-Schulz "
+                        "rounds and the Cholesky kernels (their flops are not counted: a lower bound).  Replicated on every rank; "
+                        "~43 dependency levels and ~85 purification rounds per step, each a grid barrier + one wave of 32 x 32 DMMA "
+                        "tiles: the stage is latency-bound, the GEMM units run at 18-19 TFLOP/s inside their k-loops (L2 operand "
+                        "bandwidth 31.5 B/clk/SM = the DMMA rate for 32 x 32 tiles; plain DFMA 2.9 TFLOP/s)"})
     # (a) query contraction
     flops_a = 8.0 * BATCH * r0 * r1 * r2
     ms_a = st.get("query_fwd", 0.0) + st.get("query_bwd", 0.0)
@@ -583,11 +591,13 @@ def main():
         run.one_step(*run.dev_batches[i])
     eng.timers = {}
     l0 = lib().rt_launch_count()
+    f0 = lib().rt_small_flop_count()
     run.barrier()
     for i in range(prof_steps):
         run.one_step(*run.dev_batches[args.warmup + i])
     run.barrier()
     launches_per_step = int(lib().rt_launch_count() - l0) // prof_steps
+    small_flops_per_step = float(lib().rt_small_flop_count() - f0) / prof_steps
     stage_ms = eng.stage_ms()
     eng.timers = None
     launches = launches_per_step * args.steps if launches_eager <= 2 * args.steps else launches_eager
@@ -664,7 +674,7 @@ def main():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(peaks_path)) if os.path.isfile(peaks_path) else {}
     n_local = run.n_end - run.n_begin
-    roof_all = rooflines(w, n_local, ms / args.steps, stage_ms, score_timing, eval_ms, peaks)
+    roof_all = rooflines(w, n_local, ms / args.steps, stage_ms, score_timing, eval_ms, peaks, small_flops_per_step)
     measurable = [r for r in roof_all if r.get("frac") is not None and r.get("share_of_step") is not None]
     dominant = max(measurable, key=lambda r: r["share_of_step"]) if measurable else roof_all[0]
     roofline = {k: dominant.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}

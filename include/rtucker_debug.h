@@ -32,6 +32,11 @@ int rt_bulk_reduce_selftest(const float* a, const float* b, float* out, int n, v
  * (0) or MN-major (1) view; out_dev[0] = cycles to issue, out_dev[1] = cycles until all have completed. */
 int rt_mma_probe(int N, int ksteps, int a_mn, int b_mn, int reps, long long* out_dev, void* stream);
 
+/* fp64 flops (2 m n K per product, half for a symmetric Gram) of all GEMM operations the small stage has recorded in
+ * this process -- host-side count at record time, so it advances on eager launches only (not on CUDA-graph replays).
+ * bench.py divides its increase over the eagerly launched profile steps by the stage time. */
+double rt_small_flop_count(void);
+
 #ifdef __cplusplus
 }
 #endif

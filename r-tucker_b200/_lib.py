@@ -27,6 +27,7 @@ PROTOTYPES = {
     "rt_last_error": (C.c_char_p, []),
     "rt_device_info": (i32, [C.POINTER(i32)] * 3),
     "rt_launch_count": (C.c_ulonglong, []),
+    "rt_small_flop_count": (C.c_double, []),
     "rt_rank_filtered": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "rt_target_prob": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp]),
     "rt_score_rank_ws_bytes": (sz, [i32, i32, i32]),

@@ -5,6 +5,7 @@
 namespace rt {
 static thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+double g_small_flops = 0.0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -24,3 +25,4 @@ extern "C" int rt_device_info(int* sm, int* major, int* minor) {
   return 0;
 }
 extern "C" unsigned long long rt_launch_count(void) { return rt::g_launches; }
+extern "C" double rt_small_flop_count(void) { return rt::g_small_flops; }

@@ -11,6 +11,7 @@ namespace rt {
 
 void set_error(const char* fmt, ...);
 extern unsigned long long g_launches;  // kernels launched by this library in this process
+extern double g_small_flops;           // fp64 flops of the GEMM operations RECORDED by the small stage (host side, eager launches)
 
 #define RT_CHECK_CUDA(expr)                                                            \
   do {                                                                                 \

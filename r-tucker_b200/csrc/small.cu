@@ -199,6 +199,7 @@ struct Ctx {
         }
       }
     }
+    rt::g_small_flops += (sym ? 1.0 : 2.0) * (double)batch * m * n * (double)K1 * K2;   // algorithmic (a Gram: half)
     rec.op.units = tiles * g.ksplit;
     g.thin = (m <= kThinM && K1 == 1 && K2 <= kThinK && batch == 1 && g.ksplit == 1 && n >= 4 * kThinCols) ? 1 : 0;
     if (g.thin) { rec.op.units = cdiv(n, kThinCols); g.sym = 0; }
