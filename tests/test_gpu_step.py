@@ -197,3 +197,47 @@ def test_cuda_graph_replay_is_bitwise_identical_to_eager(cuda_device, sym, beta,
     assert eager == graphed
     for a, b in zip(p_eager, p_graph):
         assert torch.equal(a, b)
+
+
+def test_reorthonormalise_restores_the_factors_without_moving_the_point(cuda_device):
+    """StepEngine.reorthonormalise: one Newton-Schulz polar step on the entity factors, the core absorbs the inverse.
+    Factors with a 1e-2 orthonormality defect come back to ~1e-4 (the defect is squared) and the TENSOR -- gauge-invariant
+    probes -- moves by O(defect^2) only.  (Reference: the QR of [U | dV] inside tucker_riemopt's round keeps the factors
+    orthonormal every step, call site src/model/asymmetric/optim.py:108.)"""
+    from rtucker_b200.engine import StepEngine
+    g = torch.Generator().manual_seed(11)
+    N, M, rank, B = 3000, 12, (6, 64, 48), 64
+    R, S, O = ortho(M, rank[0], g), ortho(N, rank[1], g), ortho(N, rank[2], g)
+    # perturb: S <- S (I + E_S), O <- O (I + E_O) with entries ~ 2e-3
+    S = S @ (torch.eye(rank[1], dtype=f64) + 2e-3 * torch.randn(rank[1], rank[1], generator=g, dtype=f64))
+    O = O @ (torch.eye(rank[2], dtype=f64) + 2e-3 * torch.randn(rank[2], rank[2], generator=g, dtype=f64))
+    core = torch.randn(rank, generator=g, dtype=f64)
+    P = torch.nn.Parameter
+    pc = P(core.float().to(cuda_device))
+    pf = [P(R.float().to(cuda_device)), P(S.float().to(cuda_device)), P(O.float().to(cuda_device))]
+    eng = StepEngine(pc, pf, False, B, 0.8)
+    a = torch.randn(40, M, generator=g, dtype=f64)
+    b = torch.randn(40, N, generator=g, dtype=f64)
+    c = torch.randn(40, N, generator=g, dtype=f64)
+
+    def probe():
+        return torch.einsum("aij,na,ni,nj->n", pc.data.double().cpu(), a @ pf[0].data.double().cpu(),
+                            b @ pf[1].data.double().cpu(), c @ pf[2].data.double().cpu())
+
+    def defect(k):
+        U = pf[k].data.double().cpu()
+        return float((U.T @ U - torch.eye(U.shape[1], dtype=f64)).abs().max())
+    before, d1, d2 = probe(), defect(1), defect(2)
+    assert d1 > 3e-3 and d2 > 3e-3
+    eng.reorthonormalise()
+    torch.cuda.synchronize()
+    after = probe()
+    e1, e2 = defect(1), defect(2)
+    assert e1 < 0.1 * d1 and e2 < 0.1 * d2, (d1, e1, d2, e2)          # the defect is squared (x n from the matrix product)
+    rel = float((after - before).norm() / before.norm())
+    assert rel < 2e-3, rel            # second order in the defect (first order would be ~2e-2)
+    eng.reorthonormalise()            # quadratic convergence: a second pass reaches the fp32 level
+    torch.cuda.synchronize()
+    assert defect(1) < 1e-5 and defect(2) < 1e-5, (defect(1), defect(2))
+    rel2 = float((probe() - before).norm() / before.norm())
+    assert rel2 < 2e-3, rel2

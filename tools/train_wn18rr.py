@@ -107,6 +107,13 @@ def main():
             vm, vl = T.evaluate(model, crit, val_loader)
             tm, tl = T.evaluate(model, crit, test_loader)
             torch.cuda.synchronize()
+            # orthonormality of the factors (the retraction assumes U^T U = I and never re-orthonormalises): max |U^T U - I|
+            defect = {}
+            for name, prm in model.named_parameters():
+                if prm.dim() == 2:
+                    U = prm.data.double()
+                    defect[name] = float((U.T @ U - torch.eye(U.shape[1], dtype=U.dtype, device=U.device)).abs().max())
+            rec.update(ortho_defect=defect)
             rec.update(eval_s=time.perf_counter() - t0, val_loss=float(vl), test_loss=float(tl),
                        **{"val_" + k: v for k, v in vm.items()}, **{"test_" + k: v for k, v in tm.items()})
         if not (args.recipe == "head" and epoch >= args.total_epochs):
