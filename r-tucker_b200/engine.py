@@ -383,11 +383,20 @@ class StepEngine:
                     ops.apply(out, None, None, [(ct, Kinv)])
                     core.copy_(out.view(r0, r2, r1).permute(0, 2, 1))
             if self.beta is not None and self.has_old and self.M_next[k] is not None:
-                self.M_next[k].copy_(K @ self.M_next[k])
+                # M <- K M = M - (G - I) M / 2 with this library's Gram kernel (A^T B, exact products, fp64 sums): the
+                # correction term is second-order small, its fp32 operands cost nothing; no cuBLAS on the path (its lazy
+                # initialisation inside a timed step was measured as a 120 ms one-off)
+                D32 = (G - eye).to(f32).contiguous()              # symmetric: D^T = D
+                M32 = self.M_next[k].to(f32).contiguous()
+                self.M_next[k].sub_(0.5 * ops.gram(D32, M32, precise=True))
 
     def _after_step(self):
         self._steps_done += 1
-        if self.reorth_every > 0 and self._steps_done % self.reorth_every == 0 and self.ops is cuda_ops:
+        # also right after the very first step of an engine: numerically a no-op on freshly orthonormalised factors, it
+        # takes the one-off costs of the maintenance path (lazy kernel loading, allocator growth) out of steady state
+        first = self._steps_done == 1 and not getattr(self, "_reorth_warm", False)
+        if self.reorth_every > 0 and (first or self._steps_done % self.reorth_every == 0) and self.ops is cuda_ops:
+            self._reorth_warm = True
             self.reorthonormalise()
 
     # -------------------------------------------------------------------------------------------
